@@ -1,0 +1,23 @@
+"""CPU oracle for the alabi surrogate hot path.  TEST INFRASTRUCTURE ONLY.
+
+This package is a plain NumPy/SciPy FP64 restatement of the algorithms the
+reference (jbirky/alabi, mounted at /root/reference) runs on its hot path.
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import it.  Nothing under
+``alabi_b200/`` imports it and the product path fails loudly when the CUDA
+library is missing.
+
+Parity status
+-------------
+* ``oracle.utility`` (BAPE / AGP / Jones, ``logsubexp``, ``lnprior_uniform``,
+  ``prior_transform_uniform``, ``regularization_term/gradient``,
+  ``estimate_burnin``) and ``oracle.benchmarks`` are PINNED: they are checked
+  in ``tests/test_oracle_golden.py`` against vectors produced by importing the
+  reference's own pure-NumPy functions (``tests/golden/make_golden.py``).
+* ``oracle.gp`` (george 0.4.x semantics) and ``oracle.emcee`` (emcee 3.x
+  stretch move) restate third-party packages that are NOT vendored in
+  /root/reference and are not installed in the build image (no network):
+  **parity unpinned** for these two modules.  They are anchored on the
+  reference's call sites (cited per function) and on self-consistency checks
+  (finite differences, closed forms, detailed balance); see DESIGN.md.
+"""
