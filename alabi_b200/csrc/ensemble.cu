@@ -1,0 +1,313 @@
+// K5: emcee-compatible ensemble stretch-move sampler, fully on device.
+//
+// Replaces emcee.EnsembleSampler.run_mcmc over SurrogateModel.lnprob
+// (alabi/core.py:2073-2100, 2319-2325): the red/blue stretch move, every
+// walker's surrogate log-probability (uniform prior box + GP predictive mean,
+// K3 mean-only) and the accept/reject step run inside ONE persistent
+// cooperative kernel; the two dependent half-updates of a step are separated
+// by a grid barrier, never by a host round trip.
+//
+// Work decomposition: a "unit" (1, 2, 4 or 8 warps) evaluates two proposals at
+// a time; its lanes stride over the training points (SoA in shared memory,
+// resident for the whole run when they fit), proposals sit in registers.
+//
+// Random numbers: Philox4x32-10 keyed by the seed, counter = (global walker id,
+// step, stream, 0) — restated on the CPU in oracle/philox.py so a device chain
+// can be replayed exactly.  The red/blue split flips one fair coin per walker
+// pair (2i, 2i+1): balanced, position independent, no compaction needed.
+#include "handle.h"
+#include "alabi_b200.h"
+
+namespace {
+
+constexpr int EW = 8;            // warps per CTA
+constexpr int ETHREADS = EW * 32;
+
+struct EnsArgs {
+    // state and outputs
+    double* coords; double* logp; long long* naccept;
+    double* chain; double* logp_chain; double* rec_q; double* rec_lp;
+    unsigned long long* barrier; int* nan_flag;
+    // surrogate
+    const double* XsT; const double* alpha; long long n, npad;
+    KernParams kp; double mean;
+    // sampler configuration
+    int nwalkers, d, nsteps, thin_by, init_logp, randomize_split, ws, ch;
+    double a;
+    unsigned seed_lo, seed_hi;
+    long long first_step, walker_offset;
+    double lo[AB_MAX_DIM], hi[AB_MAX_DIM], t_scale[AB_MAX_DIM], t_off[AB_MAX_DIM];
+    int y_kind; double y_scale, y_off;
+};
+
+struct U4 { unsigned x, y, z, w; };
+
+__device__ __forceinline__ U4 philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return U4{c0, c1, c2, c3};
+}
+__device__ __forceinline__ double u53(unsigned hi, unsigned lo) {
+    return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) / 9007199254740992.0;
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1ULL);
+        while (*((volatile unsigned long long*)counter) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// walker of pair i that belongs to set s at this step
+__device__ __forceinline__ int member_of(const EnsArgs& A, int i, int s, unsigned step_lo) {
+    int bit = 0;
+    if (A.randomize_split && 2 * i + 1 < A.nwalkers)
+        bit = philox4x32_10((unsigned)(A.walker_offset + 2 * i), step_lo, AB_STREAM_SPLIT, 0, A.seed_lo, A.seed_hi).x & 1u;
+    return 2 * i + (bit ^ s);
+}
+
+template <int KIND, int D>
+__global__ void __launch_bounds__(ETHREADS)
+ensemble_kernel(const __grid_constant__ EnsArgs A) {
+    extern __shared__ __align__(16) double sm[];
+    const int CH = A.ch;
+    double* sX = sm;                 // [D][CH]
+    double* sAl = sm + D * CH;       // [CH]
+    __shared__ double sQ[EW][2][D], sQs[EW][2][D];
+    __shared__ double sPart[EW][2], sLogZ[EW][2], sLogU[EW][2];
+    __shared__ int sW[EW][2], sInside[EW][2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int WS = A.ws, G = EW / WS;
+    const int unit = warp / WS, wiu = warp - unit * WS;
+    const int d = A.d, nw = A.nwalkers;
+    const bool resident = A.n <= CH;
+    unsigned long long bar_target = 0;
+
+    auto load_chunk = [&](long long c0) {
+        int cn = (int)((A.n - c0 < CH) ? (A.n - c0) : CH);
+        for (int idx = tid; idx < D * CH; idx += ETHREADS) {
+            int k = idx / CH, jj = idx - k * CH;
+            sX[idx] = (k < d && jj < cn) ? A.XsT[(long long)k * A.npad + c0 + jj] : 0.0;
+        }
+        for (int jj = tid; jj < CH; jj += ETHREADS) sAl[jj] = (jj < cn) ? A.alpha[c0 + jj] : 0.0;
+    };
+    if (resident) { load_chunk(0); __syncthreads(); }
+
+    const int first = A.init_logp ? -1 : 0;
+    for (int step = first; step < A.nsteps; step++) {
+        const unsigned step_lo = (unsigned)(A.first_step + (step < 0 ? 0 : step));
+        const int nsplit = (step < 0) ? 1 : 2;
+        for (int split = 0; split < nsplit; split++) {
+            const int n_items = (step < 0) ? nw : (split == 0 ? (nw + 1) / 2 : nw / 2);
+            const int n_other = (split == 0) ? nw / 2 : (nw + 1) / 2;
+            const int nbatch = (n_items + 2 * G - 1) / (2 * G);
+            for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
+                // ---- proposal (lanes 0/1 of the unit's first warp) -------------
+                if (wiu == 0 && lane < 2) {
+                    const int e = lane, item = (b * G + unit) * 2 + e;
+                    int w = -1, inside = 1;
+                    double logz = 0.0, logu = 0.0;
+                    if (item < n_items) {
+                        if (step < 0) {
+                            w = item;
+                            for (int k = 0; k < d; k++) sQ[unit][e][k] = __ldcg(&A.coords[(long long)w * d + k]);
+                        } else {
+                            w = member_of(A, item, split, step_lo);
+                            if (n_other > 0) {
+                                const unsigned gw = (unsigned)(A.walker_offset + w);
+                                U4 rp = philox4x32_10(gw, step_lo, AB_STREAM_PARTNER, 0, A.seed_lo, A.seed_hi);
+                                int jj = (int)__umulhi(rp.x, (unsigned)n_other);
+                                int partner = member_of(A, jj, 1 - split, step_lo);
+                                U4 rm = philox4x32_10(gw, step_lo, AB_STREAM_MOVE, 0, A.seed_lo, A.seed_hi);
+                                double uz = u53(rm.x, rm.y), ua = u53(rm.z, rm.w);
+                                double tz = __dadd_rn(__dmul_rn(A.a - 1.0, uz), 1.0);
+                                double zz = __ddiv_rn(__dmul_rn(tz, tz), A.a);
+                                logz = (d - 1.0) * log(zz);
+                                logu = log(ua);
+                                for (int k = 0; k < d; k++) {
+                                    double c = __ldcg(&A.coords[(long long)partner * d + k]);
+                                    double s = __ldcg(&A.coords[(long long)w * d + k]);
+                                    sQ[unit][e][k] = __dsub_rn(c, __dmul_rn(__dsub_rn(c, s), zz));
+                                }
+                            } else {
+                                inside = -1;     // no complementary walker: keep the state
+                                for (int k = 0; k < d; k++) sQ[unit][e][k] = __ldcg(&A.coords[(long long)w * d + k]);
+                            }
+                        }
+                        for (int k = 0; k < d; k++) {
+                            double q = sQ[unit][e][k];
+                            if (inside >= 0 && !((q > A.lo[k]) && (q < A.hi[k]))) inside = 0;
+                            sQs[unit][e][k] = fma(q, A.t_scale[k], A.t_off[k]) * A.kp.inv_len[k];
+                        }
+                    }
+                    for (int k = (w < 0 ? 0 : d); k < D; k++) { sQ[unit][e][k] = 0.0; sQs[unit][e][k] = 0.0; }
+                    sW[unit][e] = w; sInside[unit][e] = inside; sLogZ[unit][e] = logz; sLogU[unit][e] = logu;
+                }
+                __syncthreads();
+                // ---- surrogate mean of the two proposals of this unit ------------
+                double q0[D], q1[D];
+#pragma unroll
+                for (int k = 0; k < D; k++) { q0[k] = sQs[unit][0][k]; q1[k] = sQs[unit][1][k]; }
+                double acc0 = 0.0, acc1 = 0.0;
+                for (long long c0 = 0; c0 < A.n; c0 += CH) {
+                    if (!resident) { __syncthreads(); load_chunk(c0); __syncthreads(); }
+                    const int cn = (int)((A.n - c0 < CH) ? (A.n - c0) : CH);
+                    for (int jj = wiu * 32 + lane; jj < cn; jj += 32 * WS) {
+                        double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+                        for (int k = 0; k < D; k++) {
+                            double x = sX[k * CH + jj];
+                            double d0 = q0[k] - x, d1 = q1[k] - x;
+                            r0 = fma(d0, d0, r0);
+                            r1 = fma(d1, d1, r1);
+                        }
+                        const double al = sAl[jj];
+                        acc0 = fma(ab_radial<KIND>(r0), al, acc0);
+                        acc1 = fma(ab_radial<KIND>(r1), al, acc1);
+                    }
+                }
+                acc0 = ab_warp_sum(acc0);
+                acc1 = ab_warp_sum(acc1);
+                if (lane == 0) { sPart[warp][0] = acc0; sPart[warp][1] = acc1; }
+                __syncthreads();
+                // ---- accept / reject ------------------------------------------------
+                if (wiu == 0 && lane < 2) {
+                    const int e = lane, w = sW[unit][e];
+                    if (w >= 0) {
+                        double s = 0.0;
+                        for (int x = 0; x < WS; x++) s += sPart[unit * WS + x][e];
+                        double ys = fma(A.kp.amp, s, A.mean);
+                        double y = (A.y_kind == 0) ? fma(ys, A.y_scale, A.y_off)
+                                 : (A.y_kind == 1) ? -pow(10.0, ys) : pow(10.0, ys);
+                        const int inside = sInside[unit][e];
+                        double lp_q = (inside == 1) ? y : -INFINITY;
+                        if (inside == 1 && isnan(y)) atomicExch(A.nan_flag, 1);
+                        if (step < 0) {
+                            A.logp[w] = lp_q;
+                        } else {
+                            double lp_s = __ldcg(&A.logp[w]);
+                            bool acc = (inside >= 0) && ((sLogZ[unit][e] + lp_q - lp_s) > sLogU[unit][e]);
+                            if (acc) {
+                                for (int k = 0; k < d; k++) A.coords[(long long)w * d + k] = sQ[unit][e][k];
+                                A.logp[w] = lp_q;
+                                A.naccept[w] += 1;
+                                lp_s = lp_q;
+                            }
+                            if (A.rec_q && inside >= 0) {
+                                long long r = (long long)step * nw + w;
+                                for (int k = 0; k < d; k++) A.rec_q[r * d + k] = sQ[unit][e][k];
+                                A.rec_lp[r] = lp_q;
+                            }
+                            if (A.chain && (step + 1) % A.thin_by == 0) {
+                                long long r = (long long)((step + 1) / A.thin_by - 1) * nw + w;
+                                for (int k = 0; k < d; k++)
+                                    A.chain[r * d + k] = acc ? sQ[unit][e][k] : __ldcg(&A.coords[(long long)w * d + k]);
+                                A.logp_chain[r] = lp_s;
+                            }
+                        }
+                    }
+                }
+            }
+            grid_barrier(A.barrier, bar_target);
+        }
+    }
+}
+
+template <int KIND, int D>
+int launch_ens(ab_gp* h, EnsArgs& A, int nunits_half) {
+    auto kern = ensemble_kernel<KIND, D>;
+    // shared memory: resident when the whole training set fits, else chunks
+    const size_t budget = 160 * 1024;
+    long long need = (long long)A.n * (D + 1) * 8;
+    int ch;
+    if ((size_t)need <= budget) ch = (int)((A.n + 31) / 32 * 32);
+    else { ch = (int)(64 * 1024 / ((D + 1) * 8)); ch = ch / 32 * 32; }
+    if (ch < 32) ch = 32;
+    A.ch = ch;
+    size_t smem = (size_t)ch * (D + 1) * 8;
+    AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, nsm = 0;
+    AB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ETHREADS, smem));
+    AB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
+    if (per_sm < 1) { ab_set_error("ensemble kernel does not fit on an SM (smem %zu)", smem); return -3; }
+    int G = EW / A.ws;
+    int nbatch = (nunits_half + G - 1) / G;
+    int grid = per_sm * nsm;
+    if (grid > nbatch) grid = nbatch;
+    if (grid < 1) grid = 1;
+    void* args[] = {(void*)&A};
+    AB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(ETHREADS), args, smem, h->stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int ab_ensemble_run(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords, double* d_logp,
+                               long long* d_naccept, double* d_chain, double* d_logp_chain, double* d_rec_q,
+                               double* d_rec_lp) {
+    if (!h || !cfg) { ab_set_error("null argument"); return -1; }
+    if (!h->have_alpha) { ab_set_error("ab_ensemble_run: targets not set (call ab_gp_set_targets)"); return -2; }
+    if (cfg->nwalkers < 2 || cfg->nsteps < 0 || cfg->thin_by < 1) { ab_set_error("bad ensemble configuration"); return -1; }
+    AB_CUDA(cudaSetDevice(h->device));
+    int rc = ab_ensure_scratch(h, 64);
+    if (rc) return rc;
+    EnsArgs A{};
+    A.coords = d_coords; A.logp = d_logp; A.naccept = d_naccept;
+    A.chain = d_chain; A.logp_chain = d_logp_chain; A.rec_q = d_rec_q; A.rec_lp = d_rec_lp;
+    A.barrier = reinterpret_cast<unsigned long long*>(h->scratch);
+    A.nan_flag = reinterpret_cast<int*>(h->scratch + 1);
+    AB_CUDA(cudaMemsetAsync(h->scratch, 0, 16, h->stream));
+    A.XsT = h->XsT; A.alpha = h->alpha; A.n = h->n; A.npad = h->npad; A.kp = h->kp; A.mean = h->mean;
+    A.nwalkers = cfg->nwalkers; A.d = h->d; A.nsteps = cfg->nsteps; A.thin_by = cfg->thin_by;
+    A.init_logp = cfg->init_logp; A.randomize_split = cfg->randomize_split; A.a = cfg->a;
+    A.seed_lo = (unsigned)(cfg->seed & 0xffffffffULL); A.seed_hi = (unsigned)(cfg->seed >> 32);
+    A.first_step = cfg->first_step; A.walker_offset = cfg->walker_offset;
+    for (int k = 0; k < h->d; k++) {
+        A.lo[k] = cfg->lo[k]; A.hi[k] = cfg->hi[k];
+        A.t_scale[k] = cfg->theta_scale[k]; A.t_off[k] = cfg->theta_offset[k];
+    }
+    A.y_kind = cfg->y_kind; A.y_scale = cfg->y_scale; A.y_off = cfg->y_offset;
+    // warps per unit: aim at >= 8 warps per SM
+    int units_half = ((cfg->nwalkers + 1) / 2 + 1) / 2;
+    if (cfg->init_logp && cfg->nsteps == 0) units_half = (cfg->nwalkers + 1) / 2;
+    int ws = 1;
+    if (cfg->warps_per_unit > 0) ws = cfg->warps_per_unit;
+    else {
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+        while (ws < EW && units_half * ws * 2 <= nsm * EW) ws *= 2;
+    }
+    if (ws != 1 && ws != 2 && ws != 4 && ws != 8) { ab_set_error("warps_per_unit must be 1, 2, 4 or 8"); return -1; }
+    A.ws = ws;
+    const int d = h->d;
+#define AB_ENS(DD) AB_DISPATCH_KIND(h->kp.kind, rc = (launch_ens<KIND, DD>(h, A, units_half)))
+    if (d <= 2) AB_ENS(2);
+    else if (d <= 4) AB_ENS(4);
+    else if (d <= 8) AB_ENS(8);
+    else if (d <= 12) AB_ENS(12);
+    else if (d <= 16) AB_ENS(16);
+    else if (d <= 20) AB_ENS(20);
+    else if (d <= 24) AB_ENS(24);
+    else AB_ENS(32);
+#undef AB_ENS
+    if (rc) return rc;
+    AB_CUDA(cudaMemcpyAsync(h->h_pinned, h->scratch, 16, cudaMemcpyDeviceToHost, h->stream));
+    AB_CUDA(cudaStreamSynchronize(h->stream));
+    if (reinterpret_cast<int*>(h->h_pinned + 1)[0] != 0) {
+        ab_set_error("Probability function returned NaN");
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,324 @@
+// K3: batched GP prediction over M query points, and K4: fused acquisition
+// utilities + argmin.
+//
+// Replaces george GP.predict(y, X*, return_var) as alabi calls it
+// (alabi/core.py:85,95,1441,1486,1601,1812) and the per-point scipy loops over
+// bape/agp/jones_utility (alabi/utility.py:629-946, core.py:1587-1667).
+//
+//   mean      mu_q = amp * sum_j k(x*_q, x_j) alpha_j + mean.  The cross
+//             covariance is built on the fly: training points are staged in
+//             shared memory, every thread keeps two query points in registers.
+//   variance  sigma^2_q = amp - | L^-1 k*_q |^2.  Pass 1 also stores the cross
+//             covariance panel P[j][q] (query index contiguous, coalesced);
+//             pass 2 is a DMMA GEMM  L^-1 (N x N, lower) x P (N x 128)  per CTA
+//             whose epilogue squares and column-reduces the product in
+//             registers; nothing but sigma^2 is written back.  White noise is
+//             not added (george semantics).
+#include <float.h>
+#include "handle.h"
+#include "dmma_gemm.cuh"
+
+namespace {
+
+constexpr int NB = AB_NB;
+constexpr int TS = 128;        // training points per shared-memory tile
+constexpr int QPB = 256;       // queries per CTA (128 threads x 2)
+
+template <int KIND, int D, bool STORE>
+__global__ void __launch_bounds__(128)
+predict_mean_kernel(const double* __restrict__ Xq, int64_t m, int64_t q_off, const double* __restrict__ Xs,
+                    const double* __restrict__ alpha, int64_t n, int64_t npad, KernParams kp, double mean,
+                    double* __restrict__ mu, double* __restrict__ P, int64_t ldp, int nsplit,
+                    double* __restrict__ partial) {
+    __shared__ __align__(16) double sX[TS * D];
+    __shared__ double sAl[TS];
+    const int tid = threadIdx.x, d = kp.d;
+    const int64_t qa = (int64_t)blockIdx.x * QPB + tid, qb = qa + 128;   // local to this panel
+    double xa[D], xb[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        xa[k] = (k < d && q_off + qa < m) ? Xq[(q_off + qa) * d + k] * kp.inv_len[k] : 0.0;
+        xb[k] = (k < d && q_off + qb < m) ? Xq[(q_off + qb) * d + k] * kp.inv_len[k] : 0.0;
+    }
+    // training range of this split
+    int64_t jbeg = 0, jend = STORE ? npad : n;
+    if (nsplit > 1) {
+        int64_t per = ((n + nsplit - 1) / nsplit + TS - 1) / TS * TS;
+        jbeg = (int64_t)blockIdx.y * per;
+        jend = jbeg + per < n ? jbeg + per : n;
+    }
+    double ma = 0.0, mb = 0.0;
+    for (int64_t j0 = jbeg; j0 < jend; j0 += TS) {
+        __syncthreads();
+        for (int idx = tid; idx < TS * D; idx += 128) {
+            int jj = idx / D, k = idx - jj * D;
+            sX[idx] = (k < d && j0 + jj < npad) ? Xs[(j0 + jj) * d + k] : 0.0;
+        }
+        if (tid < TS) sAl[tid] = (j0 + tid < n) ? alpha[j0 + tid] : 0.0;
+        __syncthreads();
+        const int tn = (int)((jend - j0 < TS) ? (jend - j0) : TS);
+        for (int jj = 0; jj < tn; jj++) {
+            double ra = 0.0, rb = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; k += 2) {
+                double2 x = *reinterpret_cast<const double2*>(&sX[jj * D + k]);
+                double da0 = xa[k] - x.x, da1 = xa[k + 1] - x.y;
+                double db0 = xb[k] - x.x, db1 = xb[k + 1] - x.y;
+                ra = fma(da0, da0, ra); ra = fma(da1, da1, ra);
+                rb = fma(db0, db0, rb); rb = fma(db1, db1, rb);
+            }
+            double ka = ab_radial<KIND>(ra), kb = ab_radial<KIND>(rb);
+            const double al = sAl[jj];
+            ma = fma(ka, al, ma);
+            mb = fma(kb, al, mb);
+            if (STORE) {
+                const bool valid = (j0 + jj) < n;
+                P[(j0 + jj) * ldp + qa] = valid ? kp.amp * ka : 0.0;
+                P[(j0 + jj) * ldp + qb] = valid ? kp.amp * kb : 0.0;
+            }
+        }
+    }
+    if (nsplit > 1) {
+        if (q_off + qa < m) partial[(int64_t)blockIdx.y * m + q_off + qa] = ma;
+        if (q_off + qb < m) partial[(int64_t)blockIdx.y * m + q_off + qb] = mb;
+    } else {
+        if (q_off + qa < m) mu[q_off + qa] = fma(kp.amp, ma, mean);
+        if (q_off + qb < m) mu[q_off + qb] = fma(kp.amp, mb, mean);
+    }
+}
+
+__global__ void combine_splits_kernel(const double* __restrict__ partial, int64_t m, int nsplit, double amp,
+                                      double mean, double* __restrict__ mu) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    double s = 0.0;
+    for (int p = 0; p < nsplit; p++) s += partial[(int64_t)p * m + q];
+    mu[q] = fma(amp, s, mean);
+}
+
+// sigma^2 for the 128 queries of this CTA:  amp - sum_i ( sum_k Linv[i][k] P[k][q] )^2
+__global__ void __launch_bounds__(abg::THREADS, 1)
+predict_var_kernel(const double* __restrict__ Linv, int64_t ld, int T, const double* __restrict__ P, int64_t ldp,
+                   int64_t m, int64_t q_off, double amp, double* __restrict__ var) {
+    extern __shared__ __align__(16) double smem[];
+    const double* Bp = P + (int64_t)blockIdx.x * abg::BN;
+    double ss[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; j++) ss[j][0] = ss[j][1] = 0.0;
+    for (int i = 0; i < T; i++) {
+        abg::Acc acc;
+        acc.zero();
+        abg::mainloop<true, false>(acc, Linv + (int64_t)i * NB * ld, ld, Bp, ldp, (i + 1) * (NB / abg::BK), smem);
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                ss[j][0] = fma(acc.v[a][j][0], acc.v[a][j][0], ss[j][0]);
+                ss[j][1] = fma(acc.v[a][j][1], acc.v[a][j][1], ss[j][1]);
+            }
+    }
+    // reduce over the 8 groupIDs of the warp, then over the two warps sharing the columns
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            double v = ss[j][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            ss[j][e] = v;
+        }
+    double* red = smem;          // [2][128]
+    if (lane < 4) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) red[(warp >> 2) * 128 + (warp & 3) * 32 + j * 8 + lane * 2 + e] = ss[j][e];
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        int64_t q = q_off + (int64_t)blockIdx.x * abg::BN + threadIdx.x;
+        if (q < m) var[q] = amp - (red[threadIdx.x] + red[128 + threadIdx.x]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4 utilities.  Expression order follows the reference exactly
+// (alabi/utility.py:489-504, 696, 804, 926-939).
+// ---------------------------------------------------------------------------
+struct UtilParams {
+    int kind, d;                  // 0 bape, 1 agp, 2 jones
+    double y_best, zeta;
+    double lo[AB_MAX_DIM], hi[AB_MAX_DIM];
+};
+
+__device__ __forceinline__ double utility_value(const UtilParams& up, double mu, double var) {
+    if (up.kind == 0) {
+        double lse = (var <= 0.0) ? -INFINITY : var + log(1.0 - exp(0.0 - var));
+        return -((2.0 * mu + var) + lse);
+    }
+    if (up.kind == 1) return -(mu + 0.5 * log(2.0 * 3.141592653589793 * 2.718281828459045 * var));
+    double sd = sqrt(var);
+    if (!(sd > 0.0)) return 0.0;
+    double dd = mu - up.y_best - up.zeta;
+    double z = dd / sd;
+    double cdf = 0.5 * erfc(-z * 0.7071067811865476);
+    double pdf = exp(-(z * z) / 2.0) / 2.5066282746310002;
+    return -(dd * cdf + sd * pdf);
+}
+
+__global__ void __launch_bounds__(256)
+utility_kernel(const double* __restrict__ Xq, const double* __restrict__ mu, const double* __restrict__ var,
+               int64_t m, UtilParams up, double* __restrict__ util, double* __restrict__ bval,
+               long long* __restrict__ bidx) {
+    __shared__ double sv[8];
+    __shared__ long long si[8];
+    int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    double u = INFINITY;
+    if (q < m) {
+        bool inside = true;
+        for (int k = 0; k < up.d; k++) {
+            double x = Xq[q * up.d + k];
+            inside = inside && (x > up.lo[k]) && (x < up.hi[k]);     // strict, like lnprior_uniform
+        }
+        u = inside ? utility_value(up, mu[q], var[q]) : INFINITY;
+        if (util) util[q] = u;
+    }
+    // argmin over finite values, lowest index on ties
+    double bv = (q < m && isfinite(u)) ? u : INFINITY;
+    long long bi = (q < m && isfinite(u)) ? (long long)q : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++)
+            if (si[w] >= 0 && (bi < 0 || sv[w] < bv || (sv[w] == bv && si[w] < bi))) { bv = sv[w]; bi = si[w]; }
+        bval[blockIdx.x] = bv;
+        bidx[blockIdx.x] = bi;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+argmin_final_kernel(const double* __restrict__ bval, const long long* __restrict__ bidx, int nb,
+                    double* __restrict__ out_val, long long* __restrict__ out_idx) {
+    __shared__ double sv[256];
+    __shared__ long long si[256];
+    double bv = INFINITY;
+    long long bi = -1;
+    for (int p = threadIdx.x; p < nb; p += 256) {
+        double ov = bval[p];
+        long long oi = bidx[p];
+        if (oi >= 0 && (bi < 0 || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    sv[threadIdx.x] = bv;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 256; w++)
+            if (si[w] >= 0 && (bi < 0 || sv[w] < bv || (sv[w] == bv && si[w] < bi))) { bv = sv[w]; bi = si[w]; }
+        *out_val = bv;
+        *out_idx = bi;
+    }
+}
+
+template <int KIND, bool STORE>
+int launch_mean(ab_gp* h, int Dp, dim3 grid, const double* Xq, int64_t m, int64_t q_off, double* mu, double* P,
+                int64_t ldp, int nsplit, double* partial) {
+#define AB_PM(DD)                                                                                              \
+    predict_mean_kernel<KIND, DD, STORE><<<grid, 128, 0, h->stream>>>(Xq, m, q_off, h->Xs, h->alpha, h->n, h->npad, \
+                                                                      h->kp, h->mean, mu, P, ldp, nsplit, partial)
+    if (Dp <= 2) AB_PM(2);
+    else if (Dp <= 4) AB_PM(4);
+    else if (Dp <= 8) AB_PM(8);
+    else if (Dp <= 12) AB_PM(12);
+    else if (Dp <= 16) AB_PM(16);
+    else if (Dp <= 20) AB_PM(20);
+    else if (Dp <= 24) AB_PM(24);
+    else AB_PM(32);
+#undef AB_PM
+    AB_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+// queries per variance panel: one wave of CTAs (148 SMs x 128 queries)
+static const int64_t kPanelQueries = 148 * 128;
+
+int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double* var) {
+    if (m <= 0) return 0;
+    cudaStream_t s = h->stream;
+    const int d = h->d;
+    if (!var) {
+        int64_t nblk = (m + QPB - 1) / QPB;
+        int nsplit = 1;
+        if (nblk < 296) {
+            int64_t want = (296 + nblk - 1) / nblk, maxs = (h->n + TS - 1) / TS;
+            nsplit = (int)(want < maxs ? want : maxs);
+            if (nsplit < 1) nsplit = 1;
+        }
+        double* partial = nullptr;
+        if (nsplit > 1) {
+            int rc = ab_ensure_scratch(h, (size_t)nsplit * m * sizeof(double));
+            if (rc) return rc;
+            partial = h->scratch;
+        }
+        dim3 grid((unsigned)nblk, (unsigned)nsplit);
+        int rc = 0;
+        AB_DISPATCH_KIND(h->kp.kind, rc = (launch_mean<KIND, false>(h, d, grid, Xq, m, 0, mu, nullptr, 0, nsplit, partial)));
+        if (rc) return rc;
+        if (nsplit > 1) {
+            combine_splits_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(partial, m, nsplit, h->kp.amp, h->mean, mu);
+            AB_CHECK_LAUNCH();
+        }
+        return 0;
+    }
+    // mean + variance, processed in panels of at most kPanelQueries queries
+    AB_CUDA(cudaFuncSetAttribute(predict_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));
+    const int T = (int)(h->npad / NB);
+    int64_t mq = m < kPanelQueries ? m : kPanelQueries;
+    int64_t ldp = (mq + QPB - 1) / QPB * QPB;                 // multiple of 256 (and of 128)
+    int rc = ab_ensure_scratch(h, (size_t)h->npad * ldp * sizeof(double));
+    if (rc) return rc;
+    double* P = h->scratch;
+    for (int64_t q0 = 0; q0 < m; q0 += mq) {
+        int64_t cnt = (m - q0 < mq) ? (m - q0) : mq;
+        dim3 grid((unsigned)((cnt + QPB - 1) / QPB), 1);
+        AB_DISPATCH_KIND(h->kp.kind, rc = (launch_mean<KIND, true>(h, d, grid, Xq, m, q0, mu, P, ldp, 1, nullptr)));
+        if (rc) return rc;
+        predict_var_kernel<<<(unsigned)((cnt + abg::BN - 1) / abg::BN), abg::THREADS, abg::SMEM_BYTES, s>>>(
+            h->Linv, h->npad, T, P, ldp, m, q0, h->kp.amp, var);
+        AB_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+int ab_launch_utility(ab_gp* h, int kind, const double* Xq, const double* mu, const double* var, int64_t m,
+                      const double* h_bounds, double y_best, double zeta, double* util, int64_t* h_argmin,
+                      double* h_min) {
+    UtilParams up;
+    up.kind = kind;
+    up.d = h->d;
+    up.y_best = y_best;
+    up.zeta = zeta;
+    for (int k = 0; k < h->d; k++) { up.lo[k] = h_bounds[2 * k]; up.hi[k] = h_bounds[2 * k + 1]; }
+    int nb = (int)((m + 255) / 256);
+    int rc = ab_ensure_scratch(h, (size_t)nb * 16 + 64);
+    if (rc) return rc;
+    double* bval = h->scratch + 8;
+    long long* bidx = reinterpret_cast<long long*>(h->scratch + 8 + nb);
+    utility_kernel<<<nb, 256, 0, h->stream>>>(Xq, mu, var, m, up, util, bval, bidx);
+    argmin_final_kernel<<<1, 256, 0, h->stream>>>(bval, bidx, nb, h->scratch, reinterpret_cast<long long*>(h->scratch + 1));
+    AB_CHECK_LAUNCH();
+    AB_CUDA(cudaMemcpyAsync(h->h_pinned, h->scratch, 16, cudaMemcpyDeviceToHost, h->stream));
+    AB_CUDA(cudaStreamSynchronize(h->stream));
+    *h_min = h->h_pinned[0];
+    *h_argmin = (int64_t) * reinterpret_cast<long long*>(h->h_pinned + 1);
+    return 0;
+}

@@ -1,0 +1,198 @@
+"""emcee.EnsembleSampler look-alike running the stretch move on the GPU (K5).
+
+Mirrors the protocol alabi uses (alabi/core.py:2319-2387, alabi/mcmc_utils.py:45):
+``EnsembleSampler(nwalkers, ndim, log_prob_fn, pool=None, **kw)``,
+``run_mcmc(p0, nsteps, progress=True)``, ``get_chain(discard, thin, flat)``,
+``get_last_sample().coords``, ``acceptance_fraction``, ``get_autocorr_time``.
+
+``log_prob_fn`` must be a :class:`SurrogateLogProb` (GP predictive mean +
+uniform prior box, i.e. ``SurrogateModel.lnprob`` of alabi/core.py:2073-2100):
+the whole step then runs on the device with no host round trip.  A plain
+Python callable cannot be evaluated inside a CUDA kernel; it is rejected
+instead of silently falling back to a CPU sampler.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .mcmc_utils import integrated_time
+
+__all__ = ["EnsembleSampler", "SurrogateLogProb", "State"]
+
+
+class State:
+    def __init__(self, coords, log_prob=None, random_state=None):
+        self.coords = np.array(coords, dtype=np.float64)
+        self.log_prob = None if log_prob is None else np.array(log_prob, dtype=np.float64)
+        self.blobs = None
+        self.random_state = random_state
+
+    def __iter__(self):
+        return iter((self.coords, self.log_prob, self.random_state))
+
+
+class SurrogateLogProb:
+    """ln P(theta) = GP mean(theta_scaler(theta)) mapped back by the y scaler,
+    plus a uniform prior on the open box ``bounds`` (unscaled theta).
+
+    theta_scaled = theta * theta_scale + theta_offset;
+    y = ys * y_scale + y_offset (y_kind 0), -10**ys (1) or 10**ys (2)."""
+
+    def __init__(self, gp, y, bounds, theta_scale=None, theta_offset=None, y_kind=0, y_scale=1.0, y_offset=0.0):
+        self.gp = gp
+        self.y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+        self.bounds = np.asarray(bounds, dtype=np.float64).reshape(-1, 2)
+        d = len(self.bounds)
+        self.theta_scale = np.ones(d) if theta_scale is None else np.asarray(theta_scale, dtype=np.float64).reshape(d)
+        self.theta_offset = np.zeros(d) if theta_offset is None else np.asarray(theta_offset, dtype=np.float64).reshape(d)
+        self.y_kind, self.y_scale, self.y_offset = int(y_kind), float(y_scale), float(y_offset)
+
+    def __call__(self, theta):
+        """Host-callable form (one device predict per call) for callers that
+        need a Python function, e.g. a nested sampler's likelihood."""
+        theta = np.asarray(theta, dtype=np.float64)
+        one = theta.ndim == 1
+        t = np.atleast_2d(theta)
+        ys = self.gp.predict(self.y, t * self.theta_scale + self.theta_offset, return_cov=False)
+        yv = ys * self.y_scale + self.y_offset if self.y_kind == 0 else (-10.0 ** ys if self.y_kind == 1 else 10.0 ** ys)
+        inside = np.all((t > self.bounds[:, 0]) & (t < self.bounds[:, 1]), axis=1)
+        lp = np.where(inside, yv, -np.inf)
+        return lp[0] if one else lp
+
+
+class EnsembleSampler:
+    def __init__(self, nwalkers, ndim, log_prob_fn, pool=None, moves=None, args=None, kwargs=None,
+                 backend=None, vectorize=False, blobs_dtype=None, parameter_names=None, a=2.0, seed=None,
+                 randomize_split=True, live_dangerously=False, warps_per_unit=0):
+        if not isinstance(log_prob_fn, SurrogateLogProb):
+            raise TypeError("alabi_b200.EnsembleSampler runs on the GPU and needs a SurrogateLogProb "
+                            "(GP surrogate + uniform prior); arbitrary Python log-probabilities are not supported")
+        if moves is not None:
+            raise NotImplementedError("only the default StretchMove(a) is implemented")
+        self.nwalkers, self.ndim = int(nwalkers), int(ndim)
+        if self.nwalkers < 2 * self.ndim and not live_dangerously:
+            raise ValueError("It is unadvisable to use a red-blue move with fewer walkers than twice the number of dimensions.")
+        if ndim != len(log_prob_fn.bounds):
+            raise ValueError("ndim does not match the surrogate's bounds")
+        self.log_prob_fn = log_prob_fn
+        self.a = float(a)
+        self.seed = int(np.random.SeedSequence().entropy % (2 ** 63)) if seed is None else int(seed)
+        self.randomize_split = bool(randomize_split)
+        self.warps_per_unit = int(warps_per_unit)
+        self.reset()
+
+    def reset(self):
+        self.iteration = 0
+        self._chain = np.empty((0, self.nwalkers, self.ndim))
+        self._log_prob = np.empty((0, self.nwalkers))
+        self._naccepted = np.zeros(self.nwalkers, dtype=np.int64)
+        self._last = None
+        self._step_counter = 0
+        self.last_run_device_seconds = None
+
+    # ------------------------------------------------------------------------------------
+    def _config(self, nsteps, thin_by, init_logp, walker_offset=0):
+        lp = self.log_prob_fn
+        cfg = _lib.EnsembleConfig()
+        cfg.nwalkers, cfg.nsteps, cfg.thin_by = self.nwalkers, int(nsteps), int(thin_by)
+        cfg.init_logp, cfg.randomize_split = int(init_logp), int(self.randomize_split)
+        cfg.warps_per_unit, cfg.y_kind = self.warps_per_unit, lp.y_kind
+        cfg.a, cfg.seed = self.a, self.seed
+        cfg.first_step, cfg.walker_offset = self._step_counter, int(walker_offset)
+        cfg.y_scale, cfg.y_offset = lp.y_scale, lp.y_offset
+        for k in range(self.ndim):
+            cfg.lo[k], cfg.hi[k] = lp.bounds[k, 0], lp.bounds[k, 1]
+            cfg.theta_scale[k], cfg.theta_offset[k] = lp.theta_scale[k], lp.theta_offset[k]
+        return cfg
+
+    def run_mcmc(self, initial_state, nsteps, progress=False, thin_by=1, store=True, record_proposals=False,
+                 walker_offset=0, **kwargs):
+        """Run ``nsteps * thin_by`` ensemble steps on the device, storing every
+        ``thin_by``-th.  Returns the final :class:`State`."""
+        import torch
+        gp = self.log_prob_fn.gp
+        gp.recompute()
+        gp._set_targets(self.log_prob_fn.y)
+        hd = gp._hd
+        dev = f"cuda:{hd.device}"
+        if initial_state is None:
+            if self._last is None:
+                raise ValueError("Cannot have `initial_state=None` if run_mcmc has never been called.")
+            initial_state = self._last
+        have_lp = isinstance(initial_state, State) and initial_state.log_prob is not None
+        p0 = initial_state.coords if isinstance(initial_state, State) else np.asarray(initial_state, dtype=np.float64)
+        if p0.shape != (self.nwalkers, self.ndim):
+            raise ValueError("incompatible input dimensions")
+        if not np.all(np.isfinite(p0)):
+            raise ValueError("At least one parameter value was infinite or NaN")
+        if self.nwalkers > 1 and np.linalg.matrix_rank(p0 - p0.mean(axis=0)) < min(self.ndim, self.nwalkers - 1):
+            raise ValueError("Initial state has a large condition number. Make sure that your walkers are linearly independent for the best performance")
+        total = int(nsteps) * int(thin_by)
+        coords = torch.from_numpy(np.ascontiguousarray(p0)).to(dev)
+        logp = torch.from_numpy(np.ascontiguousarray(initial_state.log_prob)).to(dev) if have_lp \
+            else torch.empty(self.nwalkers, dtype=torch.float64, device=dev)
+        nacc = torch.zeros(self.nwalkers, dtype=torch.int64, device=dev)
+        chain = torch.empty((int(nsteps), self.nwalkers, self.ndim), dtype=torch.float64, device=dev) if store else None
+        lpc = torch.empty((int(nsteps), self.nwalkers), dtype=torch.float64, device=dev) if store else None
+        rq = torch.full((total, self.nwalkers, self.ndim), float("nan"), dtype=torch.float64, device=dev) if record_proposals else None
+        rl = torch.full((total, self.nwalkers), float("nan"), dtype=torch.float64, device=dev) if record_proposals else None
+        cfg = self._config(total, thin_by, not have_lp, walker_offset)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(hd.stream)
+        rc = _lib.check(hd.lib.ab_ensemble_run(hd.h, ctypes.byref(cfg), _lib.ptr(coords), _lib.ptr(logp), _lib.ptr(nacc),
+                                               _lib.ptr(chain), _lib.ptr(lpc), _lib.ptr(rq), _lib.ptr(rl)),
+                        "ab_ensemble_run")
+        t1.record(hd.stream)
+        t1.synchronize()
+        self.last_run_device_seconds = t0.elapsed_time(t1) * 1e-3
+        if rc == 1:
+            raise ValueError("Probability function returned NaN")
+        self._step_counter += total
+        self._naccepted += nacc.cpu().numpy()
+        if store:
+            self._chain = np.concatenate([self._chain, chain.cpu().numpy()])
+            self._log_prob = np.concatenate([self._log_prob, lpc.cpu().numpy()])
+            self.iteration += int(nsteps)
+        if record_proposals:
+            self.proposal_record = (rq.cpu().numpy(), rl.cpu().numpy())
+        self._last = State(coords.cpu().numpy(), logp.cpu().numpy())
+        return self._last
+
+    def sample(self, initial_state, iterations=1, **kwargs):
+        for _ in range(int(iterations)):
+            yield self.run_mcmc(initial_state, 1, **kwargs)
+            initial_state = None
+
+    # ------------------------------------------------------------------------------------
+    def get_chain(self, discard=0, thin=1, flat=False):
+        v = self._chain[discard + thin - 1:self.iteration:thin]
+        return v.reshape(-1, self.ndim) if flat else v
+
+    def get_log_prob(self, discard=0, thin=1, flat=False):
+        v = self._log_prob[discard + thin - 1:self.iteration:thin]
+        return v.reshape(-1) if flat else v
+
+    def get_last_sample(self):
+        if self._last is None:
+            raise AttributeError("you must run the sampler before accessing the results")
+        return self._last
+
+    @property
+    def chain(self):
+        return np.swapaxes(self.get_chain(), 0, 1)
+
+    @property
+    def flatchain(self):
+        return self.get_chain(flat=True)
+
+    @property
+    def lnprobability(self):
+        return np.swapaxes(self.get_log_prob(), 0, 1)
+
+    @property
+    def acceptance_fraction(self):
+        return self._naccepted / max(float(self._step_counter), 1.0)
+
+    def get_autocorr_time(self, discard=0, thin=1, **kwargs):
+        return thin * integrated_time(self.get_chain(discard=discard, thin=thin), **kwargs)

@@ -1,0 +1,150 @@
+/* alabi_b200 — C ABI of the B200-native GP surrogate hot path.
+ *
+ * The reference (jbirky/alabi) has no FFI layer: the seam is the object
+ * protocol it consumes from george / emcee.  Every entry point
+ * below names the reference call it replaces.  A maintainer binds this library
+ * with ctypes (INTEGRATION.md shows the stub); alabi_b200/_lib.py is that
+ * binding and alabi_b200/gp.py / ensemble.py mirror the george / emcee objects
+ * on top of it.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller (a
+ *     torch tensor's data_ptr()); h_* is a host pointer; FP64, row-major,
+ *     C-contiguous.
+ *   - a handle is bound to one device and one stream (the caller's, borrowed),
+ *     is not re-entrant, and owns K / L / L^-1 / K^-1 / alpha workspaces.
+ *   - return value: 0 = ok; > 0 = numerical status (factorisation: 1-based index
+ *     of the first non-positive pivot, LAPACK dpotrf style; sampler: 1 = NaN
+ *     log-probability); < 0 = bad argument or CUDA error, text in
+ *     ab_last_error().  Nothing throws or exits across the ABI.
+ *   - hyper-parameters follow george's vector
+ *       [mean:value, white_noise:value, kernel:k1:log_constant,
+ *        kernel:k2:metric:log_M_0_0, ...]        (docs/source/save_reload.py:117-120)
+ *     but are passed unpacked; white_noise is ln(variance), log_M is ln(l^2).
+ */
+#ifndef ALABI_B200_H
+#define ALABI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB_MAX_DIM_PUBLIC 32
+
+/* kernel ids: george.kernels.{ExpSquared,Matern32,Matern52}Kernel, alabi/core.py:998-1014 */
+#define AB_KERNEL_EXPSQUARED 0
+#define AB_KERNEL_MATERN32 1
+#define AB_KERNEL_MATERN52 2
+
+/* utility ids: alabi/utility.py:729 (bape), :629 (agp), :853 (jones) */
+#define AB_UTILITY_BAPE 0
+#define AB_UTILITY_AGP 1
+#define AB_UTILITY_JONES 2
+
+/* Philox counter streams of the sampler (restated in oracle/philox.py) */
+#define AB_STREAM_SPLIT 0
+#define AB_STREAM_PARTNER 1
+#define AB_STREAM_MOVE 2
+
+typedef struct ab_gp ab_gp;
+
+int ab_version(void);
+const char* ab_last_error(void);
+/* multiprocessor count of `device`, < 0 on error (also proves a usable GPU) */
+int ab_device_sm_count(int device);
+
+/* ---- lifecycle: george.GP(kernel, fit_mean, mean, white_noise, fit_white_noise)
+ *      alabi/gp_utils.py:233, alabi/core.py:1141 ------------------------------- */
+int ab_gp_create(ab_gp** out, int device, void* cuda_stream);
+int ab_gp_destroy(ab_gp* h);
+int ab_gp_set_lookahead(ab_gp* h, int enabled);
+
+/* training inputs of gp.compute(x): X is n x d (copied).  alabi/gp_utils.py:243 */
+int ab_gp_set_inputs(ab_gp* h, const double* d_X, int64_t n, int d);
+
+/* kernel id + unpacked george parameter vector (gp.set_parameter_vector,
+ * alabi/core.py:705,1152).  amp = exp(log_constant) (1.0 without amplitude);
+ * h_log_M has d entries; yerr2 is george's yerr^2 (0 in alabi). Marks the
+ * factorisation dirty. */
+int ab_gp_set_kernel(ab_gp* h, int kernel_id, double amp, const double* h_log_M, double mean,
+                     double white_noise, double yerr2);
+
+/* K1: kernel.get_value(x) [+ diagonal]: full symmetric n x n matrix into d_K
+ * (ld = n).  with_diag != 0 adds yerr2 + exp(white_noise) like GP.compute. */
+int ab_gp_build_cov(ab_gp* h, double* d_K, int with_diag);
+/* kernel.get_value(x1, x2) (alabi/utility.py:549-550,607): m1 x m2 into d_K */
+int ab_gp_cross_cov(ab_gp* h, const double* d_X1, int64_t m1, const double* d_X2, int64_t m2, double* d_K);
+
+/* K1 + K2: gp.compute / gp.recompute — build K, Cholesky.  Returns 0 or the
+ * 1-based index of the first non-positive pivot (george raises LinAlgError;
+ * quiet=True callers map it to -inf / zero gradient). */
+int ab_gp_factor(ab_gp* h);
+int ab_gp_log_determinant(ab_gp* h, double* h_out);
+
+/* alpha = K^-1 (y - mean) (george GP._compute_alpha); d_y has n entries. */
+int ab_gp_set_targets(ab_gp* h, const double* d_y);
+/* gp.log_likelihood(y): -1/2 r^T K^-1 r - 1/2 logdet - n/2 ln 2pi.  alabi/core.py:1248 */
+int ab_gp_log_likelihood(ab_gp* h, const double* d_y, double* h_out);
+/* gp.grad_log_likelihood(y): h_out[0..d+2] = d/d[mean, white_noise, log_constant,
+ * log_M_0..]; the caller drops frozen entries.  alabi/core.py:1261 */
+int ab_gp_grad_log_likelihood(ab_gp* h, const double* d_y, double* h_out);
+
+/* K3: gp.predict(y, t, return_var).  d_var may be NULL (mean only).
+ * alabi/core.py:85,95,1441,1486,1601 */
+int ab_gp_predict(ab_gp* h, const double* d_Xq, int64_t m, double* d_mu, double* d_var);
+/* same with HOST buffers (pageable or pinned): copies in, predicts, copies out */
+int ab_gp_predict_host(ab_gp* h, const double* h_Xq, int64_t m, double* h_mu, double* h_var);
+
+/* K4: bape/agp/jones utility over a candidate batch + argmin over the finite
+ * values (lowest index on ties; -1 if none).  h_bounds = d pairs (lo, hi) in
+ * the same (scaled) space as the candidates; d_util may be NULL.
+ * Replaces the scipy restarts of find_next_point, alabi/core.py:1587-1667. */
+int ab_gp_utility_argmin(ab_gp* h, int utility_id, const double* d_Xq, int64_t m, const double* h_bounds,
+                         double y_best, double zeta, double* d_util, int64_t* h_argmin, double* h_min);
+/* elementwise utility from given mean / variance (no GP evaluation) */
+int ab_utility_eval(ab_gp* h, int utility_id, const double* d_Xq, const double* d_mu, const double* d_var,
+                    int64_t m, const double* h_bounds, double y_best, double zeta, double* d_util,
+                    int64_t* h_argmin, double* h_min);
+
+/* factor / solver state export and import (broadcast L and alpha to other
+ * GPUs; gp._alpha, gp.solver.get_inverse() — alabi/utility.py:577-610) */
+int64_t ab_gp_padded_size(ab_gp* h);
+int ab_gp_get_factor(ab_gp* h, double* d_L /* npad x npad */);
+int ab_gp_get_alpha(ab_gp* h, double* d_alpha /* n */);
+int ab_gp_get_inverse(ab_gp* h, double* d_Kinv /* n x n, full symmetric */);
+int ab_gp_import_state(ab_gp* h, const double* d_L /* npad x npad */, const double* d_alpha /* n */);
+
+/* K5: emcee.EnsembleSampler(...).run_mcmc over lnprob = surrogate mean + uniform
+ * prior (alabi/core.py:2073-2100, 2319-2325). */
+typedef struct ab_ensemble_config {
+    int nwalkers;
+    int nsteps;            /* ensemble steps to run in this call */
+    int thin_by;           /* store every thin_by-th step (>= 1) */
+    int init_logp;         /* 1: evaluate log-prob of d_coords first */
+    int randomize_split;   /* 1: coin per walker pair, 0: parity split */
+    int warps_per_unit;    /* 0 = auto, else 1/2/4/8 */
+    int y_kind;            /* y = ys*y_scale + y_offset (0), -10^ys (1), 10^ys (2) */
+    int reserved;
+    double a;              /* stretch scale (emcee default 2.0) */
+    uint64_t seed;
+    int64_t first_step;    /* step counter of the first step (continuing chains) */
+    int64_t walker_offset; /* global id of walker 0 (sub-ensembles on other GPUs) */
+    double y_scale, y_offset;
+    double lo[AB_MAX_DIM_PUBLIC], hi[AB_MAX_DIM_PUBLIC];                    /* prior box, unscaled theta */
+    double theta_scale[AB_MAX_DIM_PUBLIC], theta_offset[AB_MAX_DIM_PUBLIC]; /* theta_scaled = theta*scale + offset */
+} ab_ensemble_config;
+
+/* d_coords (nwalkers x d) and d_logp (nwalkers) are in/out state; d_naccept is
+ * accumulated.  d_chain ((nsteps/thin_by) x nwalkers x d) and d_logp_chain may
+ * be NULL, as may the proposal record d_rec_q (nsteps x nwalkers x d) /
+ * d_rec_lp (nsteps x nwalkers) used by the parity tests. */
+int ab_ensemble_run(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords, double* d_logp,
+                    long long* d_naccept, double* d_chain, double* d_logp_chain, double* d_rec_q,
+                    double* d_rec_lp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -41,53 +41,52 @@ def u53(hi, lo):
     return (a * 67108864.0 + b) / 9007199254740992.0
 
 
-STREAM_SPLIT = 0      # c2 value: set membership bit
-STREAM_PARTNER = 1    # c2 value: partner candidates, c3 = attempt block
+STREAM_SPLIT = 0      # c2 value: coin of walker pair (2i, 2i+1), counter c0 = id of walker 2i
+STREAM_PARTNER = 1    # c2 value: partner draw of a walker
 STREAM_MOVE = 2       # c2 value: z-uniform (words 0,1) and accept-uniform (words 2,3)
-MAX_PARTNER_BLOCKS = 16
+
+
+def pair_bits(seed, nwalkers, step, randomize_split=True, walker_offset=0):
+    """Coin of every walker pair (2i, 2i+1); an unpaired last walker gets 0."""
+    npair = (nwalkers + 1) // 2
+    bits = np.zeros(npair, dtype=np.int64)
+    if randomize_split:
+        i = np.arange(npair, dtype=np.uint64)
+        r = philox4x32(np.uint64(walker_offset) + np.uint64(2) * i, step, STREAM_SPLIT, 0,
+                       seed & 0xFFFFFFFF, seed >> 32)
+        bits = (r[0] & np.uint32(1)).astype(np.int64)
+        if nwalkers % 2:
+            bits[-1] = 0
+    return bits
 
 
 def split_sets(seed, nwalkers, step, randomize_split=True, walker_offset=0):
     """Set id (0/1) of every walker at ``step``.
 
     randomize_split=False: emcee's ``arange(nwalkers) % 2``.
-    randomize_split=True : independent fair coin per (walker, step) —
-    a position-independent random partition (valid for the red-blue move;
-    emcee shuffles a balanced label vector instead)."""
-    w = np.arange(nwalkers, dtype=np.uint64)
-    if not randomize_split:
-        return (w % np.uint64(2)).astype(np.int64)
-    r = philox4x32(w + np.uint64(walker_offset), step, STREAM_SPLIT, 0,
-                   seed & 0xFFFFFFFF, seed >> 32)
-    return (r[0] & np.uint32(1)).astype(np.int64)
+    randomize_split=True : one fair coin per walker pair decides which of
+    (2i, 2i+1) is red — a balanced, position-independent random partition
+    (emcee shuffles a balanced label vector instead)."""
+    bits = pair_bits(seed, nwalkers, step, randomize_split, walker_offset)
+    w = np.arange(nwalkers)
+    return (bits[w // 2] ^ (w & 1)).astype(np.int64)
 
 
 def move_draws(seed, nwalkers, step, randomize_split=True, walker_offset=0):
     """All random draws of one ensemble step, exactly as the device makes them.
 
     Returns dict(sets, partner, u_z, u_acc): ``partner[w]`` is the LOCAL index
-    of the complementary walker drawn for walker w (-1 if none could be drawn:
-    empty complement), ``u_z`` the uniform behind z, ``u_acc`` the accept
-    uniform."""
+    of the complementary walker drawn for walker w, ``u_z`` the uniform behind
+    z, ``u_acc`` the accept uniform."""
     k0, k1 = seed & 0xFFFFFFFF, seed >> 32
-    sets = split_sets(seed, nwalkers, step, randomize_split, walker_offset)
-    w = np.arange(nwalkers, dtype=np.uint64) + np.uint64(walker_offset)
-    partner = np.full(nwalkers, -1, dtype=np.int64)
-    if randomize_split:
-        todo = np.ones(nwalkers, dtype=bool)
-        for blk in range(MAX_PARTNER_BLOCKS):
-            if not todo.any():
-                break
-            r = philox4x32(w, step, STREAM_PARTNER, blk, k0, k1)
-            for word in r:
-                cand = ((word.astype(np.uint64) * np.uint64(nwalkers)) >> np.uint64(32)).astype(np.int64)
-                ok = todo & (sets[cand] != sets)
-                partner[ok] = cand[ok]
-                todo &= ~ok
-    else:
-        r = philox4x32(w, step, STREAM_PARTNER, 0, k0, k1)
-        n_other = np.where(sets == 0, nwalkers // 2, (nwalkers + 1) // 2)
-        j = ((r[0].astype(np.uint64) * n_other.astype(np.uint64)) >> np.uint64(32)).astype(np.int64)
-        partner = np.where(n_other > 0, 2 * j + (1 - sets), -1)
+    bits = pair_bits(seed, nwalkers, step, randomize_split, walker_offset)
+    wl = np.arange(nwalkers)
+    sets = (bits[wl // 2] ^ (wl & 1)).astype(np.int64)
+    w = wl.astype(np.uint64) + np.uint64(walker_offset)
+    r = philox4x32(w, step, STREAM_PARTNER, 0, k0, k1)
+    n_other = np.where(sets == 0, nwalkers // 2, (nwalkers + 1) // 2)
+    jj = ((r[0].astype(np.uint64) * n_other.astype(np.uint64)) >> np.uint64(32)).astype(np.int64)
+    partner = 2 * jj + (bits[np.minimum(jj, len(bits) - 1)] ^ (1 - sets))
+    partner = np.where(n_other > 0, partner, -1)
     r = philox4x32(w, step, STREAM_MOVE, 0, k0, k1)
     return dict(sets=sets, partner=partner, u_z=u53(r[0], r[1]), u_acc=u53(r[2], r[3]))

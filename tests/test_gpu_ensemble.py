@@ -1,0 +1,104 @@
+"""GPU parity for K5: the device stretch-move chain replayed on the CPU from
+the same Philox draws (oracle/philox.py + oracle/emcee.py), per-proposal
+log-probabilities against the oracle GP, and posterior consistency (KS)."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from oracle import gp as ogp, emcee as oem
+
+pytestmark = pytest.mark.gpu
+
+
+def surrogate(kind, n, d, seed, bounds):
+    import alabi_b200 as ab
+    from alabi_b200.ensemble import SurrogateLogProb
+    rng = np.random.default_rng(seed)
+    b = np.asarray(bounds, dtype=np.float64)
+    X = rng.uniform(b[:, 0], b[:, 1], size=(n, d))
+    y = -0.5 * np.sum((X / 0.7) ** 2, axis=1)          # Gaussian log-density, sigma = 0.7
+    log_M = np.full(d, 1.0)
+    o = ogp.make_gp(kind, X, y, log_M, amp=np.var(y), white_noise=-8.0)
+    k = getattr(ab.kernels, kind)(metric=np.exp(log_M), ndim=d) * np.var(y)
+    g = ab.GP(kernel=k, fit_mean=True, mean=np.median(y), white_noise=-8.0, fit_white_noise=True)
+    g.compute(X)
+    lp = SurrogateLogProb(g, y, b)
+
+    def lp_oracle(q):
+        q = np.atleast_2d(q)
+        inside = np.all((q > b[:, 0]) & (q < b[:, 1]), axis=1)
+        return np.where(inside, o.predict(y, q), -np.inf)
+    return g, lp, lp_oracle, rng, b
+
+
+@pytest.mark.parametrize("kind,n,d,nw,rs,wpu", [("ExpSquaredKernel", 200, 2, 32, True, 0),
+                                                ("Matern32Kernel", 300, 3, 41, False, 1),
+                                                ("Matern52Kernel", 700, 5, 64, True, 2),
+                                                ("ExpSquaredKernel", 150, 2, 10, True, 8)])
+def test_chain_replay_and_per_proposal_logp(kind, n, d, nw, rs, wpu):
+    from alabi_b200.ensemble import EnsembleSampler
+    bounds = [(-2.0, 2.0)] * d
+    g, lp, lp_oracle, rng, b = surrogate(kind, n, d, 17, bounds)
+    p0 = rng.uniform(-1.9, 1.9, size=(nw, d))
+    nsteps, seed = 60, 987654321987
+    s = EnsembleSampler(nw, d, lp, seed=seed, randomize_split=rs, warps_per_unit=wpu, live_dangerously=True)
+    s.run_mcmc(p0, nsteps, record_proposals=True)
+    chain, lps, nacc, rec = oem.replay_device_chain(p0, lp_oracle, nsteps, seed, randomize_split=rs)
+    rq, rl = s.proposal_record
+    # (1) given the same proposals the log-probabilities are identical to 1e-9
+    n_checked = 0
+    for t in range(nsteps):
+        ok = np.isfinite(rq[t, :, 0])
+        lo = lp_oracle(rq[t, ok])
+        fin = np.isfinite(lo)
+        assert np.array_equal(np.isfinite(rl[t, ok]), fin)
+        np.testing.assert_allclose(rl[t, ok][fin], lo[fin], rtol=1e-9, atol=1e-9)
+        n_checked += ok.sum()
+    assert n_checked == nsteps * nw
+    # (2) the whole chain replays (same draws, same accept decisions)
+    np.testing.assert_allclose(s.get_chain(), chain, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(s.get_log_prob(), lps, rtol=1e-9, atol=1e-9)
+    assert np.array_equal(s._naccepted, nacc)
+    np.testing.assert_allclose(rq[5][np.isfinite(rq[5, :, 0])], rec[5]["q"][np.isfinite(rec[5]["q"][:, 0])], rtol=1e-12)
+    # continuing the run keeps the counter-based stream going
+    s.run_mcmc(None, 5)
+    chain2, _, _, _ = oem.replay_device_chain(p0, lp_oracle, nsteps + 5, seed, randomize_split=rs)
+    np.testing.assert_allclose(s.get_chain()[-1], chain2[-1], rtol=1e-9, atol=1e-12)
+
+
+def test_posterior_moments_ks_and_api():
+    from alabi_b200.ensemble import EnsembleSampler
+    from alabi_b200.mcmc_utils import estimate_burnin
+    d, nw = 2, 200
+    g, lp, lp_oracle, rng, b = surrogate("ExpSquaredKernel", 400, d, 3, [(-3.0, 3.0)] * d)
+    s = EnsembleSampler(nw, d, lp, seed=42)
+    st = s.run_mcmc(rng.uniform(-1, 1, size=(nw, d)), 1500, progress=True)
+    assert st.coords.shape == (nw, d) and s.get_chain().shape == (1500, nw, d)
+    burn, thin = estimate_burnin(s)
+    tau = s.get_autocorr_time(tol=0)
+    assert 1 < tau.max() < 100 and 0.2 < s.acceptance_fraction.mean() < 0.9
+    flat = s.get_chain(discard=max(burn, 100), thin=int(2 * tau.max()) + 1, flat=True)
+    # the surrogate interpolates a N(0, 0.7^2 I) log-density
+    assert abs(flat.mean()) < 0.05 and abs(flat.std() - 0.7) < 0.05
+    assert stats.kstest(flat[:, 0] / 0.7, "norm").pvalue > 1e-4
+    # CPU emcee-order sampler on the oracle surrogate gives the same moments
+    ref = oem.StretchEnsemble(40, d, lp_oracle, seed=1, vectorize=True)
+    ref.run_mcmc(rng.uniform(-1, 1, size=(40, d)), 1500)
+    rflat = ref.get_chain(discard=300, thin=10, flat=True)
+    assert stats.ks_2samp(flat[::3, 1], rflat[:, 1]).pvalue > 1e-4
+    # thin_by stores every k-th step only
+    s2 = EnsembleSampler(nw, d, lp, seed=42)
+    s2.run_mcmc(s.get_chain()[0], 10, thin_by=3)
+    assert s2.get_chain().shape == (10, nw, d) and s2._step_counter == 30
+
+
+def test_large_nonresident_training_set():
+    """N too large for shared memory: the chunked path gives the same chain."""
+    from alabi_b200.ensemble import EnsembleSampler
+    d, nw = 12, 96
+    g, lp, lp_oracle, rng, b = surrogate("ExpSquaredKernel", 2600, d, 9, [(-2.0, 2.0)] * d)
+    p0 = rng.uniform(-1, 1, size=(nw, d))
+    s = EnsembleSampler(nw, d, lp, seed=5)
+    s.run_mcmc(p0, 12)
+    chain, lps, nacc, _ = oem.replay_device_chain(p0, lp_oracle, 12, 5)
+    np.testing.assert_allclose(s.get_chain(), chain, rtol=1e-9, atol=1e-12)

@@ -1,0 +1,153 @@
+"""GPU parity: K1 covariance, K2 Cholesky / logL / gradient, K3 predict, K4
+utilities against the CPU oracle on identical seeded inputs (through the
+C ABI via alabi_b200.GP).  Tolerances follow north_star: 1e-9 relative in FP64
+on well-conditioned problems."""
+import numpy as np
+import pytest
+
+from oracle import gp as ogp, utility as ou, benchmarks as ob
+
+pytestmark = pytest.mark.gpu
+
+KINDS = ["ExpSquaredKernel", "Matern32Kernel", "Matern52Kernel"]
+
+
+def make_pair(kind, n, d, seed=0, white_noise=-6.0, fit_amp=True, log_M=None):
+    import alabi_b200 as ab
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-1, 1, size=(n, d))
+    y = np.sin(X.sum(axis=1)) + 0.3 * np.cos(2.0 * X[:, 0]) + 0.05 * rng.normal(size=n)
+    if log_M is None:
+        log_M = rng.uniform(-0.5, 0.8, size=d)
+    amp = np.var(y) if fit_amp else None
+    o = ogp.make_gp(kind, X, y, log_M, amp=amp, white_noise=white_noise, compute=True)
+    k = getattr(ab.kernels, kind)(metric=np.exp(log_M), ndim=d)
+    if fit_amp:
+        k = k * np.var(y)
+    g = ab.GP(kernel=k, fit_mean=True, mean=np.median(y), white_noise=white_noise, fit_white_noise=True)
+    g.compute(X)
+    return o, g, X, y, rng
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n,d", [(50, 2), (150, 2), (333, 5), (1000, 3), (1300, 10)])
+def test_names_vector_loglike_grad(kind, n, d):
+    o, g, X, y, rng = make_pair(kind, n, d, seed=n + d)
+    assert g.get_parameter_names() == o.get_parameter_names()
+    np.testing.assert_allclose(g.get_parameter_vector(), o.get_parameter_vector(), rtol=0, atol=0)
+    ll_o, ll_g = o.log_likelihood(y), g.log_likelihood(y)
+    assert abs(ll_g - ll_o) <= 1e-9 * abs(ll_o), (ll_g, ll_o)
+    assert abs(g.solver.log_determinant - o.log_determinant) <= 1e-10 * abs(o.log_determinant) + 1e-9
+    go, gg = o.grad_log_likelihood(y), g.grad_log_likelihood(y)
+    scale = np.maximum(np.abs(go), 1e-6 * np.max(np.abs(go)))
+    assert np.max(np.abs(gg - go) / scale) < 1e-7, (gg, go)
+    # a new hyper-vector marks the model dirty and is refactorised
+    p = o.get_parameter_vector() + rng.normal(0, 0.1, size=len(o.get_parameter_vector()))
+    o.set_parameter_vector(p)
+    g.set_parameter_vector(p)
+    ll_o, ll_g = o.log_likelihood(y), g.log_likelihood(y)
+    assert abs(ll_g - ll_o) <= 1e-9 * abs(ll_o)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n,d,m", [(50, 2, 1), (150, 2, 7), (700, 4, 1000), (1100, 10, 5000)])
+def test_predict_mean_var(kind, n, d, m):
+    o, g, X, y, rng = make_pair(kind, n, d, seed=7 * n + d)
+    t = rng.uniform(-1.1, 1.1, size=(m, d))
+    mu_o, var_o = o.predict(y, t, return_var=True)
+    mu_g = g.predict(y, t, return_cov=False)
+    mu_g2, var_g = g.predict(y, t, return_var=True)
+    np.testing.assert_array_equal(mu_g, mu_g2)
+    assert rel(mu_g, mu_o) < 1e-9
+    amp = np.exp(o.log_const)
+    assert np.max(np.abs(var_g - var_o)) < 1e-9 * amp, np.max(np.abs(var_g - var_o)) / amp
+    # alpha, K^-1 and kernel values as alabi/utility.py reads them
+    assert rel(g._alpha, o._alpha) < 1e-8
+    if n <= 700:
+        Ki = g.solver.get_inverse()
+        np.testing.assert_allclose(Ki, o.get_inverse(), rtol=0, atol=1e-9 * np.max(np.abs(Ki)))
+        np.testing.assert_allclose(g.kernel.get_value(t[:5], X), o.get_matrix(t[:5], X), rtol=1e-12, atol=1e-300)
+
+
+def test_device_tensor_io_and_no_amp():
+    import torch
+    o, g, X, y, rng = make_pair("Matern32Kernel", 400, 3, seed=5, fit_amp=False)
+    assert g.get_parameter_names()[2] == "kernel:metric:log_M_0_0"
+    t = rng.uniform(-1, 1, size=(300, 3))
+    mu, var = g.predict(y, torch.from_numpy(t).cuda(), return_var=True)
+    mu_o, var_o = o.predict(y, t, return_var=True)
+    assert rel(mu.cpu().numpy(), mu_o) < 1e-9 and np.max(np.abs(var.cpu().numpy() - var_o)) < 1e-9
+
+
+def test_not_positive_definite_paths():
+    import alabi_b200 as ab
+    rng = np.random.default_rng(1)
+    X = rng.uniform(-1, 1, size=(200, 2))
+    X[1] = X[0]
+    y = rng.normal(size=200)
+    k = ab.kernels.ExpSquaredKernel(metric=[1.0, 1.0], ndim=2) * 2.0     # amp = 1.0 exactly
+    g = ab.GP(kernel=k, mean=0.0, white_noise=-80.0)
+    with pytest.raises(np.linalg.LinAlgError):
+        g.compute(X)
+    assert g.log_likelihood(y, quiet=True) == -np.inf
+    assert np.all(g.grad_log_likelihood(y, quiet=True) == 0.0)
+
+
+@pytest.mark.parametrize("algo", ["bape", "agp", "jones"])
+def test_utility_argmin_matches_oracle(algo):
+    o, g, X, y, rng = make_pair("ExpSquaredKernel", 300, 2, seed=11)
+    bounds = np.array([(-1.0, 1.0), (-1.0, 1.0)])
+    cand = rng.uniform(-1.2, 1.2, size=(20000, 2))
+    mu_o, var_o = o.predict(y, cand, return_var=True)
+    u_o = ou.utility(algo, mu_o, var_o, ou.in_bounds(cand, bounds), y_best=y.max())
+    idx, val, u_g = g.utility_argmin(y, cand, bounds, algorithm=algo, y_best=y.max(), return_values=True)
+    u_g = u_g.cpu().numpy()
+    fin = np.isfinite(u_o)
+    assert np.array_equal(np.isfinite(u_g), fin)
+    assert np.array_equal(np.isposinf(u_g), np.isposinf(u_o))
+    np.testing.assert_allclose(u_g[fin], u_o[fin], rtol=1e-7, atol=1e-9)
+    want = int(np.argmin(np.where(fin, u_o, np.inf)))
+    assert idx == want and val == u_g[idx]
+
+
+def test_pickle_copy_roundtrip():
+    import copy
+    import pickle
+    o, g, X, y, rng = make_pair("Matern52Kernel", 260, 2, seed=3)
+    t = rng.uniform(-1, 1, size=(50, 2))
+    ref = g.predict(y, t, return_cov=False)
+    for h in (pickle.loads(pickle.dumps(g)), copy.copy(g), copy.deepcopy(g)):
+        np.testing.assert_array_equal(h.predict(y, t, return_cov=False), ref)
+
+
+@pytest.mark.parametrize("n", [2048, 4096])
+def test_large_factor_lookahead_equals_plain(n):
+    """Look-ahead scheduling must not change a single bit of L; logL agrees with LAPACK."""
+    import alabi_b200 as ab
+    from alabi_b200 import _lib
+    c = ob.make_config("c4", n_override=n)
+    X, y = c["X"] / 3.0, c["y"]
+    d = X.shape[1]
+    log_M = np.zeros(d) + 1.0
+    o = ogp.make_gp("ExpSquaredKernel", X, y, log_M, amp=np.var(y), white_noise=-6.0)
+    outs = []
+    for la in (1, 0):
+        g = ab.GP(kernel=ab.kernels.ExpSquaredKernel(metric=np.exp(log_M), ndim=d) * np.var(y),
+                  fit_mean=True, mean=np.median(y), white_noise=-6.0, fit_white_noise=True)
+        g._handle()
+        _lib.load().ab_gp_set_lookahead(g._hd.h, la)
+        g.compute(X)
+        ll = g.log_likelihood(y)
+        L, alpha = g.export_state()
+        outs.append((ll, L.cpu().numpy(), alpha.cpu().numpy()))
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(np.tril(outs[0][1]), np.tril(outs[1][1]))
+    ll_o = o.log_likelihood(y)
+    assert abs(outs[0][0] - ll_o) <= 1e-9 * abs(ll_o)
+    Lo = o._factor[0].T
+    assert np.max(np.abs(np.tril(outs[0][1])[:n, :n] - Lo)) < 1e-9 * np.max(np.abs(Lo))
