@@ -16,89 +16,13 @@
 #include <vector>
 #include "handle.h"
 #include "dmma_gemm.cuh"
+#include "potf2.cuh"
 
 namespace {
 
 constexpr int NB = AB_NB;
-constexpr int PLD = NB + 1;   // potf2 shared leading dimension
 
-// ---------------------------------------------------------------------------
-// diagonal block: Cholesky + triangular inverse, one CTA of 512 threads
-// ---------------------------------------------------------------------------
-// FACTOR = false: the block already holds L (imported factor); only D^-1 and the
-// log-determinant part are rebuilt, one CTA per diagonal block.
-template <bool FACTOR>
-__global__ void __launch_bounds__(512)
-potf2_inv_kernel(double* __restrict__ A, int64_t ld, int64_t o, double* __restrict__ Dinv,
-                 double* __restrict__ logdet_part, int* __restrict__ info) {
-    if (!FACTOR) {
-        o = (int64_t)blockIdx.x * NB;
-        Dinv += (int64_t)blockIdx.x * NB * NB;
-        logdet_part += blockIdx.x;
-    }
-    extern __shared__ double S[];          // [NB][PLD]; lower = A/L, (c, i+1) = B^T/X^T
-    __shared__ double sdiag[NB], sinv[NB];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int idx = tid; idx < NB * NB; idx += 512) {
-        int i = idx >> 7, j = idx & (NB - 1);
-        S[i * PLD + j] = (j <= i) ? A[(o + i) * ld + o + j] : ((j == i + 1) ? 1.0 : 0.0);
-    }
-    if (tid < NB) S[tid * PLD + NB] = (tid == NB - 1) ? 1.0 : 0.0;
-    __syncthreads();
-    // right-looking Cholesky; columns stay unscaled until the end:
-    //   S[i][k] -= S[i][j] S[k][j] / p_j
-    for (int j = 0; FACTOR && j < NB; j++) {
-        double p = S[j * PLD + j];
-        if (!(p > 0.0)) {                  // LAPACK dpotrf: ajj <= 0 or NaN -> info = j + 1
-            if (tid == 0) atomicCAS(info, 0, (int)(o + j + 1));
-            p = 1.0;
-        }
-        if (tid == 0) { double dj = sqrt(p); sdiag[j] = dj; sinv[j] = 1.0 / dj; }
-        const double ip = 1.0 / p;
-        for (int k = j + 1 + lane; k < NB; k += 32) {
-            const double akj = S[k * PLD + j] * ip;
-            for (int i = k + ((warp - k) & 15); i < NB; i += 16)   // rows i >= k, i == warp (mod 16)
-                S[i * PLD + k] = fma(-S[i * PLD + j], akj, S[i * PLD + k]);
-        }
-        __syncthreads();
-    }
-    if (!FACTOR) {
-        if (tid < NB) { double dj = S[tid * PLD + tid]; sdiag[tid] = dj; sinv[tid] = 1.0 / dj; }
-        __syncthreads();
-    }
-    for (int idx = tid; FACTOR && idx < NB * NB; idx += 512) {
-        int i = idx >> 7, j = idx & (NB - 1);
-        if (j < i) S[i * PLD + j] *= sinv[j];
-    }
-    __syncthreads();
-    if (tid < NB) S[tid * PLD + tid] = sdiag[tid];
-    if (warp == 0) {
-        double s = 0.0;
-        for (int j = lane; j < NB; j += 32) s += 2.0 * log(sdiag[j]);
-        s = ab_warp_sum(s);
-        if (lane == 0) *logdet_part = s;
-    }
-    __syncthreads();
-    for (int idx = tid; FACTOR && idx < NB * NB; idx += 512) {
-        int i = idx >> 7, j = idx & (NB - 1);
-        A[(o + i) * ld + o + j] = (j <= i) ? S[i * PLD + j] : 0.0;
-    }
-    // inverse: solve L X = I right-looking on B (element (i, c) lives at S[c][i + 1]);
-    // rows stay unscaled:  B[i][c] -= L[i][j] B[j][c] / d_j ,  X[j][c] = B[j][c] / d_j
-    for (int j = 0; j < NB - 1; j++) {
-        const double ij = sinv[j];
-        for (int c = warp; c <= j; c += 16) {
-            const double xjc = S[c * PLD + j + 1] * ij;
-            for (int i = j + 1 + lane; i < NB; i += 32)
-                S[c * PLD + i + 1] = fma(-S[i * PLD + j], xjc, S[c * PLD + i + 1]);
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < NB * NB; idx += 512) {
-        int i = idx >> 7, c = idx & (NB - 1);
-        Dinv[idx] = (c <= i) ? S[c * PLD + i + 1] * sinv[i] : 0.0;
-    }
-}
+using abp::potf2_inv_kernel;
 
 // ---------------------------------------------------------------------------
 // panel solve and trailing update (DMMA GEMM core)
@@ -317,8 +241,6 @@ int configure_once() {
     static int done = 0;
     if (done) return 0;
     int rc = 0;
-    rc |= set_smem(potf2_inv_kernel<true>, NB * PLD * 8);
-    rc |= set_smem(potf2_inv_kernel<false>, NB * PLD * 8);
     rc |= set_smem(trsm_panel_kernel, abg::SMEM_BYTES);
     rc |= set_smem(syrk_kernel, abg::SMEM_BYTES);
     rc |= set_smem(trinv_kernel<1>, abg::SMEM_BYTES);
@@ -348,11 +270,10 @@ int ab_launch_factor(ab_gp* h) {
     const int64_t ld = h->npad;
     cudaStream_t ms = h->stream;
     AB_CUDA(cudaMemsetAsync(h->d_info, 0, sizeof(int), ms));
-    const int psm = NB * PLD * 8;
     if (!h->lookahead || T < 3) {
         for (int k = 0; k < T; k++) {
             const int64_t o = (int64_t)k * NB;
-            potf2_inv_kernel<true><<<1, 512, psm, ms>>>(h->L, ld, o, h->Dinv + (int64_t)k * NB * NB, h->logdet_parts + k,
+            potf2_inv_kernel<true><<<1, 256, 0, ms>>>(h->L, ld, o, h->Dinv + (int64_t)k * NB * NB, h->logdet_parts + k,
                                                   h->d_info);
             int nb = T - k - 1;
             if (nb > 0) {
@@ -366,7 +287,7 @@ int ab_launch_factor(ab_gp* h) {
     cudaStream_t ps = h->panel_stream;
     AB_CUDA(cudaEventRecord(h->ev_fork, ms));
     AB_CUDA(cudaStreamWaitEvent(ps, h->ev_fork, 0));
-    potf2_inv_kernel<true><<<1, 512, psm, ps>>>(h->L, ld, 0, h->Dinv, h->logdet_parts, h->d_info);
+    potf2_inv_kernel<true><<<1, 256, 0, ps>>>(h->L, ld, 0, h->Dinv, h->logdet_parts, h->d_info);
     trsm_panel_kernel<<<T - 1, abg::THREADS, abg::SMEM_BYTES, ps>>>(h->L, ld, 0, h->Dinv);
     AB_CUDA(cudaEventRecord(h->ev_panel, ps));
     for (int k = 0; k < T; k++) {
@@ -378,7 +299,7 @@ int ab_launch_factor(ab_gp* h) {
         AB_CUDA(cudaEventRecord(h->ev_col, ms));
         AB_CUDA(cudaStreamWaitEvent(ps, h->ev_col, 0));
         double* Dk1 = h->Dinv + (int64_t)(k + 1) * NB * NB;
-        potf2_inv_kernel<true><<<1, 512, psm, ps>>>(h->L, ld, o + NB, Dk1, h->logdet_parts + k + 1, h->d_info);
+        potf2_inv_kernel<true><<<1, 256, 0, ps>>>(h->L, ld, o + NB, Dk1, h->logdet_parts + k + 1, h->d_info);
         if (nb - 1 > 0) trsm_panel_kernel<<<nb - 1, abg::THREADS, abg::SMEM_BYTES, ps>>>(h->L, ld, o + NB, Dk1);
         AB_CUDA(cudaEventRecord(h->ev_panel, ps));
         if (nb - 1 > 0)
@@ -392,7 +313,7 @@ int ab_launch_rebuild_dinv(ab_gp* h) {
     int rc = configure_once();
     if (rc) return rc;
     const int T = (int)(h->npad / NB);
-    potf2_inv_kernel<false><<<T, 512, NB * PLD * 8, h->stream>>>(h->L, h->npad, 0, h->Dinv, h->logdet_parts, h->d_info);
+    potf2_inv_kernel<false><<<T, 256, 0, h->stream>>>(h->L, h->npad, 0, h->Dinv, h->logdet_parts, h->d_info);
     AB_CHECK_LAUNCH();
     return 0;
 }

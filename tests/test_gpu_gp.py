@@ -39,7 +39,7 @@ def rel(a, b):
 def test_names_vector_loglike_grad(kind, n, d):
     o, g, X, y, rng = make_pair(kind, n, d, seed=n + d)
     assert g.get_parameter_names() == o.get_parameter_names()
-    np.testing.assert_allclose(g.get_parameter_vector(), o.get_parameter_vector(), rtol=0, atol=0)
+    np.testing.assert_allclose(g.get_parameter_vector(), o.get_parameter_vector(), rtol=1e-14, atol=1e-15)
     ll_o, ll_g = o.log_likelihood(y), g.log_likelihood(y)
     assert abs(ll_g - ll_o) <= 1e-9 * abs(ll_o), (ll_g, ll_o)
     assert abs(g.solver.log_determinant - o.log_determinant) <= 1e-10 * abs(o.log_determinant) + 1e-9
@@ -62,7 +62,8 @@ def test_predict_mean_var(kind, n, d, m):
     mu_o, var_o = o.predict(y, t, return_var=True)
     mu_g = g.predict(y, t, return_cov=False)
     mu_g2, var_g = g.predict(y, t, return_var=True)
-    np.testing.assert_array_equal(mu_g, mu_g2)
+    # the mean-only path may split the training sum across CTAs (order differs)
+    np.testing.assert_allclose(mu_g, mu_g2, rtol=1e-10, atol=1e-13)
     assert rel(mu_g, mu_o) < 1e-9
     amp = np.exp(o.log_const)
     assert np.max(np.abs(var_g - var_o)) < 1e-9 * amp, np.max(np.abs(var_g - var_o)) / amp
