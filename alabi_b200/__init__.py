@@ -8,6 +8,10 @@ arithmetic lives in ``libalabi_b200.so`` (hand-written sm_100a CUDA, see
 """
 from . import _lib, kernels
 from .gp import GP, LinAlgError
+from .ensemble import EnsembleSampler, SurrogateLogProb
+from .core import SurrogateModel, CachedSurrogateLikelihood
+from . import utility, gp_utils, mcmc_utils, benchmarks, parallel, nested
 
 __version__ = "0.1.0"
-__all__ = ["GP", "kernels", "LinAlgError"]
+__all__ = ["GP", "kernels", "LinAlgError", "EnsembleSampler", "SurrogateLogProb", "SurrogateModel",
+           "CachedSurrogateLikelihood", "utility", "gp_utils", "mcmc_utils", "benchmarks", "parallel", "nested"]

@@ -14,6 +14,20 @@ void ab_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void ab_count_launches(long long n) { g_launches += n; }
+
+static void prof_mark(ab_gp* h, int family) {
+    if (!h->profiling) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, h->stream);
+    h->prof_ev[family].push_back(e);
+}
+void ab_prof_begin(ab_gp* h, int family) { prof_mark(h, family); }
+void ab_prof_end(ab_gp* h, int family) { prof_mark(h, family); }
+
 #define AB_REQUIRE(cond, code, ...)            \
     do {                                       \
         if (!(cond)) {                         \
@@ -354,6 +368,35 @@ int ab_gp_utility_argmin(ab_gp* h, int utility_id, const double* d_Xq, int64_t m
     rc = ab_gp_predict(h, d_Xq, m, dmu, dvar);
     if (rc) return rc;
     return ab_utility_eval(h, utility_id, d_Xq, dmu, dvar, m, h_bounds, y_best, zeta, d_util, h_argmin, h_min);
+}
+
+long long ab_launch_counter(void) { return g_launches.load(); }
+
+int ab_gp_set_profiling(ab_gp* h, int enabled) {
+    AB_REQUIRE(h, -1, "null handle");
+    h->profiling = enabled != 0;
+    return 0;
+}
+
+// Sum of the device time (ms) between the begin/end marks of one kernel family
+// since the last call, and the number of marked launches.  Synchronises.
+int ab_gp_profile_read(ab_gp* h, int family, double* h_ms, long long* h_count) {
+    AB_REQUIRE(h && h_ms && h_count, -1, "null argument");
+    AB_REQUIRE(family >= 0 && family < AB_PROF_FAMILIES, -1, "bad family");
+    AB_CUDA(cudaSetDevice(h->device));
+    AB_CUDA(cudaStreamSynchronize(h->stream));
+    auto& v = h->prof_ev[family];
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < v.size(); i += 2) {
+        float t = 0.f;
+        AB_CUDA(cudaEventElapsedTime(&t, v[i], v[i + 1]));
+        ms += t;
+    }
+    *h_ms = ms;
+    *h_count = (long long)(v.size() / 2);
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
+    v.clear();
+    return 0;
 }
 
 int64_t ab_gp_padded_size(ab_gp* h) { return h ? h->npad : -1; }

@@ -270,6 +270,8 @@ int ab_launch_factor(ab_gp* h) {
     const int64_t ld = h->npad;
     cudaStream_t ms = h->stream;
     AB_CUDA(cudaMemsetAsync(h->d_info, 0, sizeof(int), ms));
+    ab_prof_begin(h, AB_PROF_FACTOR);
+    ab_count_launches(3LL * T);
     if (!h->lookahead || T < 3) {
         for (int k = 0; k < T; k++) {
             const int64_t o = (int64_t)k * NB;
@@ -281,6 +283,7 @@ int ab_launch_factor(ab_gp* h) {
                 syrk_kernel<<<nb * (nb + 1) / 2, abg::THREADS, abg::SMEM_BYTES, ms>>>(h->L, ld, o, o + NB, NB, 0);
             }
         }
+        ab_prof_end(h, AB_PROF_FACTOR);
         AB_CHECK_LAUNCH();
         return 0;
     }
@@ -305,6 +308,7 @@ int ab_launch_factor(ab_gp* h) {
         if (nb - 1 > 0)
             syrk_kernel<<<(nb - 1) * nb / 2, abg::THREADS, abg::SMEM_BYTES, ms>>>(h->L, ld, o, o + 2 * NB, NB, 0);
     }
+    ab_prof_end(h, AB_PROF_FACTOR);
     AB_CHECK_LAUNCH();
     return 0;
 }

@@ -136,9 +136,12 @@ int ab_launch_cov(ab_gp* h, double* K, int64_t ld, int mirror, int pad_identity)
     int64_t rows = pad_identity ? h->npad : h->n;
     int64_t nt = (rows + 63) / 64;
     int64_t ntiles = nt * (nt + 1) / 2;
+    ab_prof_begin(h, AB_PROF_COV);
     AB_DISPATCH_KIND(h->kp.kind, (cov_kernel<KIND><<<(unsigned)ntiles, 256, 0, h->stream>>>(
                                      h->XsT, h->npad, rows, h->XsT, h->npad, rows, h->n, h->kp, K, ld, 1, mirror,
                                      pad_identity)));
+    ab_prof_end(h, AB_PROF_COV);
+    ab_count_launches(1);
     AB_CHECK_LAUNCH();
     return 0;
 }

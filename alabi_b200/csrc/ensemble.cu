@@ -248,7 +248,10 @@ int launch_ens(ab_gp* h, EnsArgs& A, int nunits_half) {
     if (grid > nbatch) grid = nbatch;
     if (grid < 1) grid = 1;
     void* args[] = {(void*)&A};
+    ab_prof_begin(h, AB_PROF_ENSEMBLE);
     AB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(ETHREADS), args, smem, h->stream));
+    ab_prof_end(h, AB_PROF_ENSEMBLE);
+    ab_count_launches(1);
     return 0;
 }
 

@@ -1,7 +1,11 @@
 // Opaque GP handle behind the C ABI (include/alabi_b200.h).  One handle is bound
 // to one device and one stream; it owns the factor / inverse workspaces.
 #pragma once
+#include <vector>
 #include "common.cuh"
+
+enum { AB_PROF_COV = 0, AB_PROF_FACTOR = 1, AB_PROF_PREDICT_PANEL = 2, AB_PROF_PREDICT_VAR = 3,
+       AB_PROF_ENSEMBLE = 4, AB_PROF_FAMILIES = 5 };
 
 struct ab_gp {
     int device = 0;
@@ -37,6 +41,11 @@ struct ab_gp {
     int* d_info = nullptr;                // first non-positive pivot (1-based), 0 = SPD
     double* h_pinned = nullptr;           // small pinned host staging buffer (>= 4 KB)
 
+    // optional per-kernel-family device timing (bench.py roofline): event pairs
+    // recorded on h->stream around the launches of one family
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev[AB_PROF_FAMILIES];
+
     bool lookahead = true;
     bool factored = false, have_linv = false, have_kinv = false, have_alpha = false;
     int info = 0;
@@ -44,6 +53,10 @@ struct ab_gp {
 };
 
 int ab_ensure_scratch(ab_gp* h, size_t bytes);
+void ab_count_launches(long long n);
+// RAII-less scope helpers: record an event before / after a kernel family
+void ab_prof_begin(ab_gp* h, int family);
+void ab_prof_end(ab_gp* h, int family);
 
 // cov.cu
 int ab_launch_cov(ab_gp* h, double* K, int64_t ld, int mirror, int pad_identity);

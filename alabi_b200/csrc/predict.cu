@@ -271,7 +271,10 @@ int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double*
         }
         dim3 grid((unsigned)nblk, (unsigned)nsplit);
         int rc = 0;
+        ab_prof_begin(h, AB_PROF_PREDICT_PANEL);
         AB_DISPATCH_KIND(h->kp.kind, rc = (launch_mean<KIND, false>(h, d, grid, Xq, m, 0, mu, nullptr, 0, nsplit, partial)));
+        ab_prof_end(h, AB_PROF_PREDICT_PANEL);
+        ab_count_launches(nsplit > 1 ? 2 : 1);
         if (rc) return rc;
         if (nsplit > 1) {
             combine_splits_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(partial, m, nsplit, h->kp.amp, h->mean, mu);
@@ -290,11 +293,16 @@ int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double*
     for (int64_t q0 = 0; q0 < m; q0 += mq) {
         int64_t cnt = (m - q0 < mq) ? (m - q0) : mq;
         dim3 grid((unsigned)((cnt + QPB - 1) / QPB), 1);
+        ab_prof_begin(h, AB_PROF_PREDICT_PANEL);
         AB_DISPATCH_KIND(h->kp.kind, rc = (launch_mean<KIND, true>(h, d, grid, Xq, m, q0, mu, P, ldp, 1, nullptr)));
+        ab_prof_end(h, AB_PROF_PREDICT_PANEL);
         if (rc) return rc;
+        ab_prof_begin(h, AB_PROF_PREDICT_VAR);
         predict_var_kernel<<<(unsigned)((cnt + abg::BN - 1) / abg::BN), abg::THREADS, abg::SMEM_BYTES, s>>>(
             h->Linv, h->npad, T, P, ldp, m, q0, h->kp.amp, var);
+        ab_prof_end(h, AB_PROF_PREDICT_VAR);
         AB_CHECK_LAUNCH();
+        ab_count_launches(2);
     }
     return 0;
 }
@@ -316,6 +324,7 @@ int ab_launch_utility(ab_gp* h, int kind, const double* Xq, const double* mu, co
     utility_kernel<<<nb, 256, 0, h->stream>>>(Xq, mu, var, m, up, util, bval, bidx);
     argmin_final_kernel<<<1, 256, 0, h->stream>>>(bval, bidx, nb, h->scratch, reinterpret_cast<long long*>(h->scratch + 1));
     AB_CHECK_LAUNCH();
+    ab_count_launches(2);
     AB_CUDA(cudaMemcpyAsync(h->h_pinned, h->scratch, 16, cudaMemcpyDeviceToHost, h->stream));
     AB_CUDA(cudaStreamSynchronize(h->stream));
     *h_min = h->h_pinned[0];

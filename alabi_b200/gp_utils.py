@@ -1,0 +1,230 @@
+"""GP configuration and hyper-parameter search with the semantics of
+alabi/gp_utils.py, driving the GPU GP (``alabi_b200.GP``) instead of george.
+
+* ``configure_gp``                       alabi/gp_utils.py:170-248
+* ``regularization_term / _gradient``    alabi/gp_utils.py:30-108
+* ``optimize_gp_kfold_cv`` (3 stages)    alabi/gp_utils.py:511-1231
+* stage-2 / stage-3 candidate clouds     alabi/gp_utils.py:1234-1367
+"""
+import copy
+
+import numpy as np
+
+from .gp import GP
+
+__all__ = ["configure_gp", "optimize_gp_kfold_cv", "regularization_term", "regularization_gradient"]
+
+
+def regularization_term(hparams, lengthscale_indices, amp_0=1.0, mu_0=1.0, sigma_0=2.0):
+    """Negative log of a LogNormal(mu_0 + log sqrt(len(hparams)), sigma_0) prior
+    summed over the length-scale entries (the reference scales with the length
+    of the hyper-vector, not the problem dimension; kept)."""
+    hparams = np.asarray(hparams, dtype=np.float64)
+    ll = hparams[lengthscale_indices]
+    mu = mu_0 + 0.5 * np.log(len(hparams))
+    return amp_0 * np.sum(ll + 0.5 * np.log(2 * np.pi * sigma_0 ** 2) + (ll - mu) ** 2 / (2 * sigma_0 ** 2))
+
+
+def regularization_gradient(hparams, lengthscale_indices, amp_0=1.0, mu_0=1.0, sigma_0=2.0):
+    """(1 + (l - mu) / sigma_0^2) / exp(l) on the length-scale slots, zero elsewhere
+    (the reference differentiates w.r.t. the linear scale; kept)."""
+    hparams = np.asarray(hparams, dtype=np.float64)
+    g = np.zeros_like(hparams)
+    ll = hparams[lengthscale_indices]
+    mu = mu_0 + 0.5 * np.log(len(hparams))
+    g[lengthscale_indices] = (1.0 + (ll - mu) / sigma_0 ** 2) / np.exp(ll)
+    return amp_0 * g
+
+
+def configure_gp(theta, y, kernel, fit_amp=True, fit_mean=True, fit_white_noise=False, white_noise=-12,
+                 hyperparameters=None, device=None):
+    """Build the GP (amplitude = var(y), mean = median(y)), optionally set a
+    hyper-vector, and factorise.  Returns None when the covariance matrix is
+    not positive definite."""
+    theta = np.asarray(theta, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    if np.any(~np.isfinite(theta)):
+        raise ValueError("All theta values must be finite!")
+    if np.any(~np.isfinite(y)):
+        raise ValueError("All y values must be finite!")
+    if fit_amp:
+        kernel = kernel * np.var(y)
+    else:
+        kernel = copy.deepcopy(kernel)
+    gp = GP(kernel=kernel, fit_mean=fit_mean, mean=np.median(y), white_noise=white_noise,
+            fit_white_noise=fit_white_noise, device=device)
+    if hyperparameters is not None:
+        if np.any(~np.isfinite(hyperparameters)):
+            raise ValueError("All hyperparameter values must be finite!")
+        gp.set_parameter_vector(hyperparameters)
+    try:
+        gp.compute(theta)
+    except Exception as e:  # noqa: BLE001 - mirrors the reference's catch-all
+        print(f"configure_gp error: {e}")
+        return None
+    return gp
+
+
+def _weighted_mse(y_true, y_pred, method="exponential", temperature=1.0):
+    if method == "exponential":
+        w = np.exp(y_true / temperature)
+    elif method == "linear":
+        w = y_true - np.min(y_true) + 1e-6
+    elif method == "softmax":
+        w = np.exp(y_true / temperature)
+        w = w / np.sum(w) * len(w)
+    elif method == "rank":
+        w = np.argsort(np.argsort(y_true)) + 1
+    else:
+        raise ValueError(f"Unknown weight_method: {method}")
+    w = w / np.mean(w)
+    return np.average((y_true - y_pred) ** 2, weights=w)
+
+
+def _fold_score(scoring, y_val, y_pred, wmethod, wfactor):
+    if scoring == "mse":
+        return float(np.mean((y_val - y_pred) ** 2))
+    if scoring == "mae":
+        return float(np.mean(np.abs(y_val - y_pred)))
+    if scoring == "r2":
+        ss_res, ss_tot = np.sum((y_val - y_pred) ** 2), np.sum((y_val - np.mean(y_val)) ** 2)
+        return float(-(1.0 - ss_res / ss_tot))
+    if scoring == "weighted_mse":
+        return float(_weighted_mse(y_val, y_pred, wmethod, wfactor))
+    raise ValueError(f"Unsupported scoring method: {scoring}")
+
+
+def _evaluate_candidates(gp, theta, y, y_scaler, cands, k_folds, scoring, wmethod, wfactor):
+    """scores[cand, fold]; inf for failed folds.  Every (candidate, fold) is one
+    factorise + log-likelihood + mean-predict job on the GPU; a fresh shuffled
+    KFold split is drawn per candidate like the reference's worker does."""
+    from sklearn.model_selection import KFold
+    scores = np.full((len(cands), k_folds), np.inf)
+    work = copy.copy(gp)
+    for ci, hp in enumerate(cands):
+        if not np.all(np.isfinite(hp)):
+            continue
+        kf = KFold(n_splits=k_folds, shuffle=True, random_state=None)
+        for fi, (tr, va) in enumerate(kf.split(theta)):
+            try:
+                work.set_parameter_vector(hp)
+                work.compute(theta[tr])
+                ll = work.log_likelihood(y[tr])
+                if not np.isfinite(ll):
+                    raise ValueError("invalid log-likelihood")
+                pred = work.predict(y[tr], theta[va], return_var=False, return_cov=False)
+                if len(pred) == 0 or not np.all(np.isfinite(pred)):
+                    raise ValueError("invalid predictions")
+                y_val = y_scaler.inverse_transform(y[va].reshape(-1, 1)).flatten()
+                y_pred = y_scaler.inverse_transform(pred.reshape(-1, 1)).flatten()
+                scores[ci, fi] = _fold_score(scoring, y_val, y_pred, wmethod, wfactor)
+            except Exception:  # noqa: BLE001 - a failed fold scores inf, like the reference
+                scores[ci, fi] = np.inf
+    return scores
+
+
+def _mean_scores(scores):
+    out = np.full(len(scores), np.inf)
+    for i, row in enumerate(scores):
+        ok = row[np.isfinite(row)]
+        if len(ok):
+            out[i] = np.mean(ok)
+    return out
+
+
+def _generate_stage_candidates(best_params, n_candidates, width_factor, gp=None):
+    """Gaussian cloud of width ``width_factor`` around ``best_params`` (first
+    candidate = the centre).  Length scales move together only if the entries
+    the reference inspects are all equal (it indexes the full vector with
+    kernel-local positions; kept)."""
+    best = np.asarray(best_params, dtype=np.float64)
+    npar = len(best)
+    idx = None
+    if gp is not None:
+        idx = [i for i, nm in enumerate(gp.kernel.get_parameter_names()) if "metric:log_m" in nm.lower()]
+    if idx is not None and len(idx) > 1:
+        idx = [i for i in idx if i < npar]
+        uniform = np.allclose(best[idx], best[idx[0]])
+    elif npar > 2:
+        idx = list(range(2, npar))
+        uniform = np.allclose(best[2:], best[2])
+    else:
+        idx, uniform = [], False
+    cands = [best.copy()]
+    for _ in range(int(n_candidates) - 1):
+        if uniform and len(idx) > 0:
+            c = best.copy()
+            for j in range(npar):
+                if j not in idx:
+                    c[j] += np.random.normal(0, width_factor)
+            c[idx] += np.random.normal(0, width_factor)
+        else:
+            c = best + np.random.normal(0, width_factor, npar)
+        cands.append(c)
+    return np.array(cands)
+
+
+_generate_stage2_candidates = _generate_stage_candidates
+_generate_stage3_candidates = _generate_stage_candidates
+
+
+def optimize_gp_kfold_cv(gp, _theta, _y, hyperparameter_candidates, y_scaler, k_folds=5, scoring="mse", pool=None,
+                         stage2_candidates=None, stage2_width=0.5, stage3_candidates=None, stage3_width=0.2,
+                         weighted_mse_method="exponential", weighted_mse_factor=1.0, verbose=True):
+    """Pick the hyper-vector with the best mean k-fold validation score out of
+    the given candidates, then refine around the winner with up to two
+    Gaussian candidate clouds.  Returns the GP set to the winner and computed
+    on all data (None if every candidate fails).  ``pool`` is accepted for
+    signature compatibility; candidates are evaluated on the GPU."""
+    theta = np.asarray(_theta, dtype=np.float64)
+    y = np.asarray(_y, dtype=np.float64)
+    if theta.ndim == 1:
+        theta = theta.reshape(-1, 1)
+    if y.ndim != 1:
+        y = y.squeeze()
+    cands = np.asarray(hyperparameter_candidates, dtype=np.float64)
+    if cands.ndim == 1:
+        cands = cands.reshape(1, -1)
+    n = len(theta)
+    if len(y) != n:
+        raise ValueError(f"_theta and _y must have same length, got {len(theta)} and {len(y)}")
+    if n < k_folds:
+        raise ValueError(f"Number of samples ({n}) must be >= k_folds ({k_folds})")
+    if k_folds < 2:
+        raise ValueError(f"k_folds must be >= 2, got {k_folds}")
+    two_stage = stage2_candidates is not None
+    three_stage = stage3_candidates is not None
+
+    def run(c):
+        return _mean_scores(_evaluate_candidates(gp, theta, y, y_scaler, c, k_folds, scoring,
+                                                 weighted_mse_method, weighted_mse_factor))
+
+    s1 = run(cands)
+    if np.all(np.isinf(s1)):
+        if verbose:
+            print("CV: every stage-1 candidate failed")
+        return None
+    best_hp, best_score = cands[int(np.argmin(s1))], float(np.min(s1))
+    if verbose:
+        print(f"CV stage 1: best {scoring} = {best_score:.6g}")
+    if two_stage:
+        c2 = _generate_stage2_candidates(best_hp, stage2_candidates, stage2_width, gp=gp)
+        s2 = run(c2)
+        if not np.all(np.isinf(s2)) and np.min(s2) < best_score:
+            best_hp, best_score = c2[int(np.argmin(s2))], float(np.min(s2))
+        if verbose:
+            print(f"CV stage 2: best {scoring} = {best_score:.6g}")
+        if three_stage:
+            c3 = _generate_stage3_candidates(best_hp, stage3_candidates, stage3_width, gp=gp)
+            s3 = run(c3)
+            if not np.all(np.isinf(s3)) and np.min(s3) < best_score:
+                best_hp, best_score = c3[int(np.argmin(s3))], float(np.min(s3))
+            if verbose:
+                print(f"CV stage 3: best {scoring} = {best_score:.6g}")
+    try:
+        gp.set_parameter_vector(best_hp)
+        gp.compute(theta)
+    except Exception as e:  # noqa: BLE001
+        if verbose:
+            print(f"CV: could not set the best hyper-parameters: {e}")
+    return gp

@@ -1,0 +1,171 @@
+"""Multi-GPU layer: one process per GPU, ``torch.distributed`` (NCCL over
+NVLink / NVSwitch) for the plumbing.
+
+The GP is trained once on rank 0; the Cholesky factor L and alpha are broadcast
+(``ncclBroadcast``); after that every unit of work is independent:
+
+* query points and candidate batches are split by contiguous row ranges,
+* the utility argmin is an ``all_gather`` of one (value, index) pair per rank
+  reduced with the single-GPU tie rule (lowest global index),
+* walkers are split into independent sub-ensembles whose chain blocks are
+  ``all_gather``-ed.
+
+There is no data-path collective inside predict / utility / the sampler.  The
+host logic (ranges, pair reduction, chain gathering) works on CPU tensors with
+the ``gloo`` backend as well, which is how the CPU test-suite covers world
+size 2.
+"""
+import os
+
+import numpy as np
+
+__all__ = ["init_distributed", "shard_range", "broadcast_gp", "argmin_allgather", "allgather_rows",
+           "sharded_predict", "sharded_utility_argmin", "sharded_ensemble"]
+
+
+def init_distributed(backend=None):
+    """Initialise torch.distributed from RANK / WORLD_SIZE / LOCAL_RANK /
+    MASTER_* (torchrun).  Returns (rank, world_size, local_rank)."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    elif torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    return rank, world, local
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+def shard_range(m, rank, world):
+    """Contiguous row range [lo, hi) of shard ``rank``; sizes differ by at most one."""
+    base, rem = divmod(int(m), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def broadcast_gp(gp, x=None, y=None, src=0):
+    """Make every rank hold the GP trained on ``src``: hyper-parameters, inputs
+    and targets travel as a pickled object, L (npad x npad) and alpha as device
+    tensors over NCCL.  Returns the (imported) GP on every rank."""
+    import torch
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return gp
+    rank = dist.get_rank()
+    meta = [None]
+    if rank == src:
+        L, alpha = gp.export_state()
+        meta = [dict(vector=gp.get_parameter_vector(include_frozen=True), x=gp._x, y=gp._y, yerr2=gp._yerr2,
+                     npad=int(L.shape[0]), n=int(alpha.shape[0]))]
+    dist.broadcast_object_list(meta, src=src)
+    m = meta[0]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if rank != src:
+        L = torch.empty((m["npad"], m["npad"]), dtype=torch.float64, device=dev)
+        alpha = torch.empty(m["n"], dtype=torch.float64, device=dev)
+    dist.broadcast(L, src=src)
+    dist.broadcast(alpha, src=src)
+    if rank != src:
+        gp.set_parameter_vector(m["vector"], include_frozen=True)
+        gp.import_state(m["x"], m["y"], L, alpha, yerr=np.sqrt(m["yerr2"]))
+    return gp
+
+
+def argmin_allgather(value, index, device=None):
+    """Global (value, index) of the smallest finite value over all ranks; ties go
+    to the lowest global index (what a single-GPU argmin over the concatenated
+    candidates returns).  index < 0 means "no finite value on this rank"."""
+    import torch
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return float(value), int(index)
+    world = dist.get_world_size()
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if dist.get_backend() == "nccl" else torch.device("cpu"))
+    mine = torch.tensor([float(value), float(index)], dtype=torch.float64, device=dev)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    best_v, best_i = float("inf"), -1
+    for t in out:
+        v, i = float(t[0]), int(t[1])
+        if i >= 0 and (best_i < 0 or v < best_v or (v == best_v and i < best_i)):
+            best_v, best_i = v, i
+    return best_v, best_i
+
+
+def allgather_rows(t, dim=0):
+    """Concatenate per-rank tensors that may differ in length along ``dim``."""
+    import torch
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return t
+    world = dist.get_world_size()
+    n = torch.tensor([t.shape[dim]], dtype=torch.int64, device=t.device)
+    sizes = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s) for s in sizes]
+    mx = max(sizes)
+    t = t.movedim(dim, 0).contiguous()
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0).movedim(0, dim)
+
+
+def sharded_predict(gp, y, xq, return_var=True, gather=False):
+    """Predict this rank's contiguous slice of ``xq`` (a CUDA tensor holding
+    the full or the local query set is the caller's choice: pass the full set
+    and the slice is taken here)."""
+    dist = _dist()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    lo, hi = shard_range(xq.shape[0], rank, world)
+    out = gp.predict(y, xq[lo:hi], return_var=return_var, return_cov=False)
+    if not gather:
+        return out, (lo, hi)
+    if return_var:
+        return (allgather_rows(out[0]), allgather_rows(out[1])), (lo, hi)
+    return allgather_rows(out), (lo, hi)
+
+
+def sharded_utility_argmin(gp, y, candidates, bounds, algorithm="bape", y_best=0.0, zeta=0.01):
+    """Each rank evaluates its slice of the candidate set; one all_gather of
+    (value, global index) pairs picks the winner, bit-identical to a
+    single-GPU argmin over the whole set."""
+    dist = _dist()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    lo, hi = shard_range(candidates.shape[0], rank, world)
+    idx, val = gp.utility_argmin(y, candidates[lo:hi], bounds, algorithm=algorithm, y_best=y_best, zeta=zeta)
+    return argmin_allgather(val, idx + lo if idx >= 0 else -1)
+
+
+def sharded_ensemble(sampler_factory, p0, nsteps, gather=True, **run_kwargs):
+    """Independent sub-ensembles: rank r advances walkers [lo, hi) of ``p0`` with
+    RNG counters offset by ``lo`` (statistically independent streams), then the
+    chain blocks are all_gather-ed along the walker axis.
+
+    ``sampler_factory(nwalkers_local)`` builds the rank-local EnsembleSampler."""
+    import torch
+    dist = _dist()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    lo, hi = shard_range(len(p0), rank, world)
+    s = sampler_factory(hi - lo)
+    s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, **run_kwargs)
+    if not gather or world == 1:
+        return s, s.get_chain()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    chain = allgather_rows(torch.from_numpy(np.ascontiguousarray(s.get_chain())).to(dev), dim=1)
+    return s, chain.cpu().numpy()

@@ -55,6 +55,16 @@ const char* ab_last_error(void);
 /* multiprocessor count of `device`, < 0 on error (also proves a usable GPU) */
 int ab_device_sm_count(int device);
 
+/* instrumentation used by bench.py: number of kernels this library has launched
+ * in the process, and per-family device time between CUDA events recorded on
+ * the handle's stream (family: 0 cov, 1 factor, 2 predict panel/mean,
+ * 3 predict variance GEMM, 4 ensemble) */
+long long ab_launch_counter(void);
+/* measured issue-rate peak of the FP64 tensor pipe (DMMA.8x8x4), TFLOP/s */
+int ab_fp64_tensor_peak(int device, double* h_tflops);
+int ab_gp_set_profiling(ab_gp* h, int enabled);
+int ab_gp_profile_read(ab_gp* h, int family, double* h_ms, long long* h_count);
+
 /* ---- lifecycle: george.GP(kernel, fit_mean, mean, white_noise, fit_white_noise)
  *      alabi/gp_utils.py:233, alabi/core.py:1141 ------------------------------- */
 int ab_gp_create(ab_gp** out, int device, void* cuda_stream);

@@ -36,8 +36,11 @@ def scaled_sqdist(x1, x2, log_M):
     x1 = np.atleast_2d(np.asarray(x1, dtype=np.float64))
     x2 = np.atleast_2d(np.asarray(x2, dtype=np.float64))
     inv_M = np.exp(-np.asarray(log_M, dtype=np.float64))
-    d = x1[:, None, :] - x2[None, :, :]
-    return np.einsum("ijk,k->ij", d * d, inv_M)
+    r2 = np.zeros((x1.shape[0], x2.shape[0]))
+    for k in range(x1.shape[1]):            # per dimension: no (M, N, d) temporary
+        dk = x1[:, k, None] - x2[None, :, k]
+        r2 += dk * dk * inv_M[k]
+    return r2
 
 
 def radial(kind, r2):

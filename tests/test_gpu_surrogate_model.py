@@ -1,0 +1,75 @@
+"""End-to-end drop-in check of the alabi API on the GPU path (BASELINE config c1
+in miniature): init_samples -> init_gp -> active_train (BAPE) ->
+surrogate_log_likelihood / cached likelihood -> run_emcee -> run_dynesty."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def lnlike(theta):
+    theta = np.asarray(theta).flatten()
+    return -0.5 * np.sum((theta / np.array([0.6, 0.9])) ** 2)      # N(0, diag(0.36, 0.81)) log-density
+
+
+@pytest.mark.parametrize("hyperopt", ["ml", "cv"])
+def test_alabi_workflow(tmp_path, hyperopt):
+    import alabi_b200 as ab
+    from oracle import gp as ogp
+    np.random.seed(3)
+    bounds = [(-3.0, 3.0), (-3.0, 3.0)]
+    sm = ab.SurrogateModel(lnlike_fn=lnlike, bounds=bounds, savedir=str(tmp_path), cache=True, verbose=False)
+    sm.init_samples(ntrain=60, ntest=20, sampler="lhs")
+    assert sm.theta_train.shape == (60, 2) and sm.ntest == 20
+    kw = dict(hyperopt_method=hyperopt, gp_nopt=2)
+    if hyperopt == "cv":
+        # the reference applies LINEAR amplitude bounds (var * 10^rng) to the LOG amplitude
+        # (alabi/core.py:654-655, kept): keep them small so candidates stay factorisable
+        kw.update(cv_n_candidates=12, cv_stage2_candidates=6, cv_stage3_candidates=4, gp_amp_rng=[-2, -1])
+    test_mse = sm.init_gp(kernel="ExpSquaredKernel", fit_amp=True, fit_mean=True, fit_white_noise=False,
+                          white_noise=-10, gp_scale_rng=[-1, 3], **kw)
+    assert np.isfinite(test_mse)
+    assert sm.param_names_full[-2:] == ["kernel:k2:metric:log_M_0_0", "kernel:k2:metric:log_M_1_1"]
+    with pytest.raises(AssertionError):
+        sm.init_gp()
+    sm.active_train(niter=8, algorithm="bape", gp_opt_freq=4, nopt=2, show_progress=False)
+    assert sm.ntrain == 68 and len(sm.training_results["iteration"]) == 8
+    assert len(sm.training_results["gp_hyperparameters"][-1]) == len(sm.param_names_full)
+    assert np.all(np.isfinite(sm.training_results["training_mse"]))
+    sm.active_train(niter=2, algorithm="jones", gp_opt_freq=50, nopt=1, obj_opt_method="nelder-mead", show_progress=False)
+    sm.active_train(niter=2, algorithm="agp", gp_opt_freq=50, obj_opt_method="batch", show_progress=False)
+    assert sm.training_results["iteration"][-1] == 12
+
+    # surrogate vs an independent CPU GP with the same hyper-parameters and data
+    hp = dict(zip(sm.param_names_full, sm.gp.get_parameter_vector()))
+    o = ogp.OracleGP("ExpSquaredKernel", 2, [hp["kernel:k2:metric:log_M_0_0"], hp["kernel:k2:metric:log_M_1_1"]],
+                     log_const=hp["kernel:k1:log_constant"], mean=hp["mean:value"], white_noise=-10.0)
+    o.compute(sm._theta)
+    t = np.random.default_rng(0).uniform(-2, 2, size=(200, 2))
+    mu_o, var_o = o.predict(sm._y, t, return_var=True)
+    mu, var = sm.surrogate_log_likelihood(t, return_var=True)
+    scale = max(np.abs(mu_o).max(), 1.0)
+    assert np.max(np.abs(mu - mu_o)) < 1e-7 * scale and np.max(np.abs(var - var_o)) < 1e-7 * scale
+    assert np.isscalar(sm.surrogate_log_likelihood(t[0])) or np.ndim(sm.surrogate_log_likelihood(t[0])) == 0
+    assert abs(sm.surrogate_log_likelihood(np.zeros(2)) - lnlike(np.zeros(2))) < 0.3
+    cached = sm.create_cached_surrogate_likelihood(return_var=True)
+    cm, cv = cached(t)
+    np.testing.assert_allclose(cm, mu, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(cv, var, rtol=1e-6, atol=1e-9)
+    sm.prior_fn = lambda th: ab.utility.lnprior_uniform(th, sm.bounds)
+    assert np.isfinite(sm.lnprob(np.array([0.1, 0.2]))) and sm.lnprob(np.array([5.0, 0.0])) == -np.inf
+
+    # posterior sampling on the surrogate: device stretch move and batched nested sampling
+    sm.run_emcee(nwalkers=40, nsteps=800, min_ess=500)
+    s = sm.emcee_samples
+    assert s.shape[1] == 2 and len(s) >= 500 and 0.2 < sm.acc_frac < 0.9
+    assert abs(s[:, 0].std() - 0.6) < 0.12 and abs(s[:, 1].std() - 0.9) < 0.15 and abs(s.mean()) < 0.15
+    sm.run_dynesty(sampler_kwargs={"nlive": 200}, min_ess=200, run_kwargs={"dlogz": 0.05})
+    dz = sm.dynesty_samples
+    assert abs(dz[:, 0].std() - 0.6) < 0.12 and abs(dz[:, 1].std() - 0.9) < 0.15
+    want_logz = np.log(2 * np.pi * 0.6 * 0.9 / 36.0)
+    assert abs(sm.dynesty_logz - want_logz) < 0.35
+    # the cached pickle reloads and predicts the same numbers
+    import pickle
+    sm2 = pickle.load(open(tmp_path / "surrogate_model.pkl", "rb"))
+    np.testing.assert_allclose(sm2.surrogate_log_likelihood(t), mu, rtol=1e-9, atol=1e-9)

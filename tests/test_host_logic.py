@@ -1,0 +1,190 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol,
+host-side helpers agree with the reference's golden vectors, the product fails
+loudly without a GPU, and the multi-rank host logic works over gloo."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from alabi_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "alabi_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ab_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ab_version() == 100
+    assert ctypes.sizeof(_lib.EnsembleConfig) == 8 * 4 + 8 * 6 + 4 * 32 * 8
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import alabi_b200 as ab
+    g = ab.GP(kernel=ab.kernels.ExpSquaredKernel(metric=[1.0, 1.0], ndim=2) * 2.0)
+    with pytest.raises(ab._lib.AlabiB200Error):
+        g.compute(np.random.default_rng(0).uniform(size=(10, 2)))
+    with pytest.raises(TypeError):
+        ab.EnsembleSampler(8, 2, lambda x: 0.0)
+
+
+def test_kernel_parameter_protocol():
+    import alabi_b200 as ab
+    k = ab.kernels.Matern32Kernel(metric=np.exp([0.1, 0.2, 0.3]), metric_bounds=[(-2, 2)] * 3, ndim=3)
+    kk = k * 6.0
+    assert kk.get_parameter_names() == ("k1:log_constant", "k2:metric:log_M_0_0", "k2:metric:log_M_1_1",
+                                        "k2:metric:log_M_2_2")
+    np.testing.assert_allclose(kk.get_parameter_vector(), [np.log(6.0 / 3), 0.1, 0.2, 0.3])
+    g = ab.GP(kernel=kk, fit_mean=True, mean=1.5, white_noise=-12, fit_white_noise=True)
+    assert g.get_parameter_names() == ("mean:value", "white_noise:value", "kernel:k1:log_constant",
+                                       "kernel:k2:metric:log_M_0_0", "kernel:k2:metric:log_M_1_1",
+                                       "kernel:k2:metric:log_M_2_2")
+    v = g.get_parameter_vector() + 0.5
+    g.set_parameter_vector(v)
+    np.testing.assert_allclose(g.get_parameter_vector(), v)
+    assert list(g.get_parameter_dict().values()) == list(v) and g.dirty
+    g2 = ab.GP(kernel=k, mean=0.0)
+    assert g2.get_parameter_names() == ("kernel:metric:log_M_0_0", "kernel:metric:log_M_1_1", "kernel:metric:log_M_2_2")
+    kid, amp, lm = kk.spec()
+    assert kid == 1 and lm.shape == (3,) and abs(amp - np.exp(v[2])) < 1e-15
+
+
+def test_host_utilities_match_reference_golden():
+    from alabi_b200 import utility as ut, gp_utils, mcmc_utils
+    g = np.load(os.path.join(GOLDEN, "utility_golden.npz"))
+    b = g["bounds"]
+    for i in range(0, len(g["mu"]), 7):
+        pg = lambda x, i=i: (np.array([g["mu"][i]]), np.array([g["var"][i]]))
+        for name, fn in (("bape", ut.bape_utility), ("agp", ut.agp_utility)):
+            got = fn(g["theta"][i], pg, b)
+            assert got == g[name][i] or (np.isnan(got) and np.isnan(g[name][i]))
+        got = ut.jones_utility(g["theta"][i], pg, b, float(g["y_best"]))
+        assert got == g["jones"][i]
+        assert ut.lnprior_uniform(g["theta"][i], b) == g["lnprior"][i]
+    np.testing.assert_array_equal(ut.prior_transform_uniform(g["u"], b), g["prior_transform"])
+    with np.errstate(all="ignore"):
+        for a, c, w in zip(g["x1"], g["x2"], g["logsubexp"]):
+            assert ut.logsubexp(a, c) == w
+    lidx = list(g["lidx"])
+    for h, r, rg in zip(g["hp"], g["reg"], g["reg_grad"]):
+        np.testing.assert_allclose(gp_utils.regularization_term(h, lidx, 1.3, 0.7, 1.9), r, rtol=1e-14)
+        np.testing.assert_allclose(gp_utils.regularization_gradient(h, lidx, 1.3, 0.7, 1.9), rg, rtol=1e-14)
+    for t, n, bt in zip(g["taus"], g["tau_len"], g["burn"]):
+        class S:
+            def get_autocorr_time(self, tol=0, t=t[:n]):
+                return t.copy()
+        assert mcmc_utils.estimate_burnin(S()) == (int(bt[0]), int(bt[1]))
+
+
+def test_autocorr_and_samplers_host_side():
+    from alabi_b200 import utility as ut, mcmc_utils
+    from oracle import emcee as oem
+    rng = np.random.default_rng(0)
+    x = np.cumsum(rng.normal(size=(800, 6, 2)), axis=0) * 0.05 + rng.normal(size=(800, 6, 2))
+    np.testing.assert_allclose(mcmc_utils.integrated_time(x, tol=0), oem.integrated_time(x, tol=0), rtol=1e-12)
+    with pytest.raises(mcmc_utils.AutocorrError):
+        mcmc_utils.integrated_time(x[:60], tol=50)
+    b = [(-1, 2), (0, 5), (3, 4)]
+    for s in ("uniform", "sobol", "lhs", "halton", "hammersly", "grid"):
+        p = ut.prior_sampler(b, nsample=17, sampler=s)
+        assert p.shape == (17, 3) and np.all(p >= [-1, 0, 3]) and np.all(p <= [2, 5, 4])
+    with pytest.raises(ValueError):
+        ut.prior_sampler(b, nsample=3, sampler="nope")
+    ts, to = ut.scaler_affine(ut.no_scaler, 3)
+    assert np.all(ts == 1) and np.all(to == 0) and ut.scaler_affine(ut.nlog_scaler, 1, inverse=True)[0] == 1
+    from sklearn.preprocessing import MinMaxScaler, StandardScaler
+    mm = MinMaxScaler().fit(np.array(b, dtype=float).T)
+    ts, to = ut.scaler_affine(mm, 3)
+    q = rng.uniform(0, 1, size=(5, 3)) * 3
+    np.testing.assert_allclose(q * ts + to, mm.transform(q))
+    ss = StandardScaler().fit(rng.normal(3.0, 2.0, size=(50, 1)))
+    k, sc, off = ut.scaler_affine(ss, 1, inverse=True)
+    np.testing.assert_allclose(np.array([0.3]) * sc + off, ss.inverse_transform([[0.3]])[0])
+
+
+def test_batched_nested_sampler_evidence():
+    from alabi_b200.nested import BatchedNestedSampler, resample_equal
+    sig = 0.1
+    like = lambda t: -0.5 * np.sum(((np.atleast_2d(t) - 0.5) / sig) ** 2, axis=1)
+    s = BatchedNestedSampler(like, lambda u: u, 2, nlive=300, walks=20, rstate=1)
+    r = s.run_nested(dlogz=0.01)
+    want = np.log(2 * np.pi * sig ** 2)
+    assert abs(r.logz[-1] - want) < 5 * r.logzerr[-1] + 0.1, (r.logz[-1], want, r.logzerr[-1])
+    eq = resample_equal(r.samples, np.exp(r.logwt - r.logz[-1]), np.random.default_rng(0))
+    assert abs(eq[:, 0].mean() - 0.5) < 0.02 and abs(eq[:, 1].std() - sig) < 0.02
+    assert r.samples.shape[1] == 2 and len(r.logwt) == len(r.samples) == len(r.logz)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from alabi_b200 import parallel as par
+    r, w, _ = par.init_distributed(backend="gloo")
+    out = {}
+    # candidates 0..99, the minimum value appears on BOTH ranks: lowest global index must win
+    u = np.full(101, 5.0)
+    u[[30, 80]] = -2.0
+    lo, hi = par.shard_range(101, r, w)
+    loc = u[lo:hi]
+    i = int(np.argmin(loc))
+    out["argmin"] = par.argmin_allgather(loc[i], i + lo)
+    out["none"] = par.argmin_allgather(float("inf"), -1 if r == 0 else 7 + lo)
+    t = torch.arange(lo, hi, dtype=torch.float64).reshape(-1, 1).repeat(1, 3)
+    out["rows"] = par.allgather_rows(t).numpy()
+    ch = torch.full((4, hi - lo, 2), float(r))
+    out["chain"] = par.allgather_rows(ch, dim=1).numpy()
+    out["range"] = (lo, hi)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_host_logic():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0]["range"] == (0, 51) and res[1]["range"] == (51, 101)
+    for r in (0, 1):
+        assert res[r]["argmin"] == (-2.0, 30)
+        assert res[r]["none"][1] == 7 + 51
+        np.testing.assert_array_equal(res[r]["rows"][:, 0], np.arange(101))
+        assert res[r]["chain"].shape == (4, 101, 2) and res[r]["chain"][0, 50, 0] == 0 and res[r]["chain"][0, 51, 0] == 1
+
+
+def test_shard_range_covers_everything():
+    from alabi_b200.parallel import shard_range
+    for m in (0, 1, 7, 8, 1000003):
+        for w in (1, 2, 4, 8):
+            ranges = [shard_range(m, r, w) for r in range(w)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == m
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            sizes = [hi - lo for lo, hi in ranges]
+            assert max(sizes) - min(sizes) <= 1
