@@ -65,7 +65,10 @@ struct Acc {
 //   BKM: same for B.
 // All 256 threads must call; smem must hold SMEM_BYTES.  Ends with the pipeline
 // drained and a __syncthreads(), so smem can be reused by the caller.
-template <bool AK, bool BKM>
+//   TRI_A: the last 8 chunks (one 128-wide k block) multiply a LOWER-TRIANGULAR
+//   128 x 128 A block (A[r][k] = 0 for k > r): m-fragments whose rows all lie
+//   above the current k4-step are skipped (warp-uniform test).
+template <bool AK, bool BKM, bool TRI_A = false>
 __device__ __forceinline__ void mainloop(Acc& acc, const double* __restrict__ A, int64_t lda,
                                          const double* __restrict__ B, int64_t ldb, int nk,
                                          double* smem) {
@@ -109,10 +112,13 @@ __device__ __forceinline__ void mainloop(Acc& acc, const double* __restrict__ A,
             for (int f = 0; f < 4; f++)
                 b[f] = BKM ? sB[(wn * 32 + f * 8 + g) * LDK + kk * 4 + t]
                            : sB[(kk * 4 + t) * LDR + wn * 32 + f * 8 + g];
+            const int ktri = TRI_A ? (kc - (nk - 8)) * BK + kk * 4 : -1;   // k offset inside the diagonal block
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < 8; i++) {
+                if (TRI_A && ktri > wm * 64 + i * 8 + 7) continue;
 #pragma unroll
                 for (int j = 0; j < 4; j++) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+            }
         }
     }
     cp_async_wait<0>();

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128)
 predict_mean_kernel(const double* __restrict__ Xq, int64_t m, int64_t q_off, const double* __restrict__ Xs,
                     const double* __restrict__ alpha, int64_t n, int64_t npad, KernParams kp, double mean,
                     double* __restrict__ mu, double* __restrict__ P, int64_t ldp, int nsplit,
-                    double* __restrict__ partial) {
+                    double* __restrict__ partial, int64_t part_ld) {
     __shared__ __align__(16) double sX[TS * D];
     __shared__ double sAl[TS];
     const int tid = threadIdx.x, d = kp.d;
@@ -41,11 +41,12 @@ predict_mean_kernel(const double* __restrict__ Xq, int64_t m, int64_t q_off, con
         xb[k] = (k < d && q_off + qb < m) ? Xq[(q_off + qb) * d + k] * kp.inv_len[k] : 0.0;
     }
     // training range of this split
-    int64_t jbeg = 0, jend = STORE ? npad : n;
+    const int64_t jtot = STORE ? npad : n;      // the panel also needs the (zero) padding rows
+    int64_t jbeg = 0, jend = jtot;
     if (nsplit > 1) {
-        int64_t per = ((n + nsplit - 1) / nsplit + TS - 1) / TS * TS;
+        int64_t per = ((jtot + nsplit - 1) / nsplit + TS - 1) / TS * TS;
         jbeg = (int64_t)blockIdx.y * per;
-        jend = jbeg + per < n ? jbeg + per : n;
+        jend = jbeg + per < jtot ? jbeg + per : jtot;
     }
     double ma = 0.0, mb = 0.0;
     for (int64_t j0 = jbeg; j0 < jend; j0 += TS) {
@@ -79,21 +80,22 @@ predict_mean_kernel(const double* __restrict__ Xq, int64_t m, int64_t q_off, con
         }
     }
     if (nsplit > 1) {
-        if (q_off + qa < m) partial[(int64_t)blockIdx.y * m + q_off + qa] = ma;
-        if (q_off + qb < m) partial[(int64_t)blockIdx.y * m + q_off + qb] = mb;
+        partial[(int64_t)blockIdx.y * part_ld + qa] = ma;
+        partial[(int64_t)blockIdx.y * part_ld + qb] = mb;
     } else {
         if (q_off + qa < m) mu[q_off + qa] = fma(kp.amp, ma, mean);
         if (q_off + qb < m) mu[q_off + qb] = fma(kp.amp, mb, mean);
     }
 }
 
-__global__ void combine_splits_kernel(const double* __restrict__ partial, int64_t m, int nsplit, double amp,
-                                      double mean, double* __restrict__ mu) {
+// mu[q_off + q] = amp * sum_splits partial[split][q] + mean  for q < cnt (fixed order)
+__global__ void combine_splits_kernel(const double* __restrict__ partial, int64_t part_ld, int64_t cnt, int nsplit,
+                                      double amp, double mean, double* __restrict__ mu, int64_t q_off) {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= m) return;
+    if (q >= cnt) return;
     double s = 0.0;
-    for (int p = 0; p < nsplit; p++) s += partial[(int64_t)p * m + q];
-    mu[q] = fma(amp, s, mean);
+    for (int p = 0; p < nsplit; p++) s += partial[(int64_t)p * part_ld + q];
+    mu[q_off + q] = fma(amp, s, mean);
 }
 
 // sigma^2 for the 128 queries of this CTA:  amp - sum_i ( sum_k Linv[i][k] P[k][q] )^2
@@ -108,7 +110,7 @@ predict_var_kernel(const double* __restrict__ Linv, int64_t ld, int T, const dou
     for (int i = 0; i < T; i++) {
         abg::Acc acc;
         acc.zero();
-        abg::mainloop<true, false>(acc, Linv + (int64_t)i * NB * ld, ld, Bp, ldp, (i + 1) * (NB / abg::BK), smem);
+        abg::mainloop<true, false, true>(acc, Linv + (int64_t)i * NB * ld, ld, Bp, ldp, (i + 1) * (NB / abg::BK), smem);
 #pragma unroll
         for (int a = 0; a < 8; a++)
 #pragma unroll
@@ -229,10 +231,10 @@ argmin_final_kernel(const double* __restrict__ bval, const long long* __restrict
 
 template <int KIND, bool STORE>
 int launch_mean(ab_gp* h, int Dp, dim3 grid, const double* Xq, int64_t m, int64_t q_off, double* mu, double* P,
-                int64_t ldp, int nsplit, double* partial) {
+                int64_t ldp, int nsplit, double* partial, int64_t part_ld) {
 #define AB_PM(DD)                                                                                              \
     predict_mean_kernel<KIND, DD, STORE><<<grid, 128, 0, h->stream>>>(Xq, m, q_off, h->Xs, h->alpha, h->n, h->npad, \
-                                                                      h->kp, h->mean, mu, P, ldp, nsplit, partial)
+                                                                      h->kp, h->mean, mu, P, ldp, nsplit, partial, part_ld)
     if (Dp <= 2) AB_PM(2);
     else if (Dp <= 4) AB_PM(4);
     else if (Dp <= 8) AB_PM(8);
@@ -264,45 +266,67 @@ int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double*
             if (nsplit < 1) nsplit = 1;
         }
         double* partial = nullptr;
+        const int64_t part_ld = nblk * QPB;
         if (nsplit > 1) {
-            int rc = ab_ensure_scratch(h, (size_t)nsplit * m * sizeof(double));
+            int rc = ab_ensure_scratch(h, (size_t)nsplit * part_ld * sizeof(double));
             if (rc) return rc;
             partial = h->scratch;
         }
         dim3 grid((unsigned)nblk, (unsigned)nsplit);
         int rc = 0;
         ab_prof_begin(h, AB_PROF_PREDICT_PANEL);
-        AB_DISPATCH_KIND(h->kp.kind, rc = (launch_mean<KIND, false>(h, d, grid, Xq, m, 0, mu, nullptr, 0, nsplit, partial)));
+        AB_DISPATCH_KIND(h->kp.kind, rc = (launch_mean<KIND, false>(h, d, grid, Xq, m, 0, mu, nullptr, 0, nsplit, partial, part_ld)));
         ab_prof_end(h, AB_PROF_PREDICT_PANEL);
         ab_count_launches(nsplit > 1 ? 2 : 1);
         if (rc) return rc;
         if (nsplit > 1) {
-            combine_splits_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(partial, m, nsplit, h->kp.amp, h->mean, mu);
+            combine_splits_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(partial, part_ld, m, nsplit, h->kp.amp,
+                                                                              h->mean, mu, 0);
             AB_CHECK_LAUNCH();
         }
         return 0;
     }
-    // mean + variance, processed in panels of at most kPanelQueries queries
+    // mean + variance, processed in panels.  Panel width: whole waves of variance CTAs
+    // (148 x 128 queries), as many as fit a ~2 GB cross-covariance panel.
     AB_CUDA(cudaFuncSetAttribute(predict_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));
     const int T = (int)(h->npad / NB);
-    int64_t mq = m < kPanelQueries ? m : kPanelQueries;
-    int64_t ldp = (mq + QPB - 1) / QPB * QPB;                 // multiple of 256 (and of 128)
-    int rc = ab_ensure_scratch(h, (size_t)h->npad * ldp * sizeof(double));
+    int64_t waves = (int64_t)((2ULL << 30) / ((size_t)h->npad * kPanelQueries * sizeof(double)));
+    if (waves < 1) waves = 1;
+    if (waves > 16) waves = 16;
+    int64_t mq = waves * kPanelQueries;
+    if (m < mq) mq = m;
+    const int64_t ldp = (mq + QPB - 1) / QPB * QPB;                 // multiple of 256 (and of 128)
+    const int64_t nblk = ldp / QPB;
+    // split the training range over grid.y so that the panel kernel fills the GPU
+    int nsplit = 1;
+    if (nblk < 592) {
+        int64_t want = (592 + nblk - 1) / nblk, maxs = h->npad / TS;
+        nsplit = (int)(want < maxs ? want : maxs);
+        if (nsplit < 1) nsplit = 1;
+    }
+    const size_t panel_elems = (size_t)h->npad * ldp;
+    int rc = ab_ensure_scratch(h, (panel_elems + (size_t)nsplit * ldp) * sizeof(double));
     if (rc) return rc;
     double* P = h->scratch;
+    double* partial = h->scratch + panel_elems;
     for (int64_t q0 = 0; q0 < m; q0 += mq) {
         int64_t cnt = (m - q0 < mq) ? (m - q0) : mq;
-        dim3 grid((unsigned)((cnt + QPB - 1) / QPB), 1);
+        dim3 grid((unsigned)((cnt + QPB - 1) / QPB), (unsigned)nsplit);
         ab_prof_begin(h, AB_PROF_PREDICT_PANEL);
-        AB_DISPATCH_KIND(h->kp.kind, rc = (launch_mean<KIND, true>(h, d, grid, Xq, m, q0, mu, P, ldp, 1, nullptr)));
-        ab_prof_end(h, AB_PROF_PREDICT_PANEL);
+        AB_DISPATCH_KIND(h->kp.kind, rc = (launch_mean<KIND, true>(h, d, grid, Xq, m, q0, mu, P, ldp, nsplit, partial, ldp)));
         if (rc) return rc;
+        if (nsplit > 1) {
+            combine_splits_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(partial, ldp, cnt, nsplit, h->kp.amp,
+                                                                                h->mean, mu, q0);
+            AB_CHECK_LAUNCH();
+        }
+        ab_prof_end(h, AB_PROF_PREDICT_PANEL);
         ab_prof_begin(h, AB_PROF_PREDICT_VAR);
         predict_var_kernel<<<(unsigned)((cnt + abg::BN - 1) / abg::BN), abg::THREADS, abg::SMEM_BYTES, s>>>(
             h->Linv, h->npad, T, P, ldp, m, q0, h->kp.amp, var);
         ab_prof_end(h, AB_PROF_PREDICT_VAR);
         AB_CHECK_LAUNCH();
-        ab_count_launches(2);
+        ab_count_launches(nsplit > 1 ? 3 : 2);
     }
     return 0;
 }
