@@ -38,13 +38,16 @@ trsm_panel_kernel(double* __restrict__ A, int64_t ld, int64_t o, const double* _
 }
 
 // mode 0: lower-triangular tiles of the trailing matrix starting at r0
-// mode 1: first block column only (tile (blockIdx.x, 0))
+// mode 1: tile (blockIdx.x, 0)  — first block column
+// mode 2: first TWO block columns of an nt-row trailing matrix:
+//         blockIdx.x < nt -> (blockIdx.x, 0), else (blockIdx.x - nt + 1, 1)
 __global__ void __launch_bounds__(abg::THREADS, 1)
-syrk_kernel(double* __restrict__ A, int64_t ld, int64_t o, int64_t r0, int kdim, int mode) {
+syrk_kernel(double* __restrict__ A, int64_t ld, int64_t o, int64_t r0, int kdim, int mode, int nt) {
     extern __shared__ __align__(16) double smem[];
     int ti, tj;
     if (mode == 0) abg::tri_decode(blockIdx.x, ti, tj);
-    else { ti = blockIdx.x; tj = 0; }
+    else if (mode == 1 || (int)blockIdx.x < nt) { ti = blockIdx.x; tj = 0; }
+    else { ti = blockIdx.x - nt + 1; tj = 1; }
     abg::Acc acc;
     acc.zero();
     const double* Ap = A + (r0 + (int64_t)ti * NB) * ld + o;
@@ -263,6 +266,14 @@ int inv_tree(int r0, int nblk, std::vector<std::vector<InvNode>>& levels) {
 }
 }  // namespace
 
+// Right-looking factorisation with 128-wide panels whose trailing updates are
+// applied two panels at a time (K = 256 DMMA GEMMs: half the C traffic and half
+// the per-tile prologue/epilogue of a K = 128 sweep).  Pair (k, k+1):
+//   potf2(k) trsm(k) | update column k+1 with panel k | potf2(k+1) trsm(k+1)
+//   trailing(rows, cols >= k+2) -= [L_k L_k+1] [L_k L_k+1]^T
+// Look-ahead: the first two block columns of the trailing update go first, then
+// the next pair's panel chain runs on the high-priority stream while the rest
+// of the trailing update is still in flight.
 int ab_launch_factor(ab_gp* h) {
     int rc = configure_once();
     if (rc) return rc;
@@ -272,41 +283,47 @@ int ab_launch_factor(ab_gp* h) {
     AB_CUDA(cudaMemsetAsync(h->d_info, 0, sizeof(int), ms));
     ab_prof_begin(h, AB_PROF_FACTOR);
     ab_count_launches(3LL * T);
-    if (!h->lookahead || T < 3) {
-        for (int k = 0; k < T; k++) {
-            const int64_t o = (int64_t)k * NB;
-            potf2_inv_kernel<true><<<1, 256, 0, ms>>>(h->L, ld, o, h->Dinv + (int64_t)k * NB * NB, h->logdet_parts + k,
-                                                  h->d_info);
-            int nb = T - k - 1;
-            if (nb > 0) {
-                trsm_panel_kernel<<<nb, abg::THREADS, abg::SMEM_BYTES, ms>>>(h->L, ld, o, h->Dinv + (int64_t)k * NB * NB);
-                syrk_kernel<<<nb * (nb + 1) / 2, abg::THREADS, abg::SMEM_BYTES, ms>>>(h->L, ld, o, o + NB, NB, 0);
-            }
-        }
-        ab_prof_end(h, AB_PROF_FACTOR);
-        AB_CHECK_LAUNCH();
-        return 0;
-    }
-    cudaStream_t ps = h->panel_stream;
-    AB_CUDA(cudaEventRecord(h->ev_fork, ms));
-    AB_CUDA(cudaStreamWaitEvent(ps, h->ev_fork, 0));
-    potf2_inv_kernel<true><<<1, 256, 0, ps>>>(h->L, ld, 0, h->Dinv, h->logdet_parts, h->d_info);
-    trsm_panel_kernel<<<T - 1, abg::THREADS, abg::SMEM_BYTES, ps>>>(h->L, ld, 0, h->Dinv);
-    AB_CUDA(cudaEventRecord(h->ev_panel, ps));
-    for (int k = 0; k < T; k++) {
+    const bool la = h->lookahead && T >= 4;
+    cudaStream_t ps = la ? h->panel_stream : ms;
+    const int G = abg::THREADS, SM = abg::SMEM_BYTES;
+    auto Dk = [&](int k) { return h->Dinv + (int64_t)k * NB * NB; };
+    // panel chain of the pair starting at block k (its columns are fully updated)
+    auto pair_panels = [&](int k) {
         const int64_t o = (int64_t)k * NB;
-        AB_CUDA(cudaStreamWaitEvent(ms, h->ev_panel, 0));
-        int nb = T - k - 1;
-        if (nb == 0) break;
-        syrk_kernel<<<nb, abg::THREADS, abg::SMEM_BYTES, ms>>>(h->L, ld, o, o + NB, NB, 1);
+        potf2_inv_kernel<true><<<1, 256, 0, ps>>>(h->L, ld, o, Dk(k), h->logdet_parts + k, h->d_info);
+        if (T - k - 1 > 0) trsm_panel_kernel<<<T - k - 1, G, SM, ps>>>(h->L, ld, o, Dk(k));
+        if (k + 1 < T) {
+            syrk_kernel<<<T - k - 1, G, SM, ps>>>(h->L, ld, o, o + NB, NB, 1, 0);       // column k+1 -= L_k L_k^T
+            potf2_inv_kernel<true><<<1, 256, 0, ps>>>(h->L, ld, o + NB, Dk(k + 1), h->logdet_parts + k + 1, h->d_info);
+            if (T - k - 2 > 0) trsm_panel_kernel<<<T - k - 2, G, SM, ps>>>(h->L, ld, o + NB, Dk(k + 1));
+        }
+    };
+    if (la) {
+        AB_CUDA(cudaEventRecord(h->ev_fork, ms));
+        AB_CUDA(cudaStreamWaitEvent(ps, h->ev_fork, 0));
+    }
+    pair_panels(0);
+    if (la) AB_CUDA(cudaEventRecord(h->ev_panel, ps));
+    for (int k = 0; k < T; k += 2) {
+        const int64_t o = (int64_t)k * NB;
+        if (la) AB_CUDA(cudaStreamWaitEvent(ms, h->ev_panel, 0));
+        const int nt = T - k - 2;                    // block rows of the trailing matrix
+        if (nt <= 0) break;
+        const int kdim = 2 * NB;
+        if (!la) {
+            syrk_kernel<<<nt * (nt + 1) / 2, G, SM, ms>>>(h->L, ld, o, o + 2 * NB, kdim, 0, nt);
+            pair_panels(k + 2);
+            continue;
+        }
+        // (a) first two block columns of the trailing update, (b) next pair's panels, (c) the rest
+        const int nfirst = nt >= 2 ? 2 * nt - 1 : nt;
+        syrk_kernel<<<nfirst, G, SM, ms>>>(h->L, ld, o, o + 2 * NB, kdim, 2, nt);
         AB_CUDA(cudaEventRecord(h->ev_col, ms));
         AB_CUDA(cudaStreamWaitEvent(ps, h->ev_col, 0));
-        double* Dk1 = h->Dinv + (int64_t)(k + 1) * NB * NB;
-        potf2_inv_kernel<true><<<1, 256, 0, ps>>>(h->L, ld, o + NB, Dk1, h->logdet_parts + k + 1, h->d_info);
-        if (nb - 1 > 0) trsm_panel_kernel<<<nb - 1, abg::THREADS, abg::SMEM_BYTES, ps>>>(h->L, ld, o + NB, Dk1);
+        pair_panels(k + 2);
         AB_CUDA(cudaEventRecord(h->ev_panel, ps));
-        if (nb - 1 > 0)
-            syrk_kernel<<<(nb - 1) * nb / 2, abg::THREADS, abg::SMEM_BYTES, ms>>>(h->L, ld, o, o + 2 * NB, NB, 0);
+        if (nt > 2)
+            syrk_kernel<<<(nt - 2) * (nt - 1) / 2, G, SM, ms>>>(h->L, ld, o, o + 4 * NB, kdim, 0, nt - 2);
     }
     ab_prof_end(h, AB_PROF_FACTOR);
     AB_CHECK_LAUNCH();

@@ -19,6 +19,18 @@ namespace abp {
 
 constexpr int NB = AB_NB;
 
+// 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps (no slow-path call on the
+// critical path of the column sweep; x is a positive pivot here)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 template <bool FACTOR, int JR>
 __device__ __forceinline__ void sweep16(double (&a)[8][8], double (&b)[8][8], double (*colA)[NB], double (*rowB)[NB],
                                         double* sdiag, double* sinv, int tx, int ty, int64_t o, int* info) {
@@ -43,7 +55,7 @@ __device__ __forceinline__ void sweep16(double (&a)[8][8], double (&b)[8][8], do
             sdiag[j] = dj;
             sinv[j] = 1.0 / dj;
         }
-        const double ip = 1.0 / p;
+        const double ip = fast_rcp(p);
         double ai[8];
 #pragma unroll
         for (int r = JR; r < 8; r++) ai[r] = colA[buf][ty + 16 * r];

@@ -1,0 +1,112 @@
+"""Parity at BASELINE.json's full sizes (c3 N=4000, c4 N=8192 d=10, c5 N=16384
+d=20) through size-independent properties — the CPU oracle would need minutes
+to hours there:
+
+* L L^T reproduces K on sampled rows (K from K1's own builder AND from the
+  closed-form kernel on the host for the sampled entries);
+* K alpha = y - mean on sampled rows (solve correctness);
+* GP interpolation: the predictive mean at training points returns y up to the
+  white-noise shrinkage, and the predictive variance there is ~ white noise;
+* sigma^2 >= 0 within rounding and <= amp; prediction is independent of how
+  the query set is batched or sharded (bit-identical);
+* the utility argmin over a candidate set equals the argmin assembled from two
+  halves (what two GPUs would all_gather);
+* log-likelihood gradient vs central finite differences of the log-likelihood.
+"""
+import numpy as np
+import pytest
+
+from oracle import gp as ogp, benchmarks as ob
+
+pytestmark = pytest.mark.gpu
+
+
+def build(name, kind, n=None, white_noise=-6.0, ell=1.5):
+    import alabi_b200 as ab
+    c = ob.make_config(name, n_override=n)
+    b = c["bounds"]
+    X = (c["X"] - b[:, 0]) / (b[:, 1] - b[:, 0])          # unit cube like a MinMax theta scaler
+    y = c["y"]
+    d = X.shape[1]
+    log_M = np.full(d, np.log(ell ** 2))
+    k = getattr(ab.kernels, kind)(metric=np.exp(log_M), ndim=d) * np.var(y)
+    g = ab.GP(kernel=k, fit_mean=True, mean=np.median(y), white_noise=white_noise, fit_white_noise=True)
+    g.compute(X)
+    return g, X, y, log_M
+
+
+@pytest.mark.parametrize("name,kind,ell", [("c3", "Matern52Kernel", 0.2), ("c4", "ExpSquaredKernel", 1.5),
+                                           ("c5", "ExpSquaredKernel", 2.0)])
+def test_full_size_properties(name, kind, ell):
+    import torch
+    g, X, y, log_M = build(name, kind, ell=ell)
+    n, d = X.shape
+    rng = np.random.default_rng(0)
+    rows = np.sort(rng.choice(n, size=48, replace=False))
+    amp = np.exp(g.kernel.k1.log_constant)
+    wn = np.exp(g.white_noise)
+    # K rows from the closed-form kernel (oracle) for the sampled rows
+    Krows = ogp.kernel_value(kind, X[rows], X, log_M, np.log(amp))
+    Krows[np.arange(len(rows)), rows] += wn
+    L, alpha = g.export_state()
+    Lr = L[torch.from_numpy(rows).cuda()][:, :n]                      # sampled rows of L
+    LLt = (Lr @ L[:n, :n].T).cpu().numpy()                            # (L L^T)[rows, :]   (torch only as a checker)
+    assert np.max(np.abs(LLt - Krows)) < 1e-10 * amp
+    # K alpha = y - mean on the sampled rows
+    r = Krows @ alpha.cpu().numpy()
+    np.testing.assert_allclose(r, (y - g.mean)[rows], rtol=0, atol=2e-8 * np.max(np.abs(y - g.mean)))
+    # interpolation at training points
+    idx = rng.choice(n, size=2048, replace=False)
+    mu, var = g.predict(y, X[idx], return_var=True)
+    resid = np.abs(mu - y[idx])
+    assert np.max(resid) < 0.05 * np.std(y) and np.median(resid) < 5e-3 * np.std(y)
+    assert np.all(var > -1e-9 * amp) and np.all(var < 50 * wn + 1e-9 * amp)
+    # fresh points: 0 <= sigma^2 <= amp, batching/sharding invariance (bit-identical)
+    t = rng.uniform(0, 1, size=(5000, d))
+    mu_a, var_a = g.predict(y, t, return_var=True)
+    mu_b1, var_b1 = g.predict(y, t[:1777], return_var=True)
+    mu_b2, var_b2 = g.predict(y, t[1777:], return_var=True)
+    assert np.array_equal(np.concatenate([mu_b1, mu_b2]), mu_a)
+    assert np.array_equal(np.concatenate([var_b1, var_b2]), var_a)
+    assert np.all(var_a > -1e-9 * amp) and np.all(var_a <= amp * (1 + 1e-12))
+    # sharded argmin == global argmin
+    bounds = np.array([(0.0, 1.0)] * d)
+    i_all, v_all = g.utility_argmin(y, t, bounds, algorithm="bape")
+    i1, v1 = g.utility_argmin(y, t[:2500], bounds, algorithm="bape")
+    i2, v2 = g.utility_argmin(y, t[2500:], bounds, algorithm="bape")
+    cand = [(v1, i1)] + ([(v2, i2 + 2500)] if i2 >= 0 else [])
+    assert min(cand) == (v_all, i_all)
+
+
+def test_gradient_vs_finite_differences_n4000():
+    g, X, y, log_M = build("c3", "Matern32Kernel", ell=0.3)
+    p = g.get_parameter_vector()
+    grad = g.grad_log_likelihood(y)
+    for i in (0, 1, 2, 3):
+        h = 1e-5
+        pp, pm = p.copy(), p.copy()
+        pp[i] += h
+        pm[i] -= h
+        g.set_parameter_vector(pp)
+        lp = g.log_likelihood(y)
+        g.set_parameter_vector(pm)
+        lm = g.log_likelihood(y)
+        fd = (lp - lm) / (2 * h)
+        assert abs(fd - grad[i]) < 1e-4 * max(1.0, abs(grad[i])), (i, fd, grad[i])
+
+
+def test_sampler_large_ensemble_sharding_is_reproducible():
+    """c5-style ensemble (many walkers, 20-D): a sub-ensemble run with a walker
+    offset reproduces exactly when repeated, and differs from offset 0."""
+    from alabi_b200.ensemble import EnsembleSampler, SurrogateLogProb
+    g, X, y, log_M = build("c5", "ExpSquaredKernel", n=2048, ell=2.0)
+    d = X.shape[1]
+    lp = SurrogateLogProb(g, y, [(0.0, 1.0)] * d)
+    p0 = np.random.default_rng(1).uniform(0.2, 0.8, size=(4096, d))
+    runs = []
+    for off in (4096, 4096, 0):
+        s = EnsembleSampler(4096, d, lp, seed=11)
+        s.run_mcmc(p0, 5, walker_offset=off)
+        runs.append(s.get_chain())
+    assert np.array_equal(runs[0], runs[1]) and not np.array_equal(runs[0], runs[2])
+    assert np.all(np.isfinite(runs[0])) and 0.0 < s.acceptance_fraction.mean() < 1.0
