@@ -304,9 +304,14 @@ int ab_gp_log_likelihood(ab_gp* h, const double* d_y, double* h_out) {
 }
 
 int ab_gp_grad_log_likelihood(ab_gp* h, const double* d_y, double* h_out) {
-    AB_REQUIRE(h_out, -1, "null argument");
-    int rc = ab_gp_set_targets(h, d_y);
-    if (rc) return rc;
+    AB_REQUIRE(h && h_out, -1, "null argument");
+    int rc = 0;
+    if (d_y) {                       // NULL: reuse the alpha of the last ab_gp_set_targets / log_likelihood
+        rc = ab_gp_set_targets(h, d_y);
+        if (rc) return rc;
+    }
+    AB_REQUIRE(h->have_alpha, -2, "ab_gp_grad_log_likelihood: targets not set");
+    AB_CUDA(cudaSetDevice(h->device));
     rc = ensure_kinv(h);
     if (rc) return rc;
     rc = ab_launch_grad(h, nullptr);

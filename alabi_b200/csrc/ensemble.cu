@@ -15,19 +15,19 @@
 // step, stream, 0) — restated on the CPU in oracle/philox.py so a device chain
 // can be replayed exactly.  The red/blue split flips one fair coin per walker
 // pair (2i, 2i+1): balanced, position independent, no compaction needed.
+#include <stdio.h>
 #include "handle.h"
 #include "alabi_b200.h"
 
 namespace {
 
-constexpr int EW = 8;            // warps per CTA
-constexpr int ETHREADS = EW * 32;
+// warps per CTA (EW): 8; 16 was measured slower on the c2 workload (longer proposal and compute phases)
 
 struct EnsArgs {
     // state and outputs
     double* coords; double* logp; long long* naccept;
     double* chain; double* logp_chain; double* rec_q; double* rec_lp;
-    unsigned long long* barrier; int* nan_flag;
+    unsigned long long* barrier; int* nan_flag; long long* dbg;   // dbg: optional phase cycle counters (block 0)
     // surrogate
     const double* XsT; const double* alpha; long long n, npad;
     KernParams kp; double mean;
@@ -57,18 +57,6 @@ __device__ __forceinline__ double u53(unsigned hi, unsigned lo) {
     return ((double)(hi >> 5) * 67108864.0 + (double)(lo >> 6)) / 9007199254740992.0;
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long& target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += gridDim.x;
-        __threadfence();
-        atomicAdd(counter, 1ULL);
-        while (*((volatile unsigned long long*)counter) < target) { }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
 // walker of pair i that belongs to set s at this step
 __device__ __forceinline__ int member_of(const EnsArgs& A, int i, int s, unsigned step_lo) {
     int bit = 0;
@@ -77,15 +65,17 @@ __device__ __forceinline__ int member_of(const EnsArgs& A, int i, int s, unsigne
     return 2 * i + (bit ^ s);
 }
 
-template <int KIND, int D>
-__global__ void __launch_bounds__(ETHREADS)
+template <int KIND, int D, int EW>
+__global__ void __launch_bounds__(EW * 32)
 ensemble_kernel(const __grid_constant__ EnsArgs A) {
+    constexpr int ETHREADS = EW * 32;
     extern __shared__ __align__(16) double sm[];
     const int CH = A.ch;
     double* sX = sm;                 // [D][CH]
     double* sAl = sm + D * CH;       // [CH]
     __shared__ double sQ[EW][2][D], sQs[EW][2][D];
-    __shared__ double sPart[EW][2], sLogZ[EW][2], sLogU[EW][2];
+    __shared__ double sS[EW][2][D];              // current position of the walker being updated
+    __shared__ double sPart[EW][2], sLogZ[EW][2], sLogU[EW][2], sLps[EW][2];
     __shared__ int sW[EW][2], sInside[EW][2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -114,6 +104,8 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
             const int n_other = (split == 0) ? nw / 2 : (nw + 1) / 2;
             const int nbatch = (n_items + 2 * G - 1) / (2 * G);
             for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
+                long long t0 = 0, t1 = 0, t2 = 0;
+                if (A.dbg) t0 = clock64();
                 // ---- proposal (lanes 0/1 of the unit's first warp) -------------
                 if (wiu == 0 && lane < 2) {
                     const int e = lane, item = (b * G + unit) * 2 + e;
@@ -136,14 +128,17 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                                 double zz = __ddiv_rn(__dmul_rn(tz, tz), A.a);
                                 logz = (d - 1.0) * log(zz);
                                 logu = log(ua);
+                                sLps[unit][e] = __ldcg(&A.logp[w]);
                                 for (int k = 0; k < d; k++) {
                                     double c = __ldcg(&A.coords[(long long)partner * d + k]);
                                     double s = __ldcg(&A.coords[(long long)w * d + k]);
+                                    sS[unit][e][k] = s;
                                     sQ[unit][e][k] = __dsub_rn(c, __dmul_rn(__dsub_rn(c, s), zz));
                                 }
                             } else {
                                 inside = -1;     // no complementary walker: keep the state
-                                for (int k = 0; k < d; k++) sQ[unit][e][k] = __ldcg(&A.coords[(long long)w * d + k]);
+                                sLps[unit][e] = __ldcg(&A.logp[w]);
+                                for (int k = 0; k < d; k++) sS[unit][e][k] = sQ[unit][e][k] = __ldcg(&A.coords[(long long)w * d + k]);
                             }
                         }
                         for (int k = 0; k < d; k++) {
@@ -156,6 +151,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                     sW[unit][e] = w; sInside[unit][e] = inside; sLogZ[unit][e] = logz; sLogU[unit][e] = logu;
                 }
                 __syncthreads();
+                if (A.dbg) t1 = clock64();
                 // ---- surrogate mean of the two proposals of this unit ------------
                 double q0[D], q1[D];
 #pragma unroll
@@ -164,6 +160,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 for (long long c0 = 0; c0 < A.n; c0 += CH) {
                     if (!resident) { __syncthreads(); load_chunk(c0); __syncthreads(); }
                     const int cn = (int)((A.n - c0 < CH) ? (A.n - c0) : CH);
+#pragma unroll 4
                     for (int jj = wiu * 32 + lane; jj < cn; jj += 32 * WS) {
                         double r0 = 0.0, r1 = 0.0;
 #pragma unroll
@@ -182,6 +179,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 acc1 = ab_warp_sum(acc1);
                 if (lane == 0) { sPart[warp][0] = acc0; sPart[warp][1] = acc1; }
                 __syncthreads();
+                if (A.dbg) t2 = clock64();
                 // ---- accept / reject ------------------------------------------------
                 if (wiu == 0 && lane < 2) {
                     const int e = lane, w = sW[unit][e];
@@ -197,7 +195,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                         if (step < 0) {
                             A.logp[w] = lp_q;
                         } else {
-                            double lp_s = __ldcg(&A.logp[w]);
+                            double lp_s = sLps[unit][e];
                             bool acc = (inside >= 0) && ((sLogZ[unit][e] + lp_q - lp_s) > sLogU[unit][e]);
                             if (acc) {
                                 for (int k = 0; k < d; k++) A.coords[(long long)w * d + k] = sQ[unit][e][k];
@@ -213,21 +211,30 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                             if (A.chain && (step + 1) % A.thin_by == 0) {
                                 long long r = (long long)((step + 1) / A.thin_by - 1) * nw + w;
                                 for (int k = 0; k < d; k++)
-                                    A.chain[r * d + k] = acc ? sQ[unit][e][k] : __ldcg(&A.coords[(long long)w * d + k]);
+                                    A.chain[r * d + k] = acc ? sQ[unit][e][k] : sS[unit][e][k];
                                 A.logp_chain[r] = lp_s;
                             }
                         }
                     }
                 }
+                if (A.dbg && blockIdx.x == 0 && tid == 0) {
+                    long long t3 = clock64();
+                    A.dbg[0] += t1 - t0; A.dbg[1] += t2 - t1; A.dbg[2] += t3 - t2;
+                }
             }
-            grid_barrier(A.barrier, bar_target);
+            long long tb = 0;
+            if (A.dbg) { __syncthreads(); tb = clock64(); }
+            ab_grid_barrier(A.barrier, bar_target);
+            if (A.dbg && blockIdx.x == 0 && tid == 0) { A.dbg[3] += clock64() - tb; A.dbg[4] += 1; }
         }
     }
 }
 
 template <int KIND, int D>
 int launch_ens(ab_gp* h, EnsArgs& A, int nunits_half) {
-    auto kern = ensemble_kernel<KIND, D>;
+    constexpr int EW = 8;
+    constexpr int ETHREADS = EW * 32;
+    auto kern = ensemble_kernel<KIND, D, EW>;
     // shared memory: resident when the whole training set fits, else chunks
     const size_t budget = 160 * 1024;
     long long need = (long long)A.n * (D + 1) * 8;
@@ -271,7 +278,8 @@ extern "C" int ab_ensemble_run(ab_gp* h, const ab_ensemble_config* cfg, double* 
     A.chain = d_chain; A.logp_chain = d_logp_chain; A.rec_q = d_rec_q; A.rec_lp = d_rec_lp;
     A.barrier = reinterpret_cast<unsigned long long*>(h->scratch);
     A.nan_flag = reinterpret_cast<int*>(h->scratch + 1);
-    AB_CUDA(cudaMemsetAsync(h->scratch, 0, 16, h->stream));
+    A.dbg = cfg->reserved == 1 ? reinterpret_cast<long long*>(h->scratch + 16) : nullptr;
+    AB_CUDA(cudaMemsetAsync(h->scratch, 0, 256, h->stream));
     A.XsT = h->XsT; A.alpha = h->alpha; A.n = h->n; A.npad = h->npad; A.kp = h->kp; A.mean = h->mean;
     A.nwalkers = cfg->nwalkers; A.d = h->d; A.nsteps = cfg->nsteps; A.thin_by = cfg->thin_by;
     A.init_logp = cfg->init_logp; A.randomize_split = cfg->randomize_split; A.a = cfg->a;
@@ -290,7 +298,7 @@ extern "C" int ab_ensemble_run(ab_gp* h, const ab_ensemble_config* cfg, double* 
     else {
         int nsm = 148;
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-        while (ws < EW && units_half * ws * 2 <= nsm * EW) ws *= 2;
+        while (ws < 8 && units_half * ws * 2 <= nsm * 8) ws *= 2;
     }
     if (ws != 1 && ws != 2 && ws != 4 && ws != 8) { ab_set_error("warps_per_unit must be 1, 2, 4 or 8"); return -1; }
     A.ws = ws;
@@ -306,8 +314,13 @@ extern "C" int ab_ensemble_run(ab_gp* h, const ab_ensemble_config* cfg, double* 
     else AB_ENS(32);
 #undef AB_ENS
     if (rc) return rc;
-    AB_CUDA(cudaMemcpyAsync(h->h_pinned, h->scratch, 16, cudaMemcpyDeviceToHost, h->stream));
+    AB_CUDA(cudaMemcpyAsync(h->h_pinned, h->scratch, 256, cudaMemcpyDeviceToHost, h->stream));
     AB_CUDA(cudaStreamSynchronize(h->stream));
+    if (A.dbg) {
+        const long long* dd = reinterpret_cast<const long long*>(h->h_pinned + 16);
+        fprintf(stderr, "[ensemble dbg] cycles/half-step: proposal %.0f compute %.0f accept %.0f barrier %.0f (n=%lld, ws=%d)\n",
+                (double)dd[0] / dd[4], (double)dd[1] / dd[4], (double)dd[2] / dd[4], (double)dd[3] / dd[4], dd[4], A.ws);
+    }
     if (reinterpret_cast<int*>(h->h_pinned + 1)[0] != 0) {
         ab_set_error("Probability function returned NaN");
         return 1;

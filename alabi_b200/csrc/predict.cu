@@ -23,6 +23,7 @@ namespace {
 constexpr int NB = AB_NB;
 constexpr int TS = 128;        // training points per shared-memory tile
 constexpr int QPB = 256;       // queries per CTA (128 threads x 2)
+constexpr int JCHUNK = 512;    // training points per grid.y slice (fixed: results do not depend on batching)
 
 template <int KIND, int D, bool STORE>
 __global__ void __launch_bounds__(128)
@@ -43,10 +44,9 @@ predict_mean_kernel(const double* __restrict__ Xq, int64_t m, int64_t q_off, con
     // training range of this split
     const int64_t jtot = STORE ? npad : n;      // the panel also needs the (zero) padding rows
     int64_t jbeg = 0, jend = jtot;
-    if (nsplit > 1) {
-        int64_t per = ((jtot + nsplit - 1) / nsplit + TS - 1) / TS * TS;
-        jbeg = (int64_t)blockIdx.y * per;
-        jend = jbeg + per < jtot ? jbeg + per : jtot;
+    if (nsplit > 1) {            // fixed chunks of JCHUNK training points: the summation order
+        jbeg = (int64_t)blockIdx.y * JCHUNK;     // depends on N only, never on the batch size
+        jend = jbeg + JCHUNK < jtot ? jbeg + JCHUNK : jtot;
     }
     double ma = 0.0, mb = 0.0;
     for (int64_t j0 = jbeg; j0 < jend; j0 += TS) {
@@ -259,12 +259,7 @@ int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double*
     const int d = h->d;
     if (!var) {
         int64_t nblk = (m + QPB - 1) / QPB;
-        int nsplit = 1;
-        if (nblk < 296) {
-            int64_t want = (296 + nblk - 1) / nblk, maxs = (h->n + TS - 1) / TS;
-            nsplit = (int)(want < maxs ? want : maxs);
-            if (nsplit < 1) nsplit = 1;
-        }
+        const int nsplit = (int)((h->npad + JCHUNK - 1) / JCHUNK);
         double* partial = nullptr;
         const int64_t part_ld = nblk * QPB;
         if (nsplit > 1) {
@@ -297,13 +292,9 @@ int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double*
     if (m < mq) mq = m;
     const int64_t ldp = (mq + QPB - 1) / QPB * QPB;                 // multiple of 256 (and of 128)
     const int64_t nblk = ldp / QPB;
-    // split the training range over grid.y so that the panel kernel fills the GPU
-    int nsplit = 1;
-    if (nblk < 592) {
-        int64_t want = (592 + nblk - 1) / nblk, maxs = h->npad / TS;
-        nsplit = (int)(want < maxs ? want : maxs);
-        if (nsplit < 1) nsplit = 1;
-    }
+    // the training range is split over grid.y in fixed chunks (more CTAs, fixed summation order)
+    const int nsplit = (int)((h->npad + JCHUNK - 1) / JCHUNK);
+    (void)nblk;
     const size_t panel_elems = (size_t)h->npad * ldp;
     int rc = ab_ensure_scratch(h, (panel_elems + (size_t)nsplit * ldp) * sizeof(double));
     if (rc) return rc;

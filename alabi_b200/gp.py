@@ -156,8 +156,11 @@ class GP:
 
     def set_parameter_vector(self, vector, include_frozen=False):
         v = np.atleast_1d(np.asarray(vector, dtype=np.float64))
-        if len(v) != len(self.get_parameter_vector(include_frozen)):
+        cur = self.get_parameter_vector(include_frozen)
+        if len(v) != len(cur):
             raise ValueError("dimension mismatch")
+        if np.array_equal(v, cur):
+            return                       # same hyper-parameters: keep the factorisation (results are identical)
         n = 0
         if self.fit_mean or include_frozen:
             self.mean_value = float(v[n]); n += 1
@@ -319,13 +322,17 @@ class GP:
             return np.zeros(npar)
         y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
         hd = self._hd
-        self._y = y
-        self._y_dev = self._dev(y)
         d = self._x.shape[1]
         out = (ctypes.c_double * (d + 3))()
-        _lib.check(hd.lib.ab_gp_grad_log_likelihood(hd.h, _lib.ptr(self._y_dev), out), "ab_gp_grad_log_likelihood")
+        if self._targets_pushed and self._y is not None and np.array_equal(y, self._y):
+            yp = None                    # alpha of the preceding log_likelihood / predict is still valid
+        else:
+            self._y = y
+            self._y_dev = self._dev(y)
+            yp = _lib.ptr(self._y_dev)
+            self._alpha_np = None
+        _lib.check(hd.lib.ab_gp_grad_log_likelihood(hd.h, yp, out), "ab_gp_grad_log_likelihood")
         self._targets_pushed = True
-        self._alpha_np = None
         full = np.array(out[:], dtype=np.float64)
         g = []
         if self.fit_mean:

@@ -98,7 +98,8 @@ int ab_gp_set_targets(ab_gp* h, const double* d_y);
 /* gp.log_likelihood(y): -1/2 r^T K^-1 r - 1/2 logdet - n/2 ln 2pi.  alabi/core.py:1248 */
 int ab_gp_log_likelihood(ab_gp* h, const double* d_y, double* h_out);
 /* gp.grad_log_likelihood(y): h_out[0..d+2] = d/d[mean, white_noise, log_constant,
- * log_M_0..]; the caller drops frozen entries.  alabi/core.py:1261 */
+ * log_M_0..]; the caller drops frozen entries.  d_y == NULL reuses the alpha of
+ * the preceding ab_gp_set_targets / ab_gp_log_likelihood.  alabi/core.py:1261 */
 int ab_gp_grad_log_likelihood(ab_gp* h, const double* d_y, double* h_out);
 
 /* K3: gp.predict(y, t, return_var).  d_var may be NULL (mean only).

@@ -5,8 +5,8 @@ to hours there:
 * L L^T reproduces K on sampled rows (K from K1's own builder AND from the
   closed-form kernel on the host for the sampled entries);
 * K alpha = y - mean on sampled rows (solve correctness);
-* GP interpolation: the predictive mean at training points returns y up to the
-  white-noise shrinkage, and the predictive variance there is ~ white noise;
+* at training points the predictive mean equals y - wn * alpha and the
+  predictive variance lies in [0, wn] (exact GP identities);
 * sigma^2 >= 0 within rounding and <= amp; prediction is independent of how
   the query set is batched or sharded (bit-identical);
 * the utility argmin over a candidate set equals the argmin assembled from two
@@ -48,6 +48,7 @@ def test_full_size_properties(name, kind, ell):
     # K rows from the closed-form kernel (oracle) for the sampled rows
     Krows = ogp.kernel_value(kind, X[rows], X, log_M, np.log(amp))
     Krows[np.arange(len(rows)), rows] += wn
+    g._set_targets(y)
     L, alpha = g.export_state()
     Lr = L[torch.from_numpy(rows).cuda()][:, :n]                      # sampled rows of L
     LLt = (Lr @ L[:n, :n].T).cpu().numpy()                            # (L L^T)[rows, :]   (torch only as a checker)
@@ -58,9 +59,10 @@ def test_full_size_properties(name, kind, ell):
     # interpolation at training points
     idx = rng.choice(n, size=2048, replace=False)
     mu, var = g.predict(y, X[idx], return_var=True)
-    resid = np.abs(mu - y[idx])
-    assert np.max(resid) < 0.05 * np.std(y) and np.median(resid) < 5e-3 * np.std(y)
-    assert np.all(var > -1e-9 * amp) and np.all(var < 50 * wn + 1e-9 * amp)
+    # exact identities at training points: mu = y - wn * alpha, 0 <= sigma^2 = wn - wn^2 Kinv_ii <= wn
+    a_np = alpha.cpu().numpy()
+    np.testing.assert_allclose(mu, y[idx] - wn * a_np[idx], rtol=0, atol=1e-8 * np.max(np.abs(y - g.mean)))
+    assert np.all(var > -1e-9 * amp) and np.all(var < wn + 1e-9 * amp)
     # fresh points: 0 <= sigma^2 <= amp, batching/sharding invariance (bit-identical)
     t = rng.uniform(0, 1, size=(5000, d))
     mu_a, var_a = g.predict(y, t, return_var=True)
