@@ -118,6 +118,7 @@ int ab_gp_create(ab_gp** out, int device, void* cuda_stream) {
     AB_REQUIRE(prop.major == 10, -4, "alabi_b200 needs an sm_100a device (B200); found sm_%d%d", prop.major, prop.minor);
     ab_gp* h = new ab_gp();
     h->device = device;
+    h->nsm = prop.multiProcessorCount;
     h->stream = (cudaStream_t)cuda_stream;
     int lo = 0, hi = 0;
     AB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -143,6 +144,7 @@ int ab_gp_destroy(ab_gp* h) {
     for (double* b : bufs)
         if (b) cudaFree(b);
     if (h->d_info) cudaFree(h->d_info);
+    if (h->df_tasks) cudaFree(h->df_tasks);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->panel_stream) cudaStreamDestroy(h->panel_stream);
     cudaEvent_t evs[] = {h->ev_panel, h->ev_col, h->ev_fork, h->ev_join};
@@ -154,7 +156,7 @@ int ab_gp_destroy(ab_gp* h) {
 
 int ab_gp_set_lookahead(ab_gp* h, int enabled) {
     AB_REQUIRE(h, -1, "null handle");
-    h->lookahead = enabled != 0;
+    h->lookahead = enabled;
     return 0;
 }
 
@@ -256,10 +258,15 @@ int ab_gp_factor(ab_gp* h) {
     h->factored = h->have_linv = h->have_kinv = h->have_alpha = false;
     rc = ab_launch_cov(h, h->L, h->npad, 0, 1);
     if (rc) return rc;
-    rc = ab_launch_factor(h);
+    *reinterpret_cast<int*>(h->h_pinned + 9) = 0;
+    rc = (h->lookahead == 2) ? ab_launch_factor_dataflow(h) : ab_launch_factor(h);
     if (rc) return rc;
     AB_CUDA(cudaMemcpyAsync(h->h_pinned + 8, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     AB_CUDA(cudaStreamSynchronize(h->stream));
+    if (*reinterpret_cast<int*>(h->h_pinned + 9) != 0) {
+        ab_set_error("dataflow Cholesky watchdog fired (dependency wait exceeded its limit)");
+        return -5;
+    }
     h->info = *reinterpret_cast<int*>(h->h_pinned + 8);
     if (h->info != 0) {
         ab_set_error("matrix not positive definite: pivot %d", h->info);

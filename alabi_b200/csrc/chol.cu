@@ -56,6 +56,41 @@ syrk_kernel(double* __restrict__ A, int64_t ld, int64_t o, int64_t r0, int kdim,
     abg::store_tile(acc, A + (r0 + (int64_t)ti * NB) * ld + r0 + (int64_t)tj * NB, ld, -1.0, 1.0);
 }
 
+// Small-tile variants for the panel chain (the critical path of the factorisation):
+// a panel has only T-k-1 128-tiles, far fewer than 148 SMs for N <= 16384, and a
+// 128 x 128 x 128 tile alone costs >= 17 us on one SM.  64-row tiles spread the same
+// work over 2-4x more SMs.
+using Half = abg::Core<16, 3, 1, 1, 4>;     // 64 x 128 tile, 128 threads, 90 KB (2 CTAs / SM)
+using Small = abg::Core<16, 3, 1, 1, 2>;    // 64 x 64 tile, 64 threads, 60 KB (3 CTAs / SM)
+
+// in place: the CTA reads and writes its own 64 rows x 128 columns only
+__global__ void __launch_bounds__(Half::THREADS, 2)
+trsm_half_kernel(double* __restrict__ A, int64_t ld, int64_t o, const double* __restrict__ Dinv) {
+    extern __shared__ __align__(16) double smem[];
+    abg::Acc acc;
+    acc.zero();
+    double* Cp = A + (o + (int64_t)NB * (1 + (blockIdx.x >> 1)) + 64 * (blockIdx.x & 1)) * ld + o;
+    Half::mainloop<true, true>(acc, Cp, ld, Dinv, NB, NB / Half::BK, smem);
+    Half::store_tile(acc, Cp, ld, 1.0, 0.0);
+}
+
+// modes 1 and 2 of syrk_kernel on 64 x 64 sub-tiles (4 CTAs per 128-tile; the
+// strictly-upper sub-tile of a diagonal tile is skipped)
+__global__ void __launch_bounds__(Small::THREADS, 3)
+syrk_small_kernel(double* __restrict__ A, int64_t ld, int64_t o, int64_t r0, int kdim, int mode, int nt) {
+    extern __shared__ __align__(16) double smem[];
+    const int p = blockIdx.x >> 2, sm = (blockIdx.x >> 1) & 1, sn = blockIdx.x & 1;
+    int ti, tj;
+    if (mode == 1 || p < nt) { ti = p; tj = 0; }
+    else { ti = p - nt + 1; tj = 1; }
+    if (ti == tj && sn > sm) return;
+    abg::Acc acc;
+    acc.zero();
+    const int64_t row = r0 + (int64_t)ti * NB + 64 * sm, col = r0 + (int64_t)tj * NB + 64 * sn;
+    Small::mainloop<true, true>(acc, A + row * ld + o, ld, A + col * ld + o, ld, kdim / Small::BK, smem);
+    Small::store_tile(acc, A + row * ld + col, ld, -1.0, 1.0);
+}
+
 // ---------------------------------------------------------------------------
 // blocked triangular solves for z = L^-1 r and alpha = L^-T z
 // ---------------------------------------------------------------------------
@@ -329,6 +364,8 @@ int configure_once() {
     int rc = 0;
     rc |= set_smem(trsm_panel_kernel, abg::SMEM_BYTES);
     rc |= set_smem(syrk_kernel, abg::SMEM_BYTES);
+    rc |= set_smem(trsm_half_kernel, Half::SMEM_BYTES);
+    rc |= set_smem(syrk_small_kernel, Small::SMEM_BYTES);
     rc |= set_smem(trinv_kernel<1>, abg::SMEM_BYTES);
     rc |= set_smem(trinv_kernel<2>, abg::SMEM_BYTES);
     rc |= set_smem(kinv_kernel, abg::SMEM_BYTES);
@@ -366,19 +403,29 @@ int ab_launch_factor(ab_gp* h) {
     AB_CUDA(cudaMemsetAsync(h->d_info, 0, sizeof(int), ms));
     ab_prof_begin(h, AB_PROF_FACTOR);
     ab_count_launches(3LL * T);
-    const bool la = h->lookahead && T >= 4;
+    const bool la = h->lookahead != 0 && T >= 4;
     cudaStream_t ps = la ? h->panel_stream : ms;
     const int G = abg::THREADS, SM = abg::SMEM_BYTES;
     auto Dk = [&](int k) { return h->Dinv + (int64_t)k * NB * NB; };
     // panel chain of the pair starting at block k (its columns are fully updated)
+    // panel operations: 64-row tiles while a panel has fewer 128-tiles than SMs
+    auto trsm = [&](int nblk, int64_t o, const double* D) {
+        if (nblk <= 0) return;
+        if (nblk < h->nsm) trsm_half_kernel<<<2 * nblk, Half::THREADS, Half::SMEM_BYTES, ps>>>(h->L, ld, o, D);
+        else trsm_panel_kernel<<<nblk, G, SM, ps>>>(h->L, ld, o, D);
+    };
+    auto syrk_cols = [&](cudaStream_t st, int ntiles, int64_t o, int64_t r0, int kdim, int mode, int nt) {
+        if (ntiles < h->nsm) syrk_small_kernel<<<4 * ntiles, Small::THREADS, Small::SMEM_BYTES, st>>>(h->L, ld, o, r0, kdim, mode, nt);
+        else syrk_kernel<<<ntiles, G, SM, st>>>(h->L, ld, o, r0, kdim, mode, nt);
+    };
     auto pair_panels = [&](int k) {
         const int64_t o = (int64_t)k * NB;
         potf2_inv_kernel<true><<<1, 256, 0, ps>>>(h->L, ld, o, Dk(k), h->logdet_parts + k, h->d_info);
-        if (T - k - 1 > 0) trsm_panel_kernel<<<T - k - 1, G, SM, ps>>>(h->L, ld, o, Dk(k));
+        trsm(T - k - 1, o, Dk(k));
         if (k + 1 < T) {
-            syrk_kernel<<<T - k - 1, G, SM, ps>>>(h->L, ld, o, o + NB, NB, 1, 0);       // column k+1 -= L_k L_k^T
+            syrk_cols(ps, T - k - 1, o, o + NB, NB, 1, 0);                               // column k+1 -= L_k L_k^T
             potf2_inv_kernel<true><<<1, 256, 0, ps>>>(h->L, ld, o + NB, Dk(k + 1), h->logdet_parts + k + 1, h->d_info);
-            if (T - k - 2 > 0) trsm_panel_kernel<<<T - k - 2, G, SM, ps>>>(h->L, ld, o + NB, Dk(k + 1));
+            trsm(T - k - 2, o + NB, Dk(k + 1));
         }
     };
     if (la) {
@@ -400,7 +447,7 @@ int ab_launch_factor(ab_gp* h) {
         }
         // (a) first two block columns of the trailing update, (b) next pair's panels, (c) the rest
         const int nfirst = nt >= 2 ? 2 * nt - 1 : nt;
-        syrk_kernel<<<nfirst, G, SM, ms>>>(h->L, ld, o, o + 2 * NB, kdim, 2, nt);
+        syrk_cols(ms, nfirst, o, o + 2 * NB, kdim, 2, nt);
         AB_CUDA(cudaEventRecord(h->ev_col, ms));
         AB_CUDA(cudaStreamWaitEvent(ps, h->ev_col, 0));
         pair_panels(k + 2);

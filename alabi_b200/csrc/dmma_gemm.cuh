@@ -9,16 +9,12 @@
 // dimensions are chosen == 4 (mod 16) doubles so that the 16 lanes of a
 // half-warp (4 groupIDs x 4 threadID_in_group) hit 16 distinct 8-byte banks.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace abg {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 256;
-constexpr int LDK = BK + 4;            // K-major tile  [128][20]
-constexpr int LDR = 128 + 4;           // K-strided tile [16][132]
-constexpr int OPER_ELEMS = 128 * LDK;  // 2560 doubles >= 16 * 132
-constexpr int STAGE_ELEMS = 2 * OPER_ELEMS;
-constexpr int SMEM_BYTES = STAGES * STAGE_ELEMS * 8;   // 163840
+constexpr int BM = 128, BN = 128, THREADS = 256;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -34,21 +30,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
         : "d"(a), "d"(b));
 }
 
-// Copy one 128 x 16 operand chunk global -> shared (all 256 threads, 4 x 16 B each).
-template <bool KMAJOR>
-__device__ __forceinline__ void load_operand(double* s, const double* g, int64_t ld, int tid) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        int c = tid + i * THREADS;
-        if (KMAJOR) {
-            int row = c >> 3, c16 = c & 7;
-            cp_async16(s + row * LDK + c16 * 2, g + (int64_t)row * ld + c16 * 2);
-        } else {
-            int k = c >> 6, c16 = c & 63;
-            cp_async16(s + k * LDR + c16 * 2, g + (int64_t)k * ld + c16 * 2);
-        }
-    }
-}
+struct NoGate {
+    __device__ __forceinline__ void operator()(int) const {}
+};
 
 struct Acc {
     double v[8][4][2];   // [m-frag][n-frag][2]; 64x32 warp tile
@@ -60,102 +44,185 @@ struct Acc {
     }
 };
 
-// acc += A_tile(128 x nk*16) * B_tile(128 x nk*16)^T.
-//   AK: A is K-major, pointer at element [row0][k0]; else pointer at [k0][row0].
-//   BKM: same for B.
-// All 256 threads must call; smem must hold SMEM_BYTES.  Ends with the pipeline
-// drained and a __syncthreads(), so smem can be reused by the caller.
-//   TRI_A: the last 8 chunks (one 128-wide k block) multiply a LOWER-TRIANGULAR
-//   128 x 128 A block (A[r][k] = 0 for k > r): m-fragments whose rows all lie
-//   above the current k4-step are skipped (warp-uniform test).
-template <bool AK, bool BKM, bool TRI_A = false>
-__device__ __forceinline__ void mainloop(Acc& acc, const double* __restrict__ A, int64_t lda,
-                                         const double* __restrict__ B, int64_t ldb, int nk,
-                                         double* smem) {
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;          // 2 x 4 warps
-    const int64_t a_step = AK ? (int64_t)BK : (int64_t)BK * lda;
-    const int64_t b_step = BKM ? (int64_t)BK : (int64_t)BK * ldb;
+// BK_: k extent of one pipeline stage; STAGES_: cp.async ring depth; ORDER_ = 1
+// issues the first k4-step of a chunk BEFORE the prefetch of the next chunk, so
+// the tensor pipe is fed right after the barrier.
+// WM_ x WN_ warps of 64 x 32 each: CTA tile (64 WM_) x (32 WN_), 32 WM_ WN_ threads
+// (2 x 4 = the 128 x 128 tile of the big GEMMs; 1 x 2 = the 64 x 64 tile of the
+// Cholesky panel operations, which have too few 128-tiles to fill 148 SMs).
+template <int BK_, int STAGES_, int ORDER_, int WM_ = 2, int WN_ = 4>
+struct Core {
+    static constexpr int BK = BK_, STAGES = STAGES_, WM = WM_, WN = WN_, THREADS = 32 * WM * WN, MF = 8, NF = 4;
+    static constexpr int TM = 64 * WM, TN = 32 * WN;
+    static constexpr int LDK = BK + 4;            // K-major tile   [rows][BK + 4]
+    static constexpr int LDRA = TM + 4, LDRB = TN + 4;   // K-strided tiles [BK][rows + 4]
+    static constexpr int A_ELEMS = (TM * LDK > BK * LDRA) ? TM * LDK : BK * LDRA;
+    static constexpr int B_ELEMS = (TN * LDK > BK * LDRB) ? TN * LDK : BK * LDRB;
+    static constexpr int OPER_ELEMS = A_ELEMS;    // offset of the B operand inside a stage
+    static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_ELEMS * 8;
+    static constexpr int KB = 128 / BK;           // chunks per 128-wide k block
+    using Acc = abg::Acc;
+    static_assert(LDK % 16 == 4 && LDRA % 16 == 4 && LDRB % 16 == 4, "leading dimensions must be 4 (mod 16) doubles");
+    static_assert(SMEM_BYTES <= 227 * 1024, "pipeline does not fit shared memory");
+
+    // Copy one ROWS x BK operand chunk global -> shared (all threads, 16 B per cp.async).
+    template <bool KMAJOR, int ROWS>
+    static __device__ __forceinline__ void load_operand(double* s, const double* g, int64_t ld, int tid) {
+        constexpr int CHUNKS = ROWS * BK / 2, LDR = ROWS + 4;
+        static_assert(CHUNKS % THREADS == 0, "operand chunk count must divide evenly");
+        static_assert(LDR % 16 == 4, "K-strided leading dimension must be 4 (mod 16) doubles");
+#pragma unroll
+        for (int i = 0; i < CHUNKS / THREADS; i++) {
+            int c = tid + i * THREADS;
+            if (KMAJOR) {
+                int row = c / (BK / 2), c16 = c % (BK / 2);
+                cp_async16(s + row * LDK + c16 * 2, g + (int64_t)row * ld + c16 * 2);
+            } else {
+                int k = c / (ROWS / 2), c16 = c % (ROWS / 2);
+                cp_async16(s + k * LDR + c16 * 2, g + (int64_t)k * ld + c16 * 2);
+            }
+        }
+    }
+
+    // acc += A_tile(128 x nk*BK) * B_tile(128 x nk*BK)^T.
+    //   AK: A is K-major, pointer at element [row0][k0]; else pointer at [k0][row0].
+    //   BKM: same for B.
+    // All 256 threads must call; smem must hold SMEM_BYTES.  Ends with the pipeline
+    // drained and a __syncthreads(), so smem can be reused by the caller.
+    //   TRI_A: the last 128-wide k block multiplies a LOWER-TRIANGULAR 128 x 128 A
+    //   block (A[r][k] = 0 for k > r): m-fragments whose rows all lie above the
+    //   current k4-step are skipped (warp-uniform test).
+    //   gate(c) is called by every thread right before it issues the loads of chunk c
+    //   (the dataflow Cholesky waits there for the producer of that k block).
+    template <bool AK, bool BKM, bool TRI_A = false, typename Gate = NoGate>
+    static __device__ __forceinline__ void mainloop(Acc& acc, const double* __restrict__ A, int64_t lda,
+                                                    const double* __restrict__ B, int64_t ldb, int nk,
+                                                    double* smem, Gate gate = Gate()) {
+        const int tid = threadIdx.x;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int g = lane >> 2, t = lane & 3;
+        const int wm = warp / WN, wn = warp % WN;
+        const int64_t a_step = AK ? (int64_t)BK : (int64_t)BK * lda;
+        const int64_t b_step = BKM ? (int64_t)BK : (int64_t)BK * ldb;
 
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; s++) {
-        if (s < nk) {
-            load_operand<AK>(smem + s * STAGE_ELEMS, A + s * a_step, lda, tid);
-            load_operand<BKM>(smem + s * STAGE_ELEMS + OPER_ELEMS, B + s * b_step, ldb, tid);
-        }
-        cp_async_commit();
-    }
-    for (int kc = 0; kc < nk; kc++) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        {
-            int nx = kc + STAGES - 1;
-            if (nx < nk) {
-                int st = nx % STAGES;
-                load_operand<AK>(smem + st * STAGE_ELEMS, A + nx * a_step, lda, tid);
-                load_operand<BKM>(smem + st * STAGE_ELEMS + OPER_ELEMS, B + nx * b_step, ldb, tid);
+        for (int s = 0; s < STAGES - 1; s++) {
+            if (s < nk) {
+                gate(s);
+                load_operand<AK, TM>(smem + s * STAGE_ELEMS, A + s * a_step, lda, tid);
+                load_operand<BKM, TN>(smem + s * STAGE_ELEMS + OPER_ELEMS, B + s * b_step, ldb, tid);
             }
             cp_async_commit();
         }
-        const double* sA = smem + (kc % STAGES) * STAGE_ELEMS;
-        const double* sB = sA + OPER_ELEMS;
+        for (int kc = 0; kc < nk; kc++) {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();
+            const double* sA = smem + (kc % STAGES) * STAGE_ELEMS;
+            const double* sB = sA + OPER_ELEMS;
+            auto prefetch = [&]() {
+                int nx = kc + STAGES - 1;
+                if (nx < nk) {
+                    int st = nx % STAGES;
+                    gate(nx);
+                    load_operand<AK, TM>(smem + st * STAGE_ELEMS, A + nx * a_step, lda, tid);
+                    load_operand<BKM, TN>(smem + st * STAGE_ELEMS + OPER_ELEMS, B + nx * b_step, ldb, tid);
+                }
+                cp_async_commit();
+            };
+            if (ORDER_ == 0) prefetch();
+            // one k4-step: fragment loads, then 32 DMMAs (TRI: only the m-fragments that
+            // reach down to k offset `ktri` of the triangular block)
+            auto k4step = [&](int kk, auto tri, int ktri) {
+                double a[8], b[4];
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-            double a[8], b[4];
+                for (int f = 0; f < 8; f++)
+                    a[f] = AK ? sA[(wm * 64 + f * 8 + g) * LDK + kk * 4 + t]
+                              : sA[(kk * 4 + t) * LDRA + wm * 64 + f * 8 + g];
 #pragma unroll
-            for (int f = 0; f < 8; f++)
-                a[f] = AK ? sA[(wm * 64 + f * 8 + g) * LDK + kk * 4 + t]
-                          : sA[(kk * 4 + t) * LDR + wm * 64 + f * 8 + g];
+                for (int f = 0; f < 4; f++)
+                    b[f] = BKM ? sB[(wn * 32 + f * 8 + g) * LDK + kk * 4 + t]
+                               : sB[(kk * 4 + t) * LDRB + wn * 32 + f * 8 + g];
 #pragma unroll
-            for (int f = 0; f < 4; f++)
-                b[f] = BKM ? sB[(wn * 32 + f * 8 + g) * LDK + kk * 4 + t]
-                           : sB[(kk * 4 + t) * LDR + wn * 32 + f * 8 + g];
-            const int ktri = TRI_A ? (kc - (nk - 8)) * BK + kk * 4 : -1;   // k offset inside the diagonal block
+                for (int i = 0; i < 8; i++) {
+                    if (decltype(tri)::value && ktri > wm * 64 + i * 8 + 7) continue;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (TRI_A && ktri > wm * 64 + i * 8 + 7) continue;
+                    for (int j = 0; j < 4; j++) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+                }
+            };
+            if (TRI_A && kc >= nk - KB) {            // chunk inside the triangular diagonal block
+                const int k0 = (kc - (nk - KB)) * BK;
+                if (k0 > wm * 64 + 63) {             // nothing left for this warp's rows
+                    if (ORDER_ == 1) prefetch();
+                } else {
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
-            }
-        }
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-}
-
-// Element (row, col) owned by acc.v[i][j][e] inside the 128 x 128 CTA tile.
-__device__ __forceinline__ int acc_row(int i) {
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    return (warp >> 2) * 64 + i * 8 + (lane >> 2);
-}
-__device__ __forceinline__ int acc_col(int j) {
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    return (warp & 3) * 32 + j * 8 + (lane & 3) * 2;   // + e
-}
-
-// C[tile] = alpha * acc + beta * C[tile]   (C row-major, 16-byte vector accesses)
-__device__ __forceinline__ void store_tile(const Acc& acc, double* __restrict__ C, int64_t ldc,
-                                           double alpha, double beta) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        int r = acc_row(i);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            double2* p = reinterpret_cast<double2*>(C + (int64_t)r * ldc + acc_col(j));
-            double2 o;
-            if (beta != 0.0) {
-                double2 c = *p;
-                o.x = alpha * acc.v[i][j][0] + beta * c.x;
-                o.y = alpha * acc.v[i][j][1] + beta * c.y;
+                    for (int kk = 0; kk < BK / 4; kk++) {
+                        k4step(kk, std::true_type{}, k0 + kk * 4);
+                        if (ORDER_ == 1 && kk == 0) prefetch();
+                    }
+                }
             } else {
-                o.x = alpha * acc.v[i][j][0];
-                o.y = alpha * acc.v[i][j][1];
+#pragma unroll
+                for (int kk = 0; kk < BK / 4; kk++) {
+                    k4step(kk, std::false_type{}, -1);
+                    if (ORDER_ == 1 && kk == 0) prefetch();
+                }
             }
-            *p = o;
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+
+    // Element (row, col) owned by acc.v[i][j][e] inside the CTA tile.
+    static __device__ __forceinline__ int acc_row(int i) {
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        return (warp / WN) * 64 + i * 8 + (lane >> 2);
+    }
+    static __device__ __forceinline__ int acc_col(int j) {
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        return (warp % WN) * 32 + j * 8 + (lane & 3) * 2;   // + e
+    }
+
+    // C[tile] = alpha * acc + beta * C[tile]   (C row-major, 16-byte vector accesses)
+    static __device__ __forceinline__ void store_tile(const Acc& acc, double* __restrict__ C, int64_t ldc,
+                                                      double alpha, double beta) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            int r = acc_row(i);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double2* p = reinterpret_cast<double2*>(C + (int64_t)r * ldc + acc_col(j));
+                double2 o;
+                if (beta != 0.0) {
+                    double2 c = *p;
+                    o.x = alpha * acc.v[i][j][0] + beta * c.x;
+                    o.y = alpha * acc.v[i][j][1] + beta * c.y;
+                } else {
+                    o.x = alpha * acc.v[i][j][0];
+                    o.y = alpha * acc.v[i][j][1];
+                }
+                *p = o;
+            }
         }
     }
+};
+
+// configuration used by the product kernels
+using Main = Core<16, 4, 1>;            // 128 x 128 tile, 256 threads, 160 KB
+using Small = Core<16, 4, 1, 1, 2>;     // 64 x 64 tile, 64 threads, 80 KB (2 CTAs / SM)
+constexpr int BK = Main::BK, STAGES = Main::STAGES;
+constexpr int SMEM_BYTES = Main::SMEM_BYTES;
+
+template <bool AK, bool BKM, bool TRI_A = false>
+__device__ __forceinline__ void mainloop(Acc& acc, const double* __restrict__ A, int64_t lda,
+                                         const double* __restrict__ B, int64_t ldb, int nk, double* smem) {
+    Main::mainloop<AK, BKM, TRI_A>(acc, A, lda, B, ldb, nk, smem);
+}
+
+__device__ __forceinline__ int acc_row(int i) { return Main::acc_row(i); }
+__device__ __forceinline__ int acc_col(int j) { return Main::acc_col(j); }
+__device__ __forceinline__ void store_tile(const Acc& acc, double* __restrict__ C, int64_t ldc, double alpha, double beta) {
+    Main::store_tile(acc, C, ldc, alpha, beta);
 }
 
 // linear index p -> (i, j) with 0 <= j <= i  (row-major lower triangle)

@@ -9,6 +9,7 @@ enum { AB_PROF_COV = 0, AB_PROF_FACTOR = 1, AB_PROF_PREDICT_PANEL = 2, AB_PROF_P
 
 struct ab_gp {
     int device = 0;
+    int nsm = 148;                        // SM count of the device
     cudaStream_t stream = nullptr;        // caller's stream (borrowed)
     cudaStream_t panel_stream = nullptr;  // high-priority stream for look-ahead panels (owned)
     cudaEvent_t ev_panel = nullptr, ev_col = nullptr, ev_fork = nullptr, ev_join = nullptr;
@@ -46,7 +47,9 @@ struct ab_gp {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev[AB_PROF_FAMILIES];
 
-    bool lookahead = true;
+    int lookahead = 2;                    // factor schedule: 0 plain sweep, 1 look-ahead streams, 2 dataflow kernel
+    void* df_tasks = nullptr;             // dataflow task list (device) for df_tasks_T block rows
+    int df_tasks_T = 0;
     bool factored = false, have_linv = false, have_kinv = false, have_alpha = false;
     int info = 0;
     double logdet = 0.0, quad = 0.0;
@@ -66,6 +69,7 @@ int ab_launch_cross_cov(ab_gp* h, const double* AT, int64_t lda, int64_t na, con
                         int64_t nb, double* K, int64_t ld);
 // chol.cu
 int ab_launch_factor(ab_gp* h);
+int ab_launch_factor_dataflow(ab_gp* h);   // chol_dataflow.cu
 int ab_launch_rebuild_dinv(ab_gp* h);
 int ab_launch_solve_alpha(ab_gp* h, const double* y);
 int ab_launch_build_linv(ab_gp* h);

@@ -50,11 +50,7 @@ __device__ __forceinline__ void sweep16(double (&a)[8][8], double (&b)[8][8], do
             if (tx == 0 && ty == 0) atomicCAS(info, 0, (int)(o + j + 1));
             p = 1.0;
         }
-        if (tx == 0 && ty == 0) {
-            double dj = FACTOR ? sqrt(p) : p;
-            sdiag[j] = dj;
-            sinv[j] = 1.0 / dj;
-        }
+        if (tx == 0 && ty == 0) sdiag[j] = p;          // sqrt / reciprocal of the pivots: after the sweep
         const double ip = fast_rcp(p);
         double ai[8];
 #pragma unroll
@@ -120,6 +116,12 @@ potf2_inv_kernel(double* __restrict__ A, int64_t ld, int64_t o, double* __restri
     sweep16<FACTOR, 5>(a, b, colA, rowB, sdiag, sinv, tx, ty, o, info);
     sweep16<FACTOR, 6>(a, b, colA, rowB, sdiag, sinv, tx, ty, o, info);
     sweep16<FACTOR, 7>(a, b, colA, rowB, sdiag, sinv, tx, ty, o, info);
+    __syncthreads();
+    if (tid < NB) {                                   // pivots -> diagonal of L and its reciprocal
+        const double dj = FACTOR ? sqrt(sdiag[tid]) : sdiag[tid];
+        sdiag[tid] = dj;
+        sinv[tid] = 1.0 / dj;
+    }
     __syncthreads();
     if (tid < 32) {
         double s = 0.0;

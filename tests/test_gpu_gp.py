@@ -128,7 +128,10 @@ def test_pickle_copy_roundtrip():
 
 @pytest.mark.parametrize("n", [2048, 4096])
 def test_large_factor_lookahead_equals_plain(n):
-    """Look-ahead scheduling must not change a single bit of L; logL agrees with LAPACK."""
+    """The three factor schedules (0 plain sweep, 1 look-ahead streams, 2 dataflow
+    kernel) against LAPACK: look-ahead must not change a single bit of the plain
+    sweep; the dataflow kernel sums each tile in one long-K pass (different
+    rounding order) and must agree with LAPACK to the same tolerance."""
     import alabi_b200 as ab
     from alabi_b200 import _lib
     c = ob.make_config("c4", n_override=n)
@@ -137,7 +140,7 @@ def test_large_factor_lookahead_equals_plain(n):
     log_M = np.zeros(d) + 1.0
     o = ogp.make_gp("ExpSquaredKernel", X, y, log_M, amp=np.var(y), white_noise=-6.0)
     outs = []
-    for la in (1, 0):
+    for la in (1, 0, 2):
         g = ab.GP(kernel=ab.kernels.ExpSquaredKernel(metric=np.exp(log_M), ndim=d) * np.var(y),
                   fit_mean=True, mean=np.median(y), white_noise=-6.0, fit_white_noise=True)
         g._handle()
@@ -151,4 +154,7 @@ def test_large_factor_lookahead_equals_plain(n):
     ll_o = o.log_likelihood(y)
     assert abs(outs[0][0] - ll_o) <= 1e-9 * abs(ll_o)
     Lo = o._factor[0].T
-    assert np.max(np.abs(np.tril(outs[0][1])[:n, :n] - Lo)) < 1e-9 * np.max(np.abs(Lo))
+    for ll, L, alpha in outs:
+        assert abs(ll - ll_o) <= 1e-9 * abs(ll_o)
+        assert np.max(np.abs(np.tril(L)[:n, :n] - Lo)) < 1e-9 * np.max(np.abs(Lo))
+    assert np.max(np.abs(outs[2][2] - outs[0][2])) <= 1e-9 * np.max(np.abs(outs[0][2]))
