@@ -91,13 +91,18 @@ struct RowGate {
 __global__ void __launch_bounds__(Core::THREADS, 1)
 chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double colA[2][NB], rowB[2][NB], sdiag[NB], sinv[NB];
+    __shared__ abp::SweepShared sh;
     __shared__ int s_task;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3, wm = warp / Core::WN, wn = warp % Core::WN;
     Waiter w{a.prog, a.abort_flag, false};
     double* sC = smem;
     double* sBring = smem + C_ELEMS;
+    double* const sdiag = sh.sdiag;
+    double* const sinv = sh.sinv;
+    unsigned sweep_phase = 0;
+    if (tid == 0) abp::mbar_init((unsigned)__cvta_generic_to_shared(&sh.mbar), Core::THREADS);
+    __syncthreads();
 
     for (;;) {
         if (tid == 0) s_task = (int)atomicAdd(a.next_task, 1u);
@@ -146,21 +151,7 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
                         pa[r][c] = (kk <= ii) ? sC[ii * LDC + kk] : 0.0;
                         pb[r][c] = (kk == ii) ? 1.0 : 0.0;
                     }
-            abp::sweep16<true, 0>(pa, pb, colA, rowB, sdiag, sinv, tx, ty, col0, a.info);
-            abp::sweep16<true, 1>(pa, pb, colA, rowB, sdiag, sinv, tx, ty, col0, a.info);
-            abp::sweep16<true, 2>(pa, pb, colA, rowB, sdiag, sinv, tx, ty, col0, a.info);
-            abp::sweep16<true, 3>(pa, pb, colA, rowB, sdiag, sinv, tx, ty, col0, a.info);
-            abp::sweep16<true, 4>(pa, pb, colA, rowB, sdiag, sinv, tx, ty, col0, a.info);
-            abp::sweep16<true, 5>(pa, pb, colA, rowB, sdiag, sinv, tx, ty, col0, a.info);
-            abp::sweep16<true, 6>(pa, pb, colA, rowB, sdiag, sinv, tx, ty, col0, a.info);
-            abp::sweep16<true, 7>(pa, pb, colA, rowB, sdiag, sinv, tx, ty, col0, a.info);
-            __syncthreads();
-            if (tid < NB) {
-                const double dj = sqrt(sdiag[tid]);
-                sdiag[tid] = dj;
-                sinv[tid] = 1.0 / dj;
-            }
-            __syncthreads();
+            abp::potf2_sweep<true>(pa, pb, sh, tx, ty, col0, a.info, sweep_phase);
             if (tid < 32) {
                 double s = 0.0;
                 for (int q = tid; q < NB; q += 32) s += 2.0 * log(sdiag[q]);

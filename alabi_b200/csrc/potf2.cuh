@@ -13,6 +13,7 @@
 // register-array indices are static and the triangular structure prunes work at
 // compile time.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace abp {
@@ -31,53 +32,136 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return r;
 }
 
-template <bool FACTOR, int JR>
-__device__ __forceinline__ void sweep16(double (&a)[8][8], double (&b)[8][8], double (*colA)[NB], double (*rowB)[NB],
-                                        double* sdiag, double* sinv, int tx, int ty, int64_t o, int* info) {
-    for (int jm = 0; jm < 16; jm++) {
-        const int j = JR * 16 + jm, buf = jm & 1;
-        if (tx == jm) {
+// split-phase CTA barrier in shared memory (mbarrier): threads arrive right after
+// they have published the next pivot column and wait only when they need it
+__device__ __forceinline__ void mbar_init(unsigned addr, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned addr) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+struct SweepShared {
+    double colA[2][NB], rowB[2][NB], sdiag[NB], sinv[NB];
+    unsigned long long mbar;          // initialised once per kernel with count = 256
+};
+
+// One column step with in-kernel look-ahead.  Column j = 16 JR + jm was published
+// (into buffer j & 1) during step j - 1; this step first applies its update to
+// column j + 1 of A and row j + 1 of B (block index JRN), publishes them and
+// arrives on the barrier, and only then applies the bulk of the rank-1 updates,
+// so the barrier / shared-memory / reciprocal latency of step j + 1 is hidden
+// behind the bulk of step j.  JRN == 8: last column, nothing to publish.
+template <bool FACTOR, int JR, int JRN>
+__device__ __forceinline__ void potf2_step(double (&a)[8][8], double (&b)[8][8], SweepShared& sh, int jm, int tx,
+                                           int ty, int64_t o, int* info, unsigned mbar, unsigned& phase) {
+    const int j = JR * 16 + jm, buf = jm & 1;
+    mbar_wait(mbar, phase & 1u);
+    phase++;
+    double p = sh.colA[buf][j];
+    if (FACTOR && !(p > 0.0)) {                 // LAPACK dpotrf: ajj <= 0 or NaN -> info = j + 1
+        if (tx == 0 && ty == 0) atomicCAS(info, 0, (int)(o + j + 1));
+        p = 1.0;
+    }
+    if (tx == 0 && ty == 0) sh.sdiag[j] = p;    // sqrt / reciprocal of the pivots: after the sweep
+    const double ip = fast_rcp(p);
+    // everything this step reads from shared memory, before the arrive (the buffer is
+    // rewritten by step j + 1 of a faster thread only after every thread has arrived).
+    // The triangular structure is enforced by zeroing OPERANDS, not by predicating the
+    // FMAs: valid entries (A: i >= k > j, B: c <= j < i) only ever consume valid
+    // entries; entries outside those regions may hold garbage and are never read back.
+    double ai[8], ak[8], xk[8];
 #pragma unroll
-            for (int r = JR; r < 8; r++) colA[buf][ty + 16 * r] = a[r][JR];
-        }
-        if (ty == jm) {
+    for (int r = JR; r < 8; r++) ai[r] = sh.colA[buf][ty + 16 * r];
+    if (FACTOR) {
 #pragma unroll
-            for (int c = 0; c <= JR; c++) rowB[buf][tx + 16 * c] = b[JR][c];
-        }
-        __syncthreads();
-        double p = colA[buf][j];
-        if (FACTOR && !(p > 0.0)) {                 // LAPACK dpotrf: ajj <= 0 or NaN -> info = j + 1
-            if (tx == 0 && ty == 0) atomicCAS(info, 0, (int)(o + j + 1));
-            p = 1.0;
-        }
-        if (tx == 0 && ty == 0) sdiag[j] = p;          // sqrt / reciprocal of the pivots: after the sweep
-        const double ip = fast_rcp(p);
-        double ai[8];
+        for (int c = JR; c < 8; c++) ak[c] = sh.colA[buf][tx + 16 * c] * ip;
+        ak[JR] = (tx > jm) ? ak[JR] : 0.0;                      // columns k <= j are final
+    }
 #pragma unroll
-        for (int r = JR; r < 8; r++) ai[r] = colA[buf][ty + 16 * r];
+    for (int c = 0; c <= JR; c++) xk[c] = sh.rowB[buf][tx + 16 * c] * ip;
+    xk[JR] = (tx <= jm) ? xk[JR] : 0.0;                         // B[j][c] = 0 for c > j
+    const double ab_jr = (ty > jm) ? ai[JR] : 0.0;              // rows i <= j of B are final
+
+    if (JRN < 8) {
+        constexpr int N = JRN < 8 ? JRN : 7;
+        const int jn = (JRN == JR) ? jm + 1 : 0;
         if (FACTOR) {
 #pragma unroll
-            for (int c = JR; c < 8; c++) {
-                const bool col_on = (c > JR) || (tx > jm);             // k > j
-                const double ak = colA[buf][tx + 16 * c] * ip;
+            for (int r = N; r < 8; r++) a[r][N] = fma(-ai[r], ak[N], a[r][N]);
+        }
+        if (tx == jn) {
 #pragma unroll
-                for (int r = c; r < 8; r++) {
-                    const bool on = col_on && ((r > c) || (ty >= tx));  // i >= k
-                    if (on) a[r][c] = fma(-ai[r], ak, a[r][c]);
-                }
-            }
+            for (int r = N; r < 8; r++) sh.colA[buf ^ 1][ty + 16 * r] = a[r][N];
         }
 #pragma unroll
-        for (int c = 0; c <= JR; c++) {
-            const bool col_on = (c < JR) || (tx <= jm);                 // c' <= j
-            const double xk = rowB[buf][tx + 16 * c] * ip;
+        for (int c = 0; c <= JR; c++) b[N][c] = fma(-(N == JR ? ab_jr : ai[N]), xk[c], b[N][c]);
+        if (ty == jn) {
 #pragma unroll
-            for (int r = JR; r < 8; r++) {
-                const bool on = col_on && ((r > JR) || (ty > jm));      // i > j
-                if (on) b[r][c] = fma(-ai[r], xk, b[r][c]);
-            }
+            for (int c = 0; c <= N; c++) sh.rowB[buf ^ 1][tx + 16 * c] = b[N][c];
         }
+        mbar_arrive(mbar);
     }
+    if (FACTOR) {
+#pragma unroll
+        for (int c = JR; c < 8; c++)
+            if (c != JRN) {
+#pragma unroll
+                for (int r = c; r < 8; r++) a[r][c] = fma(-ai[r], ak[c], a[r][c]);
+            }
+    }
+#pragma unroll
+    for (int r = JR; r < 8; r++)
+        if (r != JRN) {
+#pragma unroll
+            for (int c = 0; c <= JR; c++) b[r][c] = fma(-(r == JR ? ab_jr : ai[r]), xk[c], b[r][c]);
+        }
+}
+
+template <bool FACTOR, int JR>
+__device__ __forceinline__ void sweep16(double (&a)[8][8], double (&b)[8][8], SweepShared& sh, int tx, int ty,
+                                        int64_t o, int* info, unsigned mbar, unsigned& phase) {
+    for (int jm = 0; jm < 15; jm++) potf2_step<FACTOR, JR, JR>(a, b, sh, jm, tx, ty, o, info, mbar, phase);
+    potf2_step<FACTOR, JR, JR + 1>(a, b, sh, 15, tx, ty, o, info, mbar, phase);
+}
+
+// Whole 128-column sweep on the register-tiled block (a: block -> unscaled L columns,
+// b: identity -> unscaled L^-1 rows).  On return sh.sdiag = diag(L), sh.sinv = 1 / diag(L)
+// (after a __syncthreads inside).  All 256 threads; `phase` is the running count of
+// completed barrier phases of sh.mbar (kept by the caller across calls).
+template <bool FACTOR>
+__device__ __forceinline__ void potf2_sweep(double (&a)[8][8], double (&b)[8][8], SweepShared& sh, int tx, int ty,
+                                            int64_t o, int* info, unsigned& phase) {
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(&sh.mbar);
+    // publish column 0 of A and row 0 of B
+    if (tx == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) sh.colA[0][ty + 16 * r] = a[r][0];
+    }
+    if (ty == 0) sh.rowB[0][tx] = b[0][0];
+    mbar_arrive(mbar);
+    sweep16<FACTOR, 0>(a, b, sh, tx, ty, o, info, mbar, phase);
+    sweep16<FACTOR, 1>(a, b, sh, tx, ty, o, info, mbar, phase);
+    sweep16<FACTOR, 2>(a, b, sh, tx, ty, o, info, mbar, phase);
+    sweep16<FACTOR, 3>(a, b, sh, tx, ty, o, info, mbar, phase);
+    sweep16<FACTOR, 4>(a, b, sh, tx, ty, o, info, mbar, phase);
+    sweep16<FACTOR, 5>(a, b, sh, tx, ty, o, info, mbar, phase);
+    sweep16<FACTOR, 6>(a, b, sh, tx, ty, o, info, mbar, phase);
+    sweep16<FACTOR, 7>(a, b, sh, tx, ty, o, info, mbar, phase);
+    __syncthreads();
+    if (threadIdx.x < NB) {                           // pivots -> diagonal of L and its reciprocal
+        const double dj = FACTOR ? sqrt(sh.sdiag[threadIdx.x]) : sh.sdiag[threadIdx.x];
+        sh.sdiag[threadIdx.x] = dj;
+        sh.sinv[threadIdx.x] = 1.0 / dj;
+    }
+    __syncthreads();
 }
 
 // FACTOR = true : grid 1; factor the block at offset o, write L (upper part zeroed),
@@ -93,8 +177,10 @@ potf2_inv_kernel(double* __restrict__ A, int64_t ld, int64_t o, double* __restri
         Dinv += (int64_t)blockIdx.x * NB * NB;
         logdet_part += blockIdx.x;
     }
-    __shared__ double colA[2][NB], rowB[2][NB], sdiag[NB], sinv[NB];
+    __shared__ SweepShared sh;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    if (tid == 0) mbar_init((unsigned)__cvta_generic_to_shared(&sh.mbar), 256);
+    __syncthreads();
     double a[8][8], b[8][8];
 #pragma unroll
     for (int r = 0; r < 8; r++)
@@ -108,21 +194,10 @@ potf2_inv_kernel(double* __restrict__ A, int64_t ld, int64_t o, double* __restri
                 b[r][c] = (k == i) ? 1.0 : 0.0;
             }
         }
-    sweep16<FACTOR, 0>(a, b, colA, rowB, sdiag, sinv, tx, ty, o, info);
-    sweep16<FACTOR, 1>(a, b, colA, rowB, sdiag, sinv, tx, ty, o, info);
-    sweep16<FACTOR, 2>(a, b, colA, rowB, sdiag, sinv, tx, ty, o, info);
-    sweep16<FACTOR, 3>(a, b, colA, rowB, sdiag, sinv, tx, ty, o, info);
-    sweep16<FACTOR, 4>(a, b, colA, rowB, sdiag, sinv, tx, ty, o, info);
-    sweep16<FACTOR, 5>(a, b, colA, rowB, sdiag, sinv, tx, ty, o, info);
-    sweep16<FACTOR, 6>(a, b, colA, rowB, sdiag, sinv, tx, ty, o, info);
-    sweep16<FACTOR, 7>(a, b, colA, rowB, sdiag, sinv, tx, ty, o, info);
-    __syncthreads();
-    if (tid < NB) {                                   // pivots -> diagonal of L and its reciprocal
-        const double dj = FACTOR ? sqrt(sdiag[tid]) : sdiag[tid];
-        sdiag[tid] = dj;
-        sinv[tid] = 1.0 / dj;
-    }
-    __syncthreads();
+    unsigned phase = 0;
+    potf2_sweep<FACTOR>(a, b, sh, tx, ty, o, info, phase);
+    double* sdiag = sh.sdiag;
+    double* sinv = sh.sinv;
     if (tid < 32) {
         double s = 0.0;
         for (int j = tid; j < NB; j += 32) s += 2.0 * log(sdiag[j]);

@@ -108,10 +108,12 @@ def cpu_reference_run(steps, warmup, sample_points=None, mcmc_steps=None):
     walker-steps/s on a bounded sample of the c2 workload."""
     from oracle import gp as ogp, emcee as oem
     try:
-        from threadpoolctl import threadpool_info
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
         cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     except Exception:  # noqa: BLE001
-        cores = os.cpu_count() or 1
+        cores = 1
     X, y, hp, bounds = workload()
     gp = ogp.OracleGP("Matern32Kernel", NDIM, hp["log_M"], log_const=np.log(hp["amp"]), mean=hp["mean"],
                       white_noise=hp["white_noise"])
