@@ -65,7 +65,25 @@ __device__ __forceinline__ int member_of(const EnsArgs& A, int i, int s, unsigne
     return 2 * i + (bit ^ s);
 }
 
-template <int KIND, int D, int EW>
+// grid barrier split in two: arrive as soon as this CTA's updates are published,
+// wait only when the next half-step needs the other CTAs' updates
+__device__ __forceinline__ void grid_arrive(unsigned long long* counter, unsigned long long& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1ULL);
+    }
+}
+__device__ __forceinline__ void grid_wait(unsigned long long* counter, unsigned long long target) {
+    if (threadIdx.x == 0) {
+        while (*((volatile unsigned long long*)counter) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int KIND, int D, int EW, int P>
 __global__ void __launch_bounds__(EW * 32)
 ensemble_kernel(const __grid_constant__ EnsArgs A) {
     constexpr int ETHREADS = EW * 32;
@@ -73,115 +91,180 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
     const int CH = A.ch;
     double* sX = sm;                 // [D][CH]
     double* sAl = sm + D * CH;       // [CH]
-    __shared__ double sQ[EW][2][D], sQs[EW][2][D];
-    __shared__ double sS[EW][2][D];              // current position of the walker being updated
-    __shared__ double sPart[EW][2], sLogZ[EW][2], sLogU[EW][2], sLps[EW][2];
-    __shared__ int sW[EW][2], sInside[EW][2];
+    // P proposals per unit (2: small ensembles, more units; 4: large ensembles, each
+    // training point read from shared memory once per 4 kernel evaluations)
+    __shared__ double sQ[EW][P][D], sQs[EW][P][D];
+    __shared__ double sS[EW][P][D];              // current position of the walker being updated
+    __shared__ double sPart[EW][P], sLogZ[EW][P], sLogU[EW][P], sLps[EW][P], sZZ[EW][P];
+    __shared__ int sW[EW][P], sInside[EW][P], sPartner[EW][P];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int WS = A.ws, G = EW / WS;
     const int unit = warp / WS, wiu = warp - unit * WS;
     const int d = A.d, nw = A.nwalkers;
     const bool resident = A.n <= CH;
+    const bool prop_lane = (wiu == 0 && lane < P);
     unsigned long long bar_target = 0;
 
-    auto load_chunk = [&](long long c0) {
-        int cn = (int)((A.n - c0 < CH) ? (A.n - c0) : CH);
+    // resident: the whole training set (rows >= n zero-filled) is loaded once
+    auto load_resident = [&]() {
         for (int idx = tid; idx < D * CH; idx += ETHREADS) {
             int k = idx / CH, jj = idx - k * CH;
-            sX[idx] = (k < d && jj < cn) ? A.XsT[(long long)k * A.npad + c0 + jj] : 0.0;
+            sX[idx] = (k < d && jj < A.n) ? A.XsT[(long long)k * A.npad + jj] : 0.0;
         }
-        for (int jj = tid; jj < CH; jj += ETHREADS) sAl[jj] = (jj < cn) ? A.alpha[c0 + jj] : 0.0;
+        for (int jj = tid; jj < CH; jj += ETHREADS) sAl[jj] = (jj < A.n) ? A.alpha[jj] : 0.0;
     };
-    if (resident) { load_chunk(0); __syncthreads(); }
+    // streamed: chunks of CH points (CH divides npad; padding rows of XsT and alpha
+    // are zero) through a double-buffered cp.async ring: buffer = [D][CH] + [CH]
+    const int BUF = (D + 1) * CH;
+    auto issue_chunk = [&](long long c0, int buf) {
+        double* bX = sm + buf * BUF;
+        for (int idx = tid; idx < (D + 1) * (CH / 2); idx += ETHREADS) {
+            int k = idx / (CH / 2), j2 = (idx - k * (CH / 2)) * 2;
+            const double* src = (k < D) ? ((k < d) ? A.XsT + (long long)k * A.npad + c0 + j2 : nullptr)
+                                        : A.alpha + c0 + j2;
+            double* dst = bX + k * CH + j2;
+            if (src) {
+                unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+            } else {
+                dst[0] = 0.0; dst[1] = 0.0;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (resident) { load_resident(); __syncthreads(); }
+
+    // Everything of a proposal that depends on the random stream only (which walker,
+    // which partner, the stretch factor, the accept threshold): computed by the
+    // proposal lanes BEFORE they wait on the grid barrier of the previous half-step.
+    auto prep = [&](int step, int split, int b) {
+        if (!prop_lane) return;
+        const int e = lane, item = (b * G + unit) * P + e;
+        const int n_items = (step < 0) ? nw : (split == 0 ? (nw + 1) / 2 : nw / 2);
+        const int n_other = (split == 0) ? nw / 2 : (nw + 1) / 2;
+        int w = -1, partner = -1;
+        double zz = 1.0, logz = 0.0, logu = 0.0;
+        if (item < n_items) {
+            if (step < 0) {
+                w = item;
+            } else {
+                const unsigned step_lo = (unsigned)(A.first_step + step);
+                w = member_of(A, item, split, step_lo);
+                if (n_other > 0) {
+                    const unsigned gw = (unsigned)(A.walker_offset + w);
+                    U4 rp = philox4x32_10(gw, step_lo, AB_STREAM_PARTNER, 0, A.seed_lo, A.seed_hi);
+                    int jj = (int)__umulhi(rp.x, (unsigned)n_other);
+                    partner = member_of(A, jj, 1 - split, step_lo);
+                    U4 rm = philox4x32_10(gw, step_lo, AB_STREAM_MOVE, 0, A.seed_lo, A.seed_hi);
+                    double uz = u53(rm.x, rm.y), ua = u53(rm.z, rm.w);
+                    double tz = __dadd_rn(__dmul_rn(A.a - 1.0, uz), 1.0);
+                    zz = __ddiv_rn(__dmul_rn(tz, tz), A.a);
+                    logz = (d - 1.0) * log(zz);
+                    logu = log(ua);
+                }
+            }
+        }
+        sW[unit][e] = w; sPartner[unit][e] = partner; sZZ[unit][e] = zz; sLogZ[unit][e] = logz; sLogU[unit][e] = logu;
+    };
 
     const int first = A.init_logp ? -1 : 0;
+    if (first < A.nsteps) prep(first, 0, blockIdx.x);
     for (int step = first; step < A.nsteps; step++) {
-        const unsigned step_lo = (unsigned)(A.first_step + (step < 0 ? 0 : step));
         const int nsplit = (step < 0) ? 1 : 2;
         for (int split = 0; split < nsplit; split++) {
             const int n_items = (step < 0) ? nw : (split == 0 ? (nw + 1) / 2 : nw / 2);
-            const int n_other = (split == 0) ? nw / 2 : (nw + 1) / 2;
-            const int nbatch = (n_items + 2 * G - 1) / (2 * G);
+            const int nbatch = (n_items + P * G - 1) / (P * G);
             for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
                 long long t0 = 0, t1 = 0, t2 = 0;
                 if (A.dbg) t0 = clock64();
-                // ---- proposal (lanes 0/1 of the unit's first warp) -------------
-                if (wiu == 0 && lane < 2) {
-                    const int e = lane, item = (b * G + unit) * 2 + e;
-                    int w = -1, inside = 1;
-                    double logz = 0.0, logu = 0.0;
-                    if (item < n_items) {
-                        if (step < 0) {
-                            w = item;
-                            for (int k = 0; k < d; k++) sQ[unit][e][k] = __ldcg(&A.coords[(long long)w * d + k]);
-                        } else {
-                            w = member_of(A, item, split, step_lo);
-                            if (n_other > 0) {
-                                const unsigned gw = (unsigned)(A.walker_offset + w);
-                                U4 rp = philox4x32_10(gw, step_lo, AB_STREAM_PARTNER, 0, A.seed_lo, A.seed_hi);
-                                int jj = (int)__umulhi(rp.x, (unsigned)n_other);
-                                int partner = member_of(A, jj, 1 - split, step_lo);
-                                U4 rm = philox4x32_10(gw, step_lo, AB_STREAM_MOVE, 0, A.seed_lo, A.seed_hi);
-                                double uz = u53(rm.x, rm.y), ua = u53(rm.z, rm.w);
-                                double tz = __dadd_rn(__dmul_rn(A.a - 1.0, uz), 1.0);
-                                double zz = __ddiv_rn(__dmul_rn(tz, tz), A.a);
-                                logz = (d - 1.0) * log(zz);
-                                logu = log(ua);
-                                sLps[unit][e] = __ldcg(&A.logp[w]);
-                                for (int k = 0; k < d; k++) {
-                                    double c = __ldcg(&A.coords[(long long)partner * d + k]);
-                                    double s = __ldcg(&A.coords[(long long)w * d + k]);
-                                    sS[unit][e][k] = s;
-                                    sQ[unit][e][k] = __dsub_rn(c, __dmul_rn(__dsub_rn(c, s), zz));
-                                }
-                            } else {
-                                inside = -1;     // no complementary walker: keep the state
-                                sLps[unit][e] = __ldcg(&A.logp[w]);
-                                for (int k = 0; k < d; k++) sS[unit][e][k] = sQ[unit][e][k] = __ldcg(&A.coords[(long long)w * d + k]);
-                            }
+                if (b != (int)blockIdx.x) prep(step, split, b);      // extra batches of this CTA: inline
+                // ---- gather (proposal lanes): own state and partner position, proposal ----
+                if (prop_lane) {
+                    const int e = lane, w = sW[unit][e], partner = sPartner[unit][e];
+                    int inside = 1;
+                    if (w >= 0) {
+                        // all global loads first (one L2 round trip), then the arithmetic
+                        double cs[D], ss[D];
+                        const long long ow = (long long)w * d, op = (long long)(partner >= 0 ? partner : w) * d;
+#pragma unroll
+                        for (int k = 0; k < D; k++) {
+                            ss[k] = (k < d) ? __ldcg(&A.coords[ow + k]) : 0.0;
+                            cs[k] = (k < d) ? __ldcg(&A.coords[op + k]) : 0.0;
                         }
-                        for (int k = 0; k < d; k++) {
-                            double q = sQ[unit][e][k];
-                            if (inside >= 0 && !((q > A.lo[k]) && (q < A.hi[k]))) inside = 0;
-                            sQs[unit][e][k] = fma(q, A.t_scale[k], A.t_off[k]) * A.kp.inv_len[k];
+                        if (step >= 0) sLps[unit][e] = __ldcg(&A.logp[w]);
+                        const double zz = sZZ[unit][e];
+                        if (step >= 0 && partner < 0) inside = -1;      // no complementary walker: keep the state
+#pragma unroll
+                        for (int k = 0; k < D; k++) {
+                            if (k < d) {
+                                // step < 0 or no partner: cs == ss, the proposal is the current position
+                                const double q = (step >= 0 && partner >= 0)
+                                                     ? __dsub_rn(cs[k], __dmul_rn(__dsub_rn(cs[k], ss[k]), zz)) : ss[k];
+                                sS[unit][e][k] = ss[k];
+                                sQ[unit][e][k] = q;
+                                if (inside >= 0 && !((q > A.lo[k]) && (q < A.hi[k]))) inside = 0;
+                                sQs[unit][e][k] = fma(q, A.t_scale[k], A.t_off[k]) * A.kp.inv_len[k];
+                            }
                         }
                     }
                     for (int k = (w < 0 ? 0 : d); k < D; k++) { sQ[unit][e][k] = 0.0; sQs[unit][e][k] = 0.0; }
-                    sW[unit][e] = w; sInside[unit][e] = inside; sLogZ[unit][e] = logz; sLogU[unit][e] = logu;
+                    sInside[unit][e] = inside;
                 }
                 __syncthreads();
                 if (A.dbg) t1 = clock64();
                 // ---- surrogate mean of the two proposals of this unit ------------
-                double q0[D], q1[D];
+                double q[P][D], acc[P];
 #pragma unroll
-                for (int k = 0; k < D; k++) { q0[k] = sQs[unit][0][k]; q1[k] = sQs[unit][1][k]; }
-                double acc0 = 0.0, acc1 = 0.0;
-                for (long long c0 = 0; c0 < A.n; c0 += CH) {
-                    if (!resident) { __syncthreads(); load_chunk(c0); __syncthreads(); }
-                    const int cn = (int)((A.n - c0 < CH) ? (A.n - c0) : CH);
-#pragma unroll 4
+                for (int e = 0; e < P; e++) {
+                    acc[e] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; k++) q[e][k] = sQs[unit][e][k];
+                }
+                auto eval_points = [&](const double* bX, const double* bAl, int cn) {
+#pragma unroll 2
                     for (int jj = wiu * 32 + lane; jj < cn; jj += 32 * WS) {
-                        double r0 = 0.0, r1 = 0.0;
+                        double r[P];
+#pragma unroll
+                        for (int e = 0; e < P; e++) r[e] = 0.0;
 #pragma unroll
                         for (int k = 0; k < D; k++) {
-                            double x = sX[k * CH + jj];
-                            double d0 = q0[k] - x, d1 = q1[k] - x;
-                            r0 = fma(d0, d0, r0);
-                            r1 = fma(d1, d1, r1);
+                            const double x = bX[k * CH + jj];
+#pragma unroll
+                            for (int e = 0; e < P; e++) {
+                                const double df = q[e][k] - x;
+                                r[e] = fma(df, df, r[e]);
+                            }
                         }
-                        const double al = sAl[jj];
-                        acc0 = fma(ab_radial<KIND>(r0), al, acc0);
-                        acc1 = fma(ab_radial<KIND>(r1), al, acc1);
+                        const double al = bAl[jj];
+#pragma unroll
+                        for (int e = 0; e < P; e++) acc[e] = fma(ab_radial<KIND>(r[e]), al, acc[e]);
+                    }
+                };
+                if (resident) {
+                    eval_points(sX, sAl, (int)A.n);
+                } else {
+                    const int nch = (int)(A.npad / CH);
+                    issue_chunk(0, 0);
+                    for (int c = 0; c < nch; c++) {
+                        if (c + 1 < nch) issue_chunk((long long)(c + 1) * CH, (c + 1) & 1);
+                        else asm volatile("cp.async.commit_group;" ::: "memory");
+                        asm volatile("cp.async.wait_group 1;" ::: "memory");
+                        __syncthreads();
+                        const double* bX = sm + (c & 1) * BUF;
+                        eval_points(bX, bX + D * CH, CH);
+                        __syncthreads();             // buffer c & 1 is refilled by chunk c + 2
                     }
                 }
-                acc0 = ab_warp_sum(acc0);
-                acc1 = ab_warp_sum(acc1);
-                if (lane == 0) { sPart[warp][0] = acc0; sPart[warp][1] = acc1; }
+#pragma unroll
+                for (int e = 0; e < P; e++) {
+                    acc[e] = ab_warp_sum(acc[e]);
+                    if (lane == 0) sPart[warp][e] = acc[e];
+                }
                 __syncthreads();
                 if (A.dbg) t2 = clock64();
                 // ---- accept / reject ------------------------------------------------
-                if (wiu == 0 && lane < 2) {
+                if (prop_lane) {
                     const int e = lane, w = sW[unit][e];
                     if (w >= 0) {
                         double s = 0.0;
@@ -200,7 +283,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                             if (acc) {
                                 for (int k = 0; k < d; k++) A.coords[(long long)w * d + k] = sQ[unit][e][k];
                                 A.logp[w] = lp_q;
-                                A.naccept[w] += 1;
+                                atomicAdd(reinterpret_cast<unsigned long long*>(A.naccept + w), 1ULL);
                                 lp_s = lp_q;
                             }
                             if (A.rec_q && inside >= 0) {
@@ -221,37 +304,52 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                     long long t3 = clock64();
                     A.dbg[0] += t1 - t0; A.dbg[1] += t2 - t1; A.dbg[2] += t3 - t2;
                 }
+                // the proposal lanes own sW.. of their unit: the next prep / gather by the same
+                // lanes follows in program order; sQs / sPart readers are fenced by the two
+                // __syncthreads above and the one that opens grid_arrive / the next gather
+                if (b + (int)gridDim.x < nbatch) __syncthreads();
             }
             long long tb = 0;
             if (A.dbg) { __syncthreads(); tb = clock64(); }
-            ab_grid_barrier(A.barrier, bar_target);
+            grid_arrive(A.barrier, bar_target);
+            {   // random-stream part of the next half-step, overlapped with the barrier
+                int nstep = step, nsp = split + 1;
+                if (nsp >= nsplit) { nstep = step + 1; nsp = 0; }
+                if (nstep < A.nsteps) prep(nstep, nsp, blockIdx.x);
+            }
+            grid_wait(A.barrier, bar_target);
             if (A.dbg && blockIdx.x == 0 && tid == 0) { A.dbg[3] += clock64() - tb; A.dbg[4] += 1; }
         }
     }
 }
 
-template <int KIND, int D>
-int launch_ens(ab_gp* h, EnsArgs& A, int nunits_half) {
+template <int KIND, int D, int P>
+int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
     constexpr int EW = 8;
     constexpr int ETHREADS = EW * 32;
-    auto kern = ensemble_kernel<KIND, D, EW>;
-    // shared memory: resident when the whole training set fits, else chunks
+    auto kern = ensemble_kernel<KIND, D, EW, P>;
+    // shared memory: resident when the whole training set fits, else two chunk buffers
     const size_t budget = 160 * 1024;
     long long need = (long long)A.n * (D + 1) * 8;
     int ch;
-    if ((size_t)need <= budget) ch = (int)((A.n + 31) / 32 * 32);
-    else { ch = (int)(64 * 1024 / ((D + 1) * 8)); ch = ch / 32 * 32; }
-    if (ch < 32) ch = 32;
+    size_t smem;
+    if ((size_t)need <= budget) {
+        ch = (int)((A.n + 31) / 32 * 32);
+        if (ch < 32) ch = 32;
+        smem = (size_t)ch * (D + 1) * 8;
+    } else {
+        ch = 128;                                   // divides npad; two buffers of at most ~48 KB each
+        while (ch * 2 <= 512 && A.npad % (ch * 2) == 0 && (size_t)(ch * 2) * (D + 1) * 8 <= 48 * 1024) ch *= 2;
+        smem = 2 * (size_t)ch * (D + 1) * 8;
+    }
     A.ch = ch;
-    size_t smem = (size_t)ch * (D + 1) * 8;
     AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0, nsm = 0;
+    int per_sm = 0;
     AB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ETHREADS, smem));
-    AB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
     if (per_sm < 1) { ab_set_error("ensemble kernel does not fit on an SM (smem %zu)", smem); return -3; }
     int G = EW / A.ws;
-    int nbatch = (nunits_half + G - 1) / G;
-    int grid = per_sm * nsm;
+    int nbatch = (n_half + P * G - 1) / (P * G);
+    int grid = per_sm * h->nsm;
     if (grid > nbatch) grid = nbatch;
     if (grid < 1) grid = 1;
     void* args[] = {(void*)&A};
@@ -260,6 +358,13 @@ int launch_ens(ab_gp* h, EnsArgs& A, int nunits_half) {
     ab_prof_end(h, AB_PROF_ENSEMBLE);
     ab_count_launches(1);
     return 0;
+}
+
+// n_half: proposals of the larger half-step (or all walkers for a log-prob-only call)
+template <int KIND, int D>
+int launch_ens(ab_gp* h, EnsArgs& A, int n_half, int p) {
+    if (D <= 24 && p == 4) return launch_ens_p<KIND, (D <= 24 ? D : 2), 4>(h, A, n_half);
+    return launch_ens_p<KIND, D, 2>(h, A, n_half);
 }
 
 }  // namespace
@@ -290,20 +395,21 @@ extern "C" int ab_ensemble_run(ab_gp* h, const ab_ensemble_config* cfg, double* 
         A.t_scale[k] = cfg->theta_scale[k]; A.t_off[k] = cfg->theta_offset[k];
     }
     A.y_kind = cfg->y_kind; A.y_scale = cfg->y_scale; A.y_off = cfg->y_offset;
-    // warps per unit: aim at >= 8 warps per SM
-    int units_half = ((cfg->nwalkers + 1) / 2 + 1) / 2;
-    if (cfg->init_logp && cfg->nsteps == 0) units_half = (cfg->nwalkers + 1) / 2;
+    // proposals per half-step; P = 4 per unit once 2 per unit would need several passes per CTA
+    int n_half = (cfg->nwalkers + 1) / 2;
+    if (cfg->init_logp && cfg->nsteps == 0) n_half = cfg->nwalkers;
+    const int nsm = h->nsm;
+    int p = (h->d <= 24 && n_half >= 16 * nsm) ? 4 : 2;
+    if (cfg->reserved >= 2) p = (cfg->reserved == 4 && h->d <= 24) ? 4 : 2;        // development override
+    // warps per unit: all 8 warps on one unit while that still fills the GPU
+    const int units_half = (n_half + p - 1) / p;
     int ws = 1;
     if (cfg->warps_per_unit > 0) ws = cfg->warps_per_unit;
-    else {
-        int nsm = 148;
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-        while (ws < 8 && units_half * ws * 2 <= nsm * 8) ws *= 2;
-    }
+    else while (ws < 8 && units_half * ws <= nsm * 8) ws *= 2;
     if (ws != 1 && ws != 2 && ws != 4 && ws != 8) { ab_set_error("warps_per_unit must be 1, 2, 4 or 8"); return -1; }
     A.ws = ws;
     const int d = h->d;
-#define AB_ENS(DD) AB_DISPATCH_KIND(h->kp.kind, rc = (launch_ens<KIND, DD>(h, A, units_half)))
+#define AB_ENS(DD) AB_DISPATCH_KIND(h->kp.kind, rc = (launch_ens<KIND, DD>(h, A, n_half, p)))
     if (d <= 2) AB_ENS(2);
     else if (d <= 4) AB_ENS(4);
     else if (d <= 8) AB_ENS(8);

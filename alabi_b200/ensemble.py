@@ -152,8 +152,15 @@ class EnsembleSampler:
         self._step_counter += total
         self._naccepted += nacc.cpu().numpy()
         if store:
-            self._chain = np.concatenate([self._chain, chain.cpu().numpy()])
-            self._log_prob = np.concatenate([self._log_prob, lpc.cpu().numpy()])
+            # device -> pinned host staging (torch's caching host allocator reuses the block);
+            # a first run adopts the staging array instead of copying it again
+            def to_host(t):
+                hbuf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                hbuf.copy_(t)
+                return hbuf.numpy()
+            ch, lh = to_host(chain), to_host(lpc)
+            self._chain = ch if len(self._chain) == 0 else np.concatenate([self._chain, ch])
+            self._log_prob = lh if len(self._log_prob) == 0 else np.concatenate([self._log_prob, lh])
             self.iteration += int(nsteps)
         if record_proposals:
             self.proposal_record = (rq.cpu().numpy(), rl.cpu().numpy())

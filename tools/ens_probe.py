@@ -9,8 +9,8 @@ k = ab.kernels.Matern32Kernel(metric=np.full(2, 9.0), ndim=2) * np.var(y)
 g = ab.GP(kernel=k, fit_mean=True, mean=np.median(y), white_noise=-8.0, fit_white_noise=True)
 g.compute(X)
 lp = SurrogateLogProb(g, y, [(-6, 6), (-6, 6)])
-for wpu in (4, 8):
-    for dbg in (1, 0):
+for wpu in (0, 4, 8):
+    for dbg in (1, 0, 4):
         s = EnsembleSampler(1000, 2, lp, seed=1, warps_per_unit=wpu)
         s.debug_timing = dbg
         s.run_mcmc(rng.uniform(-5, 5, size=(1000, 2)), 50, store=False)
@@ -26,9 +26,11 @@ k = ab.kernels.ExpSquaredKernel(metric=np.full(d, 4.0), ndim=d) * np.var(y)
 g = ab.GP(kernel=k, fit_mean=True, mean=np.median(y), white_noise=-6.0, fit_white_noise=True)
 g.compute(X)
 lp = SurrogateLogProb(g, y, [(0, 1)] * d)
-s = EnsembleSampler(nw, d, lp, seed=1)
-s.run_mcmc(rng.uniform(0.3, 0.7, size=(nw, d)), 2, store=False)
-s.run_mcmc(None, 20, store=False)
-ws = nw * 20 / s.last_run_device_seconds
-print(json.dumps({"c5_like": True, "walker_steps_per_s": ws, "fp64_instr_rate_frac": ws * n * (2 * d + 22) / 1.8e13,
-                  "acc": float(s.acceptance_fraction.mean())}), flush=True)
+for pp in (2, 4, 0):
+    s = EnsembleSampler(nw, d, lp, seed=1)
+    s.debug_timing = pp
+    s.run_mcmc(rng.uniform(0.3, 0.7, size=(nw, d)), 2, store=False)
+    s.run_mcmc(None, 20, store=False)
+    ws = nw * 20 / s.last_run_device_seconds
+    print(json.dumps({"c5_like": True, "P": pp, "walker_steps_per_s": ws, "fp64_instr_rate_frac": ws * n * (2 * d + 22) / 1.8e13,
+                      "acc": float(s.acceptance_fraction.mean())}), flush=True)
