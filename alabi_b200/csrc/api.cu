@@ -280,9 +280,14 @@ int ab_gp_set_targets(ab_gp* h, const double* d_y) {
     AB_REQUIRE(h && d_y, -1, "ab_gp_set_targets: null argument");
     AB_REQUIRE(h->factored, -2, "ab_gp_set_targets: not factorised (call ab_gp_factor)");
     AB_CUDA(cudaSetDevice(h->device));
+    *reinterpret_cast<int*>(h->h_pinned + 10) = 0;
     int rc = ab_launch_solve_alpha(h, d_y);
     if (rc) return rc;
     AB_CUDA(cudaStreamSynchronize(h->stream));
+    if (*reinterpret_cast<int*>(h->h_pinned + 10) != 0) {
+        ab_set_error("dataflow triangular solve watchdog fired (dependency wait exceeded its limit)");
+        return -5;
+    }
     h->quad = h->h_pinned[0];
     h->logdet = h->h_pinned[1];
     h->have_alpha = true;

@@ -162,89 +162,6 @@ trsv_bwd_kernel(const double* __restrict__ L, int64_t ld, const double* __restri
     z[cb + tid] -= s0 + s1;
 }
 
-// out[row] = sum_c M[row][c] x[c] for the 16 rows {warp + 8 i} of a 128 x 128 block
-// (all 64 loads of the warp issued before the first use); dst != nullptr:
-// dst[row] -= result (read through L2), else result -> out.
-__device__ __forceinline__ void gemv_rows16(const double* __restrict__ M, int64_t ldm, const double* x, double* out,
-                                            double* dst, int warp, int lane) {
-    double v[16][4];
-#pragma unroll
-    for (int i = 0; i < 16; i++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) v[i][c] = M[(int64_t)(warp + 8 * i) * ldm + lane + 32 * c];
-    double xv[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) xv[c] = x[lane + 32 * c];
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        double s = v[i][0] * xv[0];
-        s = fma(v[i][1], xv[1], s);
-        s = fma(v[i][2], xv[2], s);
-        s = fma(v[i][3], xv[3], s);
-        s = ab_warp_sum(s);
-        if (lane == 0) {
-            const int row = warp + 8 * i;
-            if (dst) dst[row] = __ldcg(&dst[row]) - s;
-            else out[row] = s;
-        }
-    }
-}
-
-// y[col] = sum_c M[c][col] x[c] over a 128 x 128 block, one column per thread (tid < 128)
-__device__ __forceinline__ double gemv_col(const double* __restrict__ M, int64_t ldm, const double* x, int col) {
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-    for (int c = 0; c < NB; c += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; u++) s[u] = fma(M[(int64_t)(c + u) * ldm + col], x[c + u], s[u]);
-    }
-    return (s[0] + s[1]) + (s[2] + s[3]);
-}
-
-// Both triangular solves in ONE cooperative kernel (a grid barrier per block
-// step instead of a kernel launch): forward z = L^-1 r, then alpha = L^-T z.
-// r (npad) is consumed: it serves as the running right-hand side of both sweeps.
-__global__ void __launch_bounds__(256)
-trsv_coop_kernel(const double* __restrict__ L, int64_t ld, const double* __restrict__ Dinv, int T,
-                 double* r, double* z, double* alpha, unsigned long long* bar) {
-    __shared__ double sr[NB], sz[NB];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned long long target = 0;
-    for (int k = 0; k < T; k++) {
-        const int64_t o = (int64_t)k * NB;
-        if (tid < NB) sr[tid] = __ldcg(&r[o + tid]);
-        __syncthreads();
-        const double* D = Dinv + (int64_t)k * NB * NB;
-        gemv_rows16(D, NB, sr, sz, nullptr, warp, lane);
-        __syncthreads();
-        if (blockIdx.x == 0 && tid < NB) z[o + tid] = sz[tid];
-        for (int b = k + 1 + blockIdx.x; b < T; b += gridDim.x) {
-            const int64_t rb = (int64_t)b * NB;
-            gemv_rows16(L + rb * ld + o, ld, sz, nullptr, r + rb, warp, lane);
-        }
-        ab_grid_barrier(bar, target);
-    }
-    // r := z  (running right-hand side of the backward sweep)
-    for (int64_t i = (int64_t)blockIdx.x * 256 + tid; i < (int64_t)T * NB; i += (int64_t)gridDim.x * 256) r[i] = __ldcg(&z[i]);
-    ab_grid_barrier(bar, target);
-    for (int k = T - 1; k >= 0; k--) {
-        const int64_t o = (int64_t)k * NB;
-        if (tid < NB) sr[tid] = __ldcg(&r[o + tid]);
-        __syncthreads();
-        const double* D = Dinv + (int64_t)k * NB * NB;
-        if (tid < NB) sz[tid] = gemv_col(D, NB, sr, tid);
-        __syncthreads();
-        if (blockIdx.x == 0 && tid < NB) alpha[o + tid] = sz[tid];
-        for (int cb = blockIdx.x; cb < k; cb += gridDim.x) {
-            if (tid < NB) {
-                double s = gemv_col(L + o * ld + (int64_t)cb * NB, ld, sz, tid);
-                r[(int64_t)cb * NB + tid] = __ldcg(&r[(int64_t)cb * NB + tid]) - s;
-            }
-        }
-        ab_grid_barrier(bar, target);
-    }
-}
-
 __global__ void residual_kernel(const double* __restrict__ y, int64_t n, int64_t npad, double mean,
                                 double* __restrict__ r) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -476,19 +393,9 @@ int ab_launch_solve_alpha(ab_gp* h, const double* y) {
     const int64_t ld = h->npad;
     cudaStream_t s = h->stream;
     residual_kernel<<<(unsigned)((h->npad + 255) / 256), 256, 0, s>>>(y, h->n, h->npad, h->mean, h->work);
-    if (T >= 3) {
-        int nsm = 148;
-        AB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
-        int grid = T - 1 < nsm ? T - 1 : nsm;
-        unsigned long long* bar = reinterpret_cast<unsigned long long*>(h->scratch + 8);
-        AB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned long long), s));
-        const double* Lc = h->L;
-        const double* Dc = h->Dinv;
-        int Tt = T;
-        int64_t ldc = ld;
-        double *rw = h->work, *zz = h->z, *aa = h->alpha;
-        void* args[] = {(void*)&Lc, (void*)&ldc, (void*)&Dc, (void*)&Tt, (void*)&rw, (void*)&zz, (void*)&aa, (void*)&bar};
-        AB_CUDA(cudaLaunchCooperativeKernel((void*)trsv_coop_kernel, dim3(grid), dim3(256), args, 0, s));
+    if (T >= 2) {
+        int rc = ab_launch_trsv_dataflow(h, h->work);          // both sweeps, one cooperative launch
+        if (rc) return rc;
     } else {
         for (int k = 0; k < T; k++) trsv_fwd_kernel<<<T - k, 256, 0, s>>>(h->L, ld, h->Dinv, k, h->work, h->z);
         AB_CUDA(cudaMemcpyAsync(h->work, h->z, h->npad * sizeof(double), cudaMemcpyDeviceToDevice, s));
