@@ -22,33 +22,46 @@ struct KernParams {
     double inv_len[AB_MAX_DIM];   // exp(-0.5 log_M_k)
 };
 
+// 2^(j/64), j = 0..63, correctly rounded (global memory, L1 resident: 512 B)
+static __device__ const double ab_exp2_tab[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+
 // Branch-free FP64 exp(x) for x <= 0 (the only arguments the kernels produce):
-// n = rint(x log2 e), f = x - n ln2 (Cody-Waite), degree-13 Taylor on |f| <= 0.347
-// (remainder 4e-18), scaling by 2^n through the exponent field; exp(x) < 1e-307
-// flushes to 0.  Relative error ~2e-16, no slow-path call, no divergence.
+// n = rint(64 x / ln 2) = 64 m + j, r = x - n ln2/64 (Cody-Waite, |r| <= 0.0055),
+// exp(x) = 2^m 2^(j/64) (1 + r + r^2/2 + .. + r^5/120)  (remainder 4e-17): ten FP64
+// instructions and one L1 table load.  Relative error about 1 ulp; exp(x) < 1e-307
+// flushes to 0.  No slow-path call, no divergence.
 __device__ __forceinline__ double ab_exp_neg(double x) {
     const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52
-    double t = fma(x, 1.4426950408889634, SHIFT);
-    int n = __double2loint(t);
-    double nf = t - SHIFT;
-    double f = fma(nf, -6.93147180369123816490e-01, x);
-    f = fma(nf, -1.90821492927058770002e-10, f);
-    double p = 1.6059043836821613e-10;                       // 1/13!
-    p = fma(p, f, 2.0876756987868100e-09);                   // 1/12!
-    p = fma(p, f, 2.5052108385441720e-08);                   // 1/11!
-    p = fma(p, f, 2.7557319223985893e-07);                   // 1/10!
-    p = fma(p, f, 2.7557319223985888e-06);                   // 1/9!
-    p = fma(p, f, 2.4801587301587302e-05);                   // 1/8!
-    p = fma(p, f, 1.9841269841269841e-04);                   // 1/7!
-    p = fma(p, f, 1.3888888888888889e-03);                   // 1/6!
-    p = fma(p, f, 8.3333333333333332e-03);                   // 1/5!
-    p = fma(p, f, 4.1666666666666664e-02);                   // 1/4!
-    p = fma(p, f, 1.6666666666666666e-01);                   // 1/3!
-    p = fma(p, f, 0.5);
-    p = fma(p, f, 1.0);
-    p = fma(p, f, 1.0);
-    double r = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-    return (x > -707.0) ? r : 0.0;
+    const double t = fma(x, 92.33248261689366, SHIFT);       // 64 / ln 2
+    const int n = __double2loint(t);
+    const double nf = t - SHIFT;
+    double r = fma(nf, -0x1.62e42fee00000p-7, x);            // ln2/64, high part (32 bits)
+    r = fma(nf, -0x1.a39ef35793c76p-39, r);                  // low part
+    double q = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q *= r;
+    const double tj = __ldg(&ab_exp2_tab[n & 63]);
+    const double p = fma(tj, q, tj);
+    const double res = __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
+    return (x > -707.0) ? res : 0.0;
 }
 
 // Branch-free sqrt(x) for finite x >= 0: MUFU.RSQ64H seed, two Newton steps on
