@@ -363,6 +363,29 @@ class SurrogateModel(object):
         gp.compute(_theta)
         return gp, time.time() - t0
 
+    def _append_gp(self, _theta_prop, _y_prop):
+        """O(N^2) alternative to ``_fit_gp`` for the active-learning step: when exactly
+        one point was appended and the hyper-parameters are the current ones, the
+        factor is extended by a bordered Cholesky update (``GP.append_point``) instead
+        of being rebuilt (the reference refactorises, alabi/core.py:1780).  Returns
+        None when the preconditions do not hold; ``incremental_fit = False`` disables it."""
+        gp = getattr(self, "gp", None)
+        if not getattr(self, "incremental_fit", True) or gp is None or not self.fit_mean:
+            return None
+        x_old = gp._x
+        if not gp.computed or x_old is None or len(_theta_prop) != len(x_old) + 1:
+            return None
+        # theta() -> transform() round trips may move old points by an ulp
+        tol = 8 * np.finfo(float).eps * max(1.0, float(np.max(np.abs(x_old))))
+        if np.max(np.abs(np.asarray(_theta_prop)[:-1] - x_old)) > tol:
+            return None
+        t0 = time.time()
+        try:
+            gp.append_point(np.asarray(_theta_prop)[-1])
+        except np.linalg.LinAlgError:
+            return None
+        return gp, time.time() - t0
+
     def _opt_gp(self, hyperopt_method="ml", regularize=True, amp_0=1.0, mu_0=1.0, sigma_0=2.0,
                 optimizer_kwargs={"maxiter": 100, "xatol": 1e-4, "fatol": 1e-3, "adaptive": True}, cv_folds=5,
                 cv_scoring="mse", cv_n_candidates=20, multi_proc=True, cv_stage2_candidates=None,
@@ -609,8 +632,11 @@ class SurrogateModel(object):
                     if attempts >= max_attempts:
                         raise RuntimeError(f"Failed to find a valid training point after {max_attempts} attempts.")
                     continue
-                self.gp, fit_gp_timing = self._fit_gp(_theta=_theta_prop, _y=_y_prop,
-                                                      hyperparameters=self.gp.get_parameter_vector())
+                fitted = self._append_gp(_theta_prop, _y_prop)
+                if fitted is None:
+                    fitted = self._fit_gp(_theta=_theta_prop, _y=_y_prop,
+                                          hyperparameters=self.gp.get_parameter_vector())
+                self.gp, fit_gp_timing = fitted
                 success = True
             self._theta, self._y = _theta_prop, _y_prop
             if (ii + first_iter) % self.gp_opt_freq == 0:

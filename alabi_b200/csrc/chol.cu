@@ -386,6 +386,25 @@ int ab_launch_rebuild_dinv(ab_gp* h) {
     return 0;
 }
 
+// inverse and log-determinant part of ONE diagonal block of an existing factor
+int ab_launch_rebuild_dinv_block(ab_gp* h, int kb) {
+    int rc = configure_once();
+    if (rc) return rc;
+    const int64_t o = (int64_t)kb * NB;
+    potf2_inv_kernel<false><<<1, 256, 0, h->stream>>>(h->L + o * h->npad + o, h->npad, 0, h->Dinv + o * NB,
+                                                      h->logdet_parts + kb, h->d_info);
+    AB_CHECK_LAUNCH();
+    return 0;
+}
+
+// one-block factor: z = D_0^-1 r (r is not modified)
+int ab_launch_trsv_single(ab_gp* h, const double* r) {
+    AB_CUDA(cudaMemcpyAsync(h->alpha, r, NB * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));   // alpha: scratch here
+    trsv_fwd_kernel<<<1, 256, 0, h->stream>>>(h->L, h->npad, h->Dinv, 0, h->alpha, h->z);
+    AB_CHECK_LAUNCH();
+    return 0;
+}
+
 // z = L^-1 (y - mean), alpha = L^-T z, quad = |z|^2, logdet = sum parts.
 // Leaves {quad, logdet} in h->h_pinned[0..1] after a stream sync by the caller.
 int ab_launch_solve_alpha(ab_gp* h, const double* y) {
@@ -394,7 +413,7 @@ int ab_launch_solve_alpha(ab_gp* h, const double* y) {
     cudaStream_t s = h->stream;
     residual_kernel<<<(unsigned)((h->npad + 255) / 256), 256, 0, s>>>(y, h->n, h->npad, h->mean, h->work);
     if (T >= 2) {
-        int rc = ab_launch_trsv_dataflow(h, h->work);          // both sweeps, one cooperative launch
+        int rc = ab_launch_trsv_dataflow(h, h->work, 1);          // both sweeps, one cooperative launch
         if (rc) return rc;
     } else {
         for (int k = 0; k < T; k++) trsv_fwd_kernel<<<T - k, 256, 0, s>>>(h->L, ld, h->Dinv, k, h->work, h->z);

@@ -70,7 +70,9 @@ int ab_launch_cross_cov(ab_gp* h, const double* AT, int64_t lda, int64_t na, con
 // chol.cu
 int ab_launch_factor(ab_gp* h);
 int ab_launch_factor_dataflow(ab_gp* h);   // chol_dataflow.cu
-int ab_launch_trsv_dataflow(ab_gp* h, const double* r);   // trsv_dataflow.cu
+int ab_launch_trsv_dataflow(ab_gp* h, const double* r, int backward);   // trsv_dataflow.cu
+int ab_launch_trsv_single(ab_gp* h, const double* r);      // chol.cu: z = D_0^-1 r for a one-block factor
+int ab_launch_rebuild_dinv_block(ab_gp* h, int kb);        // chol.cu
 int ab_launch_rebuild_dinv(ab_gp* h);
 int ab_launch_solve_alpha(ab_gp* h, const double* y);
 int ab_launch_build_linv(ab_gp* h);

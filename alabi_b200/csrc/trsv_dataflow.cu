@@ -28,6 +28,7 @@ struct TrsvArgs {
     const double* L; int64_t ld; const double* Dinv; int T;
     const double* r; double* z; double* alpha;
     int* zflag; int* aflag; int* abort_flag;
+    int backward;                 // 0: forward sweep only (z), 1: both
 };
 
 __device__ __forceinline__ int ld_acquire_i(const int* p) {
@@ -125,6 +126,7 @@ trsv_dataflow_kernel(const __grid_constant__ TrsvArgs a) {
         if (tid == 0) st_release_i(a.zflag + k, 1);
     }
 
+    if (!a.backward) return;
     // ---------------- backward: alpha = L^-T z ----------------
     const int last = (T - 1) - (int)blockIdx.x;           // CTA c takes rows T-1-c, T-1-c-G, ...
     for (int k = last; k >= 0; k -= G) {
@@ -184,7 +186,7 @@ trsv_dataflow_kernel(const __grid_constant__ TrsvArgs a) {
 
 // z = L^-1 r, alpha = L^-T z;  r (npad) is read only.  Returns 0 after enqueueing;
 // the abort flag is copied to h->h_pinned + 10 (checked by the caller after its sync).
-int ab_launch_trsv_dataflow(ab_gp* h, const double* r) {
+int ab_launch_trsv_dataflow(ab_gp* h, const double* r, int backward) {
     static bool configured = false;
     const int smem = NB * NB * (int)sizeof(double);
     if (!configured) {
@@ -202,6 +204,7 @@ int ab_launch_trsv_dataflow(ab_gp* h, const double* r) {
     a.L = h->L; a.ld = h->npad; a.Dinv = h->Dinv; a.T = T;
     a.r = r; a.z = h->z; a.alpha = h->alpha;
     a.abort_flag = ctrl; a.zflag = ctrl + 1; a.aflag = ctrl + 1 + T;
+    a.backward = backward;
     int grid = T < h->nsm ? T : h->nsm;
     void* args[] = {(void*)&a};
     AB_CUDA(cudaLaunchCooperativeKernel((void*)trsv_dataflow_kernel, dim3(grid), dim3(256), args, smem, s));

@@ -258,6 +258,30 @@ class GP:
         self.computed = True
         return self
 
+    def append_point(self, x_new):
+        """Append ONE training point to a computed model in O(N^2) (bordered Cholesky
+        update, ``ab_gp_append_point``) — the same factor, up to rounding, as
+        ``compute(vstack(x, x_new))``, which is what the reference does after every
+        active-learning step (alabi/core.py:1780).  Targets are reset: pass the new
+        ``y`` to the next ``predict`` / ``log_likelihood`` call."""
+        if not self.computed or self._x is None:
+            raise RuntimeError("You need to compute the model first")
+        x_new = np.ascontiguousarray(np.asarray(x_new, dtype=np.float64).reshape(-1))
+        if x_new.shape[0] != self.kernel.ndim:
+            raise ValueError("Dimension mismatch")
+        hd = self._hd
+        xd = self._dev(x_new)
+        rc = _lib.check(hd.lib.ab_gp_append_point(hd.h, _lib.ptr(xd)), "ab_gp_append_point")
+        hd.stream.synchronize()
+        self._x = np.vstack([self._x, x_new[None, :]])
+        self._targets_pushed = False
+        self._alpha_np = None
+        self._y = None
+        if rc > 0:
+            self.computed = False
+            raise LinAlgError(f"{rc}-th leading minor of the covariance matrix is not positive definite")
+        return self
+
     def recompute(self, quiet=False, **kwargs):
         if not self.computed:
             if self._x is None:

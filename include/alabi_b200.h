@@ -71,6 +71,14 @@ int ab_gp_create(ab_gp** out, int device, void* cuda_stream);
 int ab_gp_destroy(ab_gp* h);
 int ab_gp_set_lookahead(ab_gp* h, int enabled);
 
+/* Append ONE training point (d doubles on the device, same space as X) to a
+ * factorised model in O(N^2): bordered Cholesky update instead of the full
+ * refactorisation `_fit_gp` -> `gp.compute` performs after every active-learning
+ * step (alabi/core.py:1780 -> 1158) when the hyper-parameters are unchanged.
+ * Returns 0, or k > 0 (= n + 1) when the bordered matrix is not positive definite
+ * (the handle is then left un-factorised, like a failed ab_gp_factor). */
+int ab_gp_append_point(ab_gp* h, const double* d_x);
+
 /* training inputs of gp.compute(x): X is n x d (copied).  alabi/gp_utils.py:243 */
 int ab_gp_set_inputs(ab_gp* h, const double* d_X, int64_t n, int d);
 

@@ -158,3 +158,39 @@ def test_large_factor_lookahead_equals_plain(n):
         assert abs(ll - ll_o) <= 1e-9 * abs(ll_o)
         assert np.max(np.abs(np.tril(L)[:n, :n] - Lo)) < 1e-9 * np.max(np.abs(Lo))
     assert np.max(np.abs(outs[2][2] - outs[0][2])) <= 1e-9 * np.max(np.abs(outs[0][2]))
+
+
+@pytest.mark.parametrize("kind,n0,nadd,d", [("ExpSquaredKernel", 60, 5, 2), ("Matern32Kernel", 126, 5, 3),
+                                            ("Matern52Kernel", 383, 4, 2), ("ExpSquaredKernel", 1000, 3, 5)])
+def test_append_point_equals_refactorisation(kind, n0, nadd, d):
+    """Bordered Cholesky update (ab_gp_append_point) against a fresh factorisation of
+    the extended training set and against the oracle, including the steps that cross
+    a 128-row padding boundary."""
+    o, g, X, y, rng = make_pair(kind, n0 + nadd, d, seed=11)
+    import alabi_b200 as ab
+    log_M = o.log_M
+    mk = lambda: ab.GP(kernel=getattr(ab.kernels, kind)(metric=np.exp(log_M), ndim=d) * (np.exp(o.log_const) * d),
+                       fit_mean=True, mean=o.mean, white_noise=o.white_noise, fit_white_noise=True)
+    ga = mk()
+    ga.compute(X[:n0])
+    t = rng.uniform(X.min(), X.max(), size=(300, d))
+    for k in range(nadd):
+        ga.append_point(X[n0 + k])
+        m = n0 + k + 1
+        gf = mk()
+        gf.compute(X[:m])
+        oo = ogp.OracleGP(kind, d, log_M, log_const=o.log_const, mean=o.mean, fit_mean=True,
+                          white_noise=o.white_noise, fit_white_noise=True).compute(X[:m])
+        ll_a, ll_f, ll_o = ga.log_likelihood(y[:m]), gf.log_likelihood(y[:m]), oo.log_likelihood(y[:m])
+        assert abs(ll_a - ll_f) <= 1e-10 * abs(ll_f)
+        assert abs(ll_a - ll_o) <= 1e-9 * abs(ll_o)
+        mu_a, var_a = ga.predict(y[:m], t, return_var=True)
+        mu_f, var_f = gf.predict(y[:m], t, return_var=True)
+        assert rel(mu_a, mu_f) < 1e-10
+        assert np.max(np.abs(var_a - var_f)) < 1e-10 * np.exp(o.log_const)
+        ga_g, gf_g = ga.grad_log_likelihood(y[:m]), gf.grad_log_likelihood(y[:m])
+        assert np.max(np.abs(ga_g - gf_g)) <= 1e-8 * np.max(np.abs(gf_g))
+    La, _ = ga.export_state()
+    Lf, _ = gf.export_state()
+    m = n0 + nadd
+    assert np.max(np.abs(np.tril(La.cpu().numpy())[:m, :m] - np.tril(Lf.cpu().numpy())[:m, :m])) < 1e-10 * float(Lf.abs().max())
