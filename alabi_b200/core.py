@@ -588,9 +588,13 @@ class SurrogateModel(object):
             if str(self.obj_opt_method).lower() != "batch" and nopt > 0:
                 u = util.cpu().numpy()
                 order = np.argsort(np.where(np.isfinite(u), u, np.inf))[:max(int(nopt), 1)]
+                grad_obj_fn = None                      # alabi/core.py:1613-1618
+                if getattr(self, "grad_utility", None) is not None:
+                    self.gp._set_targets(self._y)
+                    grad_obj_fn = partial(self.grad_utility, gp=self.gp, bounds=self._bounds)
                 tp, fp = ut.minimize_objective(obj_fn, bounds=self._bounds, nopt=len(order),
                                                method=self.obj_opt_method, options=optimizer_kwargs or None,
-                                               starting_points=cand[order])
+                                               grad_obj_fn=grad_obj_fn, starting_points=cand[order])
                 if np.all(np.isfinite(tp)) and np.isfinite(fp) and fp < best:
                     _thetaN, best = np.asarray(tp), fp
         opt_timing = time.time() - t0
@@ -614,6 +618,8 @@ class SurrogateModel(object):
                      allow_opt_multiproc=True, max_attempts=10, ncand=None):
         self.algorithm = str(algorithm).lower()
         self.utility, self.grad_utility = ut.assign_utility(self.algorithm)
+        if not use_grad_opt:
+            self.grad_utility = None
         self.gp_opt_freq, self.obj_opt_method, self.ncand = gp_opt_freq, obj_opt_method, ncand
         tr = self.training_results
         first_iter = 0 if len(tr["iteration"]) == 0 else tr["iteration"][-1]

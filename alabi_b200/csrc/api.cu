@@ -344,6 +344,16 @@ int ab_gp_predict(ab_gp* h, const double* d_Xq, int64_t m, double* d_mu, double*
     return ab_launch_predict(h, d_Xq, m, d_mu, d_var);
 }
 
+int ab_gp_predict_grad(ab_gp* h, const double* d_Xq, int64_t m, double* d_mu, double* d_var, double* d_dmu,
+                       double* d_dvar) {
+    AB_REQUIRE(h && d_Xq && d_mu && d_var && d_dmu && d_dvar, -1, "ab_gp_predict_grad: null argument");
+    AB_REQUIRE(h->have_alpha, -2, "ab_gp_predict_grad: targets not set (call ab_gp_factor + ab_gp_set_targets)");
+    AB_CUDA(cudaSetDevice(h->device));
+    int rc = ensure_linv(h);
+    if (rc) return rc;
+    return ab_launch_predict_grad(h, d_Xq, m, d_mu, d_var, d_dmu, d_dvar);
+}
+
 int ab_gp_predict_host(ab_gp* h, const double* h_Xq, int64_t m, double* h_mu, double* h_var) {
     AB_REQUIRE(h && h_Xq && h_mu, -1, "ab_gp_predict_host: null argument");
     AB_REQUIRE(h->have_alpha, -2, "ab_gp_predict_host: targets not set");

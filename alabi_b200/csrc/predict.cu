@@ -146,6 +146,102 @@ predict_var_kernel(const double* __restrict__ Linv, int64_t ld, int T, const dou
 }
 
 // ---------------------------------------------------------------------------
+// Gradients of the predictive mean and variance w.r.t. the query point
+// (alabi/utility.py:558-621 `grad_gp_mean_prediction` / `grad_gp_var_prediction`,
+// which difference the kernel numerically and form a dense K^-1 per call):
+//   d mu / dx      =        sum_j alpha_j        d k*_j / dx
+//   d sigma^2 / dx = -2     sum_j (K^-1 k*)_j    d k*_j / dx
+//   d k*_j / dx_k  = amp k'(r^2) 2 (x_k - x_jk) / M_k          (analytic)
+// K^-1 k* for a panel of queries is two triangular DMMA GEMMs with L^-1.
+// ---------------------------------------------------------------------------
+// C(i, q-tile) = sum_k op(Linv)(i, k) B(k, q-tile);  TRANS = false: Linv (k <= i, diagonal
+// block triangular), TRANS = true: Linv^T (k >= i).  B, C: [row][query], query contiguous.
+template <bool TRANS>
+__global__ void __launch_bounds__(abg::THREADS, 1)
+tri_gemm_kernel(const double* __restrict__ Linv, int64_t ld, int T, const double* __restrict__ B, int64_t ldb,
+                double* __restrict__ C) {
+    extern __shared__ __align__(16) double smem[];
+    const int i = blockIdx.y;
+    const double* Bp = B + (int64_t)blockIdx.x * abg::BN;
+    abg::Acc acc;
+    acc.zero();
+    if (!TRANS)
+        abg::mainloop<true, false, true>(acc, Linv + (int64_t)i * NB * ld, ld, Bp, ldb, (i + 1) * (NB / abg::BK), smem);
+    else
+        abg::mainloop<false, false>(acc, Linv + (int64_t)i * NB * ld + (int64_t)i * NB, ld, Bp + (int64_t)i * NB * ldb, ldb,
+                                    (T - i) * (NB / abg::BK), smem);
+    abg::store_tile(acc, C + (int64_t)i * NB * ldb + (int64_t)blockIdx.x * abg::BN, ldb, 1.0, 0.0);
+}
+
+// one query per thread; partial[(split * 2D + k) * part_ld + q] = sum over the split's
+// training points of alpha_j g_j diff_k (k < D) and V_jq g_j diff_k (D <= k < 2D)
+template <int KIND, int D>
+__global__ void __launch_bounds__(128)
+predict_grad_kernel(const double* __restrict__ Xq, int64_t m, int64_t q_off, const double* __restrict__ Xs,
+                    const double* __restrict__ alpha, const double* __restrict__ V, int64_t ldp, int64_t n,
+                    int64_t npad, KernParams kp, double* __restrict__ partial, int64_t part_ld) {
+    __shared__ __align__(16) double sX[TS * D];
+    __shared__ double sAl[TS];
+    const int tid = threadIdx.x, d = kp.d;
+    const int64_t q = (int64_t)blockIdx.x * 128 + tid;
+    double x[D], gm[D], gv[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        x[k] = (k < d && q_off + q < m) ? Xq[(q_off + q) * d + k] * kp.inv_len[k] : 0.0;
+        gm[k] = gv[k] = 0.0;
+    }
+    const int64_t jbeg = (int64_t)blockIdx.y * JCHUNK;
+    const int64_t jend = jbeg + JCHUNK < n ? jbeg + JCHUNK : n;
+    for (int64_t j0 = jbeg; j0 < jend; j0 += TS) {
+        __syncthreads();
+        for (int idx = tid; idx < TS * D; idx += 128) {
+            int jj = idx / D, k = idx - jj * D;
+            sX[idx] = (k < d && j0 + jj < npad) ? Xs[(j0 + jj) * d + k] : 0.0;
+        }
+        if (tid < TS) sAl[tid] = (j0 + tid < n) ? alpha[j0 + tid] : 0.0;
+        __syncthreads();
+        const int tn = (int)((jend - j0 < TS) ? (jend - j0) : TS);
+        for (int jj = 0; jj < tn; jj++) {
+            double df[D], r2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                df[k] = x[k] - sX[jj * D + k];
+                r2 = fma(df[k], df[k], r2);
+            }
+            const double g = ab_radial_grad<KIND>(r2);
+            const double c1 = sAl[jj] * g, c2 = V[(j0 + jj) * ldp + q] * g;
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                gm[k] = fma(c1, df[k], gm[k]);
+                gv[k] = fma(c2, df[k], gv[k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        partial[((int64_t)blockIdx.y * 2 * D + k) * part_ld + q] = gm[k];
+        partial[((int64_t)blockIdx.y * 2 * D + D + k) * part_ld + q] = gv[k];
+    }
+}
+
+__global__ void grad_combine_kernel(const double* __restrict__ partial, int64_t part_ld, int64_t cnt, int nsplit, int D,
+                                    int d, KernParams kp, double* __restrict__ dmu, double* __restrict__ dvar,
+                                    int64_t q_off) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cnt * d) return;
+    const int64_t q = idx / d;
+    const int k = (int)(idx - q * d);
+    double sm = 0.0, sv = 0.0;
+    for (int p = 0; p < nsplit; p++) {
+        sm += partial[((int64_t)p * 2 * D + k) * part_ld + q];
+        sv += partial[((int64_t)p * 2 * D + D + k) * part_ld + q];
+    }
+    const double f = 2.0 * kp.amp * kp.inv_len[k];
+    dmu[(q_off + q) * d + k] = f * sm;
+    dvar[(q_off + q) * d + k] = -2.0 * f * sv;
+}
+
+// ---------------------------------------------------------------------------
 // K4 utilities.  Expression order follows the reference exactly
 // (alabi/utility.py:489-504, 696, 804, 926-939).
 // ---------------------------------------------------------------------------
@@ -318,6 +414,77 @@ int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double*
         ab_prof_end(h, AB_PROF_PREDICT_VAR);
         AB_CHECK_LAUNCH();
         ab_count_launches(nsplit > 1 ? 3 : 2);
+    }
+    return 0;
+}
+
+
+template <int KIND>
+static int launch_grad_points(ab_gp* h, int Dp, dim3 grid, const double* Xq, int64_t m, int64_t q0, const double* V,
+                              int64_t ldp, double* partial) {
+#define AB_PG(DD)                                                                                                 \
+    predict_grad_kernel<KIND, DD><<<grid, 128, 0, h->stream>>>(Xq, m, q0, h->Xs, h->alpha, V, ldp, h->n, h->npad, h->kp, \
+                                                                partial, ldp)
+    if (Dp <= 2) AB_PG(2);
+    else if (Dp <= 4) AB_PG(4);
+    else if (Dp <= 8) AB_PG(8);
+    else if (Dp <= 12) AB_PG(12);
+    else if (Dp <= 16) AB_PG(16);
+    else if (Dp <= 20) AB_PG(20);
+    else if (Dp <= 24) AB_PG(24);
+    else AB_PG(32);
+#undef AB_PG
+    AB_CHECK_LAUNCH();
+    return 0;
+}
+
+static int padded_dim(int d) {
+    const int opts[] = {2, 4, 8, 12, 16, 20, 24, 32};
+    for (int o : opts) if (d <= o) return o;
+    return 32;
+}
+
+// mean, variance and their gradients w.r.t. the query coordinates (row-major m x d)
+int ab_launch_predict_grad(ab_gp* h, const double* Xq, int64_t m, double* mu, double* var, double* dmu, double* dvar) {
+    if (m <= 0) return 0;
+    cudaStream_t s = h->stream;
+    const int d = h->d, D = padded_dim(d);
+    AB_CUDA(cudaFuncSetAttribute(predict_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));
+    AB_CUDA(cudaFuncSetAttribute(tri_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));
+    AB_CUDA(cudaFuncSetAttribute(tri_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));
+    const int T = (int)(h->npad / NB);
+    int64_t mq = m < 1024 ? m : 1024;                              // queries per panel
+    const int64_t ldp = (mq + QPB - 1) / QPB * QPB;
+    const int nsplit = (int)((h->npad + JCHUNK - 1) / JCHUNK);
+    const size_t panel = (size_t)h->npad * ldp;
+    int rc = ab_ensure_scratch(h, (3 * panel + (size_t)nsplit * ldp * (1 + 2 * D)) * sizeof(double));
+    if (rc) return rc;
+    double* P = h->scratch;
+    double* W = P + panel;
+    double* V = W + panel;
+    double* partial = V + panel;                                   // [nsplit][ldp] mean partials
+    double* gpartial = partial + (size_t)nsplit * ldp;             // [nsplit][2 D][ldp]
+    for (int64_t q0 = 0; q0 < m; q0 += mq) {
+        const int64_t cnt = (m - q0 < mq) ? (m - q0) : mq;
+        dim3 grid((unsigned)((cnt + QPB - 1) / QPB), (unsigned)nsplit);
+        AB_DISPATCH_KIND(h->kp.kind, rc = (launch_mean<KIND, true>(h, d, grid, Xq, m, q0, mu, P, ldp, nsplit, partial, ldp)));
+        if (rc) return rc;
+        if (nsplit > 1) {
+            combine_splits_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(partial, ldp, cnt, nsplit, h->kp.amp,
+                                                                              h->mean, mu, q0);
+        }
+        const unsigned ntq = (unsigned)((cnt + abg::BN - 1) / abg::BN);
+        predict_var_kernel<<<ntq, abg::THREADS, abg::SMEM_BYTES, s>>>(h->Linv, h->npad, T, P, ldp, m, q0, h->kp.amp, var);
+        tri_gemm_kernel<false><<<dim3(ntq, T), abg::THREADS, abg::SMEM_BYTES, s>>>(h->Linv, h->npad, T, P, ldp, W);
+        tri_gemm_kernel<true><<<dim3(ntq, T), abg::THREADS, abg::SMEM_BYTES, s>>>(h->Linv, h->npad, T, W, ldp, V);
+        AB_CHECK_LAUNCH();
+        dim3 ggrid((unsigned)((cnt + 127) / 128), (unsigned)nsplit);
+        AB_DISPATCH_KIND(h->kp.kind, rc = (launch_grad_points<KIND>(h, d, ggrid, Xq, m, q0, V, ldp, gpartial)));
+        if (rc) return rc;
+        grad_combine_kernel<<<(unsigned)((cnt * d + 255) / 256), 256, 0, s>>>(gpartial, ldp, cnt, nsplit, D, d, h->kp, dmu,
+                                                                            dvar, q0);
+        AB_CHECK_LAUNCH();
+        ab_count_launches(7);
     }
     return 0;
 }

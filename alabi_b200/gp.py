@@ -410,6 +410,26 @@ class GP:
         _lib.check(hd.lib.ab_gp_predict_host(hd.h, _lib.ptr(xs), m, _lib.ptr(mu), _lib.ptr(var)), "ab_gp_predict_host")
         return (mu, var) if want_var else mu
 
+    def predict_grad(self, y, t):
+        """(mu, var, d mu / dx, d var / dx) at the query points ``t`` (M x d); the
+        gradients are M x d, w.r.t. the query coordinates (``ab_gp_predict_grad``).
+        Analytic replacement for ``grad_gp_mean_prediction`` /
+        ``grad_gp_var_prediction`` (alabi/utility.py:558-621)."""
+        torch = _torch()
+        self.recompute()
+        self._set_targets(y)
+        hd = self._hd
+        tq = self._dev(self.parse_samples(t))
+        m, d = tq.shape
+        dev = tq.device
+        mu = torch.empty(m, dtype=torch.float64, device=dev)
+        var = torch.empty(m, dtype=torch.float64, device=dev)
+        dmu = torch.empty((m, d), dtype=torch.float64, device=dev)
+        dvar = torch.empty((m, d), dtype=torch.float64, device=dev)
+        _lib.check(hd.lib.ab_gp_predict_grad(hd.h, _lib.ptr(tq), m, _lib.ptr(mu), _lib.ptr(var), _lib.ptr(dmu),
+                                             _lib.ptr(dvar)), "ab_gp_predict_grad")
+        return mu.cpu().numpy(), var.cpu().numpy(), dmu.cpu().numpy(), dvar.cpu().numpy()
+
     # -- batched acquisition (K4) -------------------------------------------------------------------
     def utility_argmin(self, y, candidates, bounds, algorithm="bape", y_best=0.0, zeta=0.01, return_values=False):
         """Evaluate an acquisition utility over a candidate batch and return

@@ -183,16 +183,38 @@ def jones_utility(theta, predict_gp, bounds, y_best, zeta=0.01):
     return float(-((mu - y_best - zeta) * norm.cdf(z) + std * norm.pdf(z)))
 
 
+def grad_agp_utility(theta, gp, bounds):
+    """alabi/utility.py:704-726: -(d mu + 0.5 d sigma^2) (the reference's expression,
+    kept as is), inf outside the prior box.  d mu and d sigma^2 come from the device
+    (``GP.predict_grad``, analytic kernel derivative; the reference differences the
+    kernel with h = 1e-6 and forms a dense K^-1 per call)."""
+    theta = np.asarray(theta, dtype=np.float64).flatten()
+    if not np.isfinite(lnprior_uniform(theta, bounds)):
+        return np.full(len(theta), np.inf)
+    _, _, d_mu, d_var = gp.predict_grad(gp._y, theta.reshape(1, -1))
+    return (-(d_mu[0] + 0.5 * d_var[0])).flatten()
+
+
+def grad_bape_utility(theta, gp, bounds):
+    """alabi/utility.py:813-850: chain rule on -((2 mu + s2) + log(exp(s2) - 1))."""
+    theta = np.asarray(theta, dtype=np.float64).flatten()
+    if not np.isfinite(lnprior_uniform(theta, bounds)):
+        return np.full(len(theta), np.inf)
+    _, var, d_mu, d_var = gp.predict_grad(gp._y, theta.reshape(1, -1))
+    with np.errstate(all="ignore"):
+        exp_var = np.exp(var[0])
+        d_bape_d_var = -(1.0 + exp_var / (exp_var - 1.0))
+    return -2.0 * d_mu[0] + d_bape_d_var * d_var[0]
+
+
 def assign_utility(algorithm):
-    """(utility, gradient) pair; gradients are left to the optimiser's finite
-    differences (the reference's analytic-looking gradients are themselves
-    finite differences of the kernel plus a dense K^-1 per call,
-    alabi/utility.py:511-621,704-850)."""
-    table = {"bape": bape_utility, "agp": agp_utility, "jones": jones_utility}
+    """(utility, gradient) pair (alabi/utility.py:949-966); jones has no gradient."""
+    table = {"bape": (bape_utility, grad_bape_utility), "agp": (agp_utility, grad_agp_utility),
+             "jones": (jones_utility, None)}
     if algorithm not in table:
         print(f"ERROR: Unknown utility function: {algorithm}. Defaulting to BAPE.")
-        return bape_utility, None
-    return table[algorithm], None
+        return bape_utility, grad_bape_utility
+    return table[algorithm]
 
 
 def _minimize_single(obj_fn, bounds, x0, method, options, grad_obj_fn=None):

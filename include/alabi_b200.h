@@ -113,6 +113,14 @@ int ab_gp_grad_log_likelihood(ab_gp* h, const double* d_y, double* h_out);
 /* K3: gp.predict(y, t, return_var).  d_var may be NULL (mean only).
  * alabi/core.py:85,95,1441,1486,1601 */
 int ab_gp_predict(ab_gp* h, const double* d_Xq, int64_t m, double* d_mu, double* d_var);
+
+/* gp.predict plus the gradients of mean and variance w.r.t. the query point:
+ * d_dmu, d_dvar are m x d row-major.  Replaces grad_gp_mean_prediction /
+ * grad_gp_var_prediction (alabi/utility.py:558-621), which difference the kernel
+ * numerically (h = 1e-6) and form a dense K^-1 per call; here the kernel derivative
+ * is analytic and K^-1 k* is two triangular DMMA GEMMs with L^-1. */
+int ab_gp_predict_grad(ab_gp* h, const double* d_Xq, int64_t m, double* d_mu, double* d_var, double* d_dmu,
+                       double* d_dvar);
 /* same with HOST buffers (pageable or pinned): copies in, predicts, copies out */
 int ab_gp_predict_host(ab_gp* h, const double* h_Xq, int64_t m, double* h_mu, double* h_var);
 

@@ -242,6 +242,39 @@ class OracleGP:
         cov = self.get_matrix(xs) - Kxs @ KinvKxs
         return mu, cov
 
+    # -- gradients of the prediction w.r.t. the query point -----------------------------
+    def predict_grad(self, y, t, h=None):
+        """d mu / dx and d sigma^2 / dx (M x d) as alabi/utility.py:558-621 defines
+        them: ``grad_k^T alpha`` and ``-2 grad_k^T K^-1 k*``.  ``h=None`` uses the
+        analytic kernel derivative dk/dx_k = amp k'(r^2) 2 (x_k - x_jk) / M_k; a float
+        reproduces the reference's central difference of the kernel
+        (``numerical_kernel_gradient``, h = 1e-6 there)."""
+        self.recompute()
+        alpha = self._compute_alpha(y)
+        xs = np.atleast_2d(np.asarray(t, dtype=np.float64))
+        amp = 1.0 if self.log_const is None else np.exp(self.log_const)
+        inv_M = np.exp(-self.log_M)
+        dmu = np.zeros_like(xs)
+        dvar = np.zeros_like(xs)
+        for q in range(len(xs)):
+            x = xs[q]
+            if h is None:
+                diff = x[None, :] - self._x                                   # (N, d)
+                r2 = np.sum(diff * diff * inv_M[None, :], axis=1)
+                gk = (amp * radial_grad(self.kind, r2))[:, None] * 2.0 * diff * inv_M[None, :]
+            else:
+                gk = np.zeros_like(self._x)
+                for i in range(self.ndim):
+                    xp, xm = x.copy(), x.copy()
+                    xp[i] += h
+                    xm[i] -= h
+                    gk[:, i] = (self.get_matrix(xp[None, :], self._x).ravel()
+                                - self.get_matrix(xm[None, :], self._x).ravel()) / (2 * h)
+            ks = self.get_matrix(x[None, :], self._x).ravel()
+            dmu[q] = gk.T @ alpha
+            dvar[q] = -2.0 * gk.T @ self.apply_inverse(ks)
+        return dmu, dvar
+
     # extended-precision style variance used to measure conditioning effects
     def predict_var_via_L(self, t):
         """sigma^2 = k** - ||L^{-1} k*||^2 (the form the GPU path uses)."""

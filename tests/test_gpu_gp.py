@@ -194,3 +194,52 @@ def test_append_point_equals_refactorisation(kind, n0, nadd, d):
     Lf, _ = gf.export_state()
     m = n0 + nadd
     assert np.max(np.abs(np.tril(La.cpu().numpy())[:m, :m] - np.tril(Lf.cpu().numpy())[:m, :m])) < 1e-10 * float(Lf.abs().max())
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("n,d,m", [(60, 1, 3), (300, 2, 40), (700, 5, 300), (1100, 10, 1500)])
+def test_predict_grad(kind, n, d, m):
+    """ab_gp_predict_grad: analytic d mu / dx, d sigma^2 / dx against the oracle's analytic
+    form (1e-8) and against the reference's finite-difference construction (1e-4)."""
+    if d == 1 and kind != "ExpSquaredKernel":
+        pytest.skip("1-D covered once")
+    o, g, X, y, rng = make_pair(kind, n, d, seed=5 * n + d)
+    t = rng.uniform(-1.1, 1.1, size=(m, d))
+    mu_g, var_g, dmu_g, dvar_g = g.predict_grad(y, t)
+    mu_o, var_o = o.predict(y, t, return_var=True)
+    amp = np.exp(o.log_const)
+    assert rel(mu_g, mu_o) < 1e-9
+    assert np.max(np.abs(var_g - var_o)) < 1e-9 * amp
+    sub = slice(0, min(m, 60))
+    dmu_o, dvar_o = o.predict_grad(y, t[sub])
+    assert np.max(np.abs(dmu_g[sub] - dmu_o)) <= 1e-8 * np.max(np.abs(dmu_o))
+    assert np.max(np.abs(dvar_g[sub] - dvar_o)) <= 1e-8 * max(np.max(np.abs(dvar_o)), 1e-6 * amp)
+    dmu_f, dvar_f = o.predict_grad(y, t[:5], h=1e-6)
+    assert np.max(np.abs(dmu_g[:5] - dmu_f)) <= 1e-4 * np.max(np.abs(dmu_f))
+    assert np.max(np.abs(dvar_g[:5] - dvar_f)) <= 1e-4 * max(np.max(np.abs(dvar_f)), 1e-6 * amp)
+
+
+def test_grad_utilities_match_reference_expressions():
+    """grad_agp_utility / grad_bape_utility (alabi/utility.py:704-850) on the device
+    gradients, against the same expressions on the oracle's gradients, and against a
+    finite difference of the utility itself where the reference's expression is its
+    true derivative (bape)."""
+    from alabi_b200 import utility as ut
+    o, g, X, y, rng = make_pair("ExpSquaredKernel", 250, 2, seed=77)
+    b = np.array([(-1.2, 1.2)] * 2)
+    g._set_targets(y)
+    g._y = y
+    for th in rng.uniform(-1, 1, size=(4, 2)):
+        dmu_o, dvar_o = o.predict_grad(y, th[None, :])
+        _, var_o = o.predict(y, th[None, :], return_var=True)
+        ga = ut.grad_agp_utility(th, g, b)
+        np.testing.assert_allclose(ga, -(dmu_o[0] + 0.5 * dvar_o[0]), rtol=1e-7, atol=1e-10)
+        gb = ut.grad_bape_utility(th, g, b)
+        e = np.exp(var_o[0])
+        np.testing.assert_allclose(gb, -2.0 * dmu_o[0] - (1.0 + e / (e - 1.0)) * dvar_o[0], rtol=1e-6, atol=1e-9)
+        pg = lambda xs: g.predict(y, xs, return_var=True)
+        h = 1e-5
+        fd = np.array([(ut.bape_utility(th + h * np.eye(2)[k], pg, b) - ut.bape_utility(th - h * np.eye(2)[k], pg, b)) / (2 * h)
+                       for k in range(2)])
+        np.testing.assert_allclose(gb, fd, rtol=2e-4, atol=1e-6)
+    assert np.all(np.isinf(ut.grad_agp_utility(np.array([5.0, 0.0]), g, b)))
