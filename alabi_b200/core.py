@@ -444,7 +444,12 @@ class SurrogateModel(object):
             else:
                 p0 = ut.prior_sampler(bounds=self.hp_bounds, nsample=self.gp_nopt, sampler="lhs", random_state=None)
                 p0[0] = current_hp
-                results = min([_optimize_fn(p) for p in p0], key=lambda r: r.fun)
+                from . import parallel as par
+                if getattr(self, "shard_restarts", False) and par.world_size() > 1:
+                    # restart r on rank r mod world, one all_gather of (fun, x)
+                    results, _ = par.sharded_restarts(_optimize_fn, par.broadcast_object(p0))
+                else:
+                    results = min([_optimize_fn(p) for p in p0], key=lambda r: r.fun)
             op_gp = self.set_hyperparameter_vector(cur, results.x)
             op_gp.compute(_theta)
             if self.verbose:

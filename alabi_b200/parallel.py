@@ -20,7 +20,8 @@ import os
 import numpy as np
 
 __all__ = ["init_distributed", "shard_range", "broadcast_gp", "argmin_allgather", "allgather_rows",
-           "sharded_predict", "sharded_utility_argmin", "sharded_ensemble"]
+           "sharded_predict", "sharded_utility_argmin", "sharded_ensemble", "sharded_restarts",
+           "broadcast_object", "world_size"]
 
 
 def init_distributed(backend=None):
@@ -169,3 +170,47 @@ def sharded_ensemble(sampler_factory, p0, nsteps, gather=True, **run_kwargs):
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     chain = allgather_rows(torch.from_numpy(np.ascontiguousarray(s.get_chain())).to(dev), dim=1)
     return s, chain.cpu().numpy()
+
+
+def world_size():
+    dist = _dist()
+    return dist.get_world_size() if dist else 1
+
+
+def broadcast_object(obj, src=0):
+    """Every rank returns ``src``'s object (restart seeds, candidate sets)."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def sharded_restarts(optimize_fn, starts):
+    """Hyper-parameter optimiser restarts sharded over ranks: restart r
+    runs on rank r mod world (its own K1 + K2 per objective evaluation, no
+    communication), then ONE all_gather of (fun, restart index, x) and every rank
+    picks the same winner: smallest finite ``fun``, lowest restart index on ties —
+    the serial ``min(results, key=fun)`` of alabi/core.py:1309-1311.
+
+    ``optimize_fn(x0)`` returns a scipy ``OptimizeResult``; ``starts`` must be the
+    same on every rank (use :func:`broadcast_object`).  Returns (best, all results
+    sorted by restart index) as ``OptimizeResult`` / list of tuples."""
+    from scipy.optimize import OptimizeResult
+    dist = _dist()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    local = []
+    for r in range(rank, len(starts), world):
+        res = optimize_fn(starts[r])
+        local.append((float(res.fun), r, np.asarray(res.x, dtype=np.float64), int(getattr(res, "nit", 0)),
+                      bool(getattr(res, "success", True))))
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, local)
+        allr = [t for g in gathered for t in g]
+    else:
+        allr = local
+    allr.sort(key=lambda t: t[1])
+    best = min(allr, key=lambda t: (t[0] if np.isfinite(t[0]) else np.inf, t[1]))
+    return OptimizeResult(x=best[2], fun=best[0], nit=best[3], success=best[4], restart=best[1]), allr

@@ -154,6 +154,12 @@ def _worker(rank, world, port, q):
     ch = torch.full((4, hi - lo, 2), float(r))
     out["chain"] = par.allgather_rows(ch, dim=1).numpy()
     out["range"] = (lo, hi)
+    # optimiser restarts sharded over ranks: same winner everywhere, ties -> lowest restart index
+    from scipy.optimize import minimize
+    starts = par.broadcast_object(np.random.default_rng(100 + r).uniform(-3, 3, size=(5, 2)))
+    fun = lambda x: float(np.sum((x ** 2 - 1.0) ** 2))             # four equal minima
+    best, allr = par.sharded_restarts(lambda x0: minimize(fun, x0, method="l-bfgs-b"), starts)
+    out["restarts"] = (best.fun, best.restart, best.x.tolist(), [t[1] for t in allr], starts.tolist())
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -177,6 +183,13 @@ def test_world_size_2_gloo_host_logic():
         assert res[r]["none"][1] == 7 + 51
         np.testing.assert_array_equal(res[r]["rows"][:, 0], np.arange(101))
         assert res[r]["chain"].shape == (4, 101, 2) and res[r]["chain"][0, 50, 0] == 0 and res[r]["chain"][0, 51, 0] == 1
+    assert res[0]["restarts"] == res[1]["restarts"]                 # identical winner and seeds on both ranks
+    fun_b, idx_b, x_b, order, starts = res[0]["restarts"]
+    assert order == [0, 1, 2, 3, 4] and fun_b < 1e-8
+    from scipy.optimize import minimize
+    serial = [minimize(lambda x: float(np.sum((x ** 2 - 1.0) ** 2)), np.array(s0), method="l-bfgs-b") for s0 in starts]
+    want = min(range(5), key=lambda i: (serial[i].fun, i))
+    assert idx_b == want and np.allclose(x_b, serial[want].x)
 
 
 def test_shard_range_covers_everything():
