@@ -154,6 +154,12 @@ int ab_gp_destroy(ab_gp* h) {
     return 0;
 }
 
+int ab_gp_debug_stamps(ab_gp* h, void* d_buf) {
+    AB_REQUIRE(h, -1, "null handle");
+    h->df_dbg = d_buf;
+    return 0;
+}
+
 int ab_gp_set_lookahead(ab_gp* h, int enabled) {
     AB_REQUIRE(h, -1, "null handle");
     h->lookahead = enabled;

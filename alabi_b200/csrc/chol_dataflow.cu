@@ -36,6 +36,45 @@ constexpr int BSTAGE = NB * Core::LDK;                   // one Dinv chunk [128]
 constexpr int DF_SMEM_BYTES = (C_ELEMS + Core::STAGES * BSTAGE) * 8;     // 217088
 static_assert(DF_SMEM_BYTES >= Core::SMEM_BYTES && DF_SMEM_BYTES <= 227 * 1024, "shared memory plan");
 
+constexpr int LDH = 64 + 4;                              // 64 x 64 blocks staged in the B ring
+
+// 64 x 64 x 64 product from shared memory on 8 warps (32 x 16 each):
+//   acc[m][n] = sum_k A[m][k] * (B_KMAJOR ? B[n][k] : B[k][n]);   lda, ldb == 4 (mod 16)
+// TRI prunes k4-steps whose operand block is structurally zero (warp-uniform):
+//   1: B zero for k > n     2: B zero for k < n     3: A zero for k > m
+template <bool B_KMAJOR, int TRI>
+__device__ __forceinline__ void gemm64(double (&acc)[4][2][2], const double* A, int lda, const double* B, int ldb,
+                                       int warp, int lane) {
+    const int g = lane >> 2, t = lane & 3, wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+    for (int f = 0; f < 4; f++)
+#pragma unroll
+        for (int q = 0; q < 2; q++) acc[f][q][0] = acc[f][q][1] = 0.0;
+#pragma unroll 4
+    for (int k4 = 0; k4 < 16; k4++) {
+        const int k0 = k4 * 4;
+        if (TRI == 1 && k0 > wn * 16 + 15) continue;
+        if (TRI == 2 && k0 + 3 < wn * 16) continue;
+        if (TRI == 3 && k0 > wm * 32 + 31) continue;
+        double fa[4], fb[2];
+#pragma unroll
+        for (int f = 0; f < 4; f++) fa[f] = A[(wm * 32 + f * 8 + g) * lda + k0 + t];
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+            fb[q] = B_KMAJOR ? B[(wn * 16 + q * 8 + g) * ldb + k0 + t] : B[(k0 + t) * ldb + wn * 16 + q * 8 + g];
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            if (TRI == 3 && k0 > wm * 32 + f * 8 + 7) continue;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (TRI == 1 && k0 > wn * 16 + q * 8 + 7) continue;
+                if (TRI == 2 && k0 + 3 < wn * 16 + q * 8) continue;
+                abg::dmma884(acc[f][q][0], acc[f][q][1], fa[f], fb[q]);
+            }
+        }
+    }
+}
+
 struct DfArgs {
     double* A; int64_t ld; int T;
     double* Dinv; double* logdet_parts; int* info;
@@ -43,7 +82,15 @@ struct DfArgs {
     unsigned int* next_task;      // task counter
     int* abort_flag;
     const int2* tasks; int ntasks;
+    unsigned long long* dbg;      // optional: 6 globaltimer stamps per task (development)
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DF_STAMP(slot) do { if (a.dbg && tid == 0) a.dbg[(size_t)task * 6 + (slot)] = gtime(); } while (0)
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
@@ -54,37 +101,61 @@ __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// wait until prog[row] > k; `seen` caches the last value this thread observed
+// wait until prog[row] > k; `seen` caches the last value this warp observed.  Called
+// convergently by whole warps: lane 0 polls (ld.acquire.gpu), the result is broadcast,
+// and the trailing __syncwarp + fence orders every lane's later loads after it.
 struct Waiter {
     const int* prog; int* abort_flag; bool aborted;
     __device__ __forceinline__ void wait(int row, int k, int& seen) {
         if (seen > k || aborted) return;
-        long long t0 = 0;
-        unsigned spins = 0;
-        for (;;) {
-            seen = ld_acquire(prog + row);
-            if (seen > k) break;
-            __nanosleep(40);
-            if ((++spins & 255u) == 0) {
-                if (t0 == 0) t0 = clock64();
-                if (*((volatile int*)abort_flag) != 0 || clock64() - t0 > 4000000000LL) {
-                    atomicExch(abort_flag, 1);
-                    aborted = true;
-                    return;
+        int v = seen, ab = 0;
+        if ((threadIdx.x & 31) == 0) {
+            long long t0 = 0;
+            unsigned spins = 0;
+            for (;;) {
+                v = ld_acquire(prog + row);
+                if (v > k) break;
+                if ((++spins & 255u) == 0) {
+                    if (t0 == 0) t0 = clock64();
+                    if (*((volatile int*)abort_flag) != 0 || clock64() - t0 > 4000000000LL) {
+                        atomicExch(abort_flag, 1);
+                        ab = 1;
+                        break;
+                    }
                 }
             }
+            __threadfence();
         }
+        __syncwarp();
+        seen = __shfl_sync(0xffffffffu, v, 0);
+        aborted = __shfl_sync(0xffffffffu, ab, 0) != 0;
     }
 };
 
+// gate of the accumulation loop: chunk c belongs to k block c / KB, final once both
+// block rows i and j have progressed past it
 struct RowGate {
-    Waiter* w; int i, j; int* seen_i; int* seen_j;
-    __device__ __forceinline__ void operator()(int c) const {
-        if ((c % Core::KB) == 0) {
-            const int k = c / Core::KB;
-            w->wait(i, k, *seen_i);
-            w->wait(j, k, *seen_j);
+    Waiter* w; int i, j; int seen_i, seen_j;
+    __device__ __forceinline__ bool ready(int c) {
+        if ((c % Core::KB) != 0) return true;                 // same k block as the chunk before it
+        const int k = c / Core::KB;
+        if (seen_i > k && seen_j > k) return true;
+        if (w->aborted) return true;
+        int vi = seen_i, vj = seen_j;
+        if ((threadIdx.x & 31) == 0) {
+            if (vi <= k) vi = ld_acquire(w->prog + i);
+            if (vj <= k) vj = ld_acquire(w->prog + j);
+            __threadfence();
         }
+        __syncwarp();
+        seen_i = __shfl_sync(0xffffffffu, vi, 0);
+        seen_j = __shfl_sync(0xffffffffu, vj, 0);
+        return seen_i > k && seen_j > k;
+    }
+    __device__ __forceinline__ void wait(int c) {
+        const int k = c / Core::KB;
+        w->wait(i, k, seen_i);
+        w->wait(j, k, seen_j);
     }
 };
 
@@ -95,6 +166,7 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
     __shared__ int s_task;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3, wm = warp / Core::WN, wn = warp % Core::WN;
+    const int wm64 = warp >> 2, wn64 = warp & 3;          // gemm64 warp grid
     Waiter w{a.prog, a.abort_flag, false};
     double* sC = smem;
     double* sBring = smem + C_ELEMS;
@@ -112,15 +184,22 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
         const int i = a.tasks[task].x, j = a.tasks[task].y;
         const int64_t row0 = (int64_t)i * NB, col0 = (int64_t)j * NB;
         int seen_i = 0, seen_j = 0;
+        DF_STAMP(0);
+        // the tile of K itself is only needed after the long accumulation: pull it into L2 now
+        for (int c = tid; c < NB * 8; c += Core::THREADS)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.A + (row0 + (c >> 3)) * a.ld + col0 + (c & 7) * 16));
 
         // ---- S = sum_{k<j} L_ik L_jk^T, gated per k block --------------------------
         abg::Acc acc;
         acc.zero();
         if (j > 0) {
-            RowGate gate{&w, i, j, &seen_i, &seen_j};
-            Core::mainloop<true, true, false, RowGate>(acc, a.A + row0 * a.ld, a.ld, a.A + col0 * a.ld, a.ld,
-                                                       j * Core::KB, smem, gate);
+            RowGate gate{&w, i, j, 0, 0};
+            Core::mainloop_gated<true, true>(acc, a.A + row0 * a.ld, a.ld, a.A + col0 * a.ld, a.ld, j * Core::KB, smem,
+                                             gate, i == j);
+            seen_i = gate.seen_i;
+            seen_j = gate.seen_j;
         }
+        DF_STAMP(1);
         // ---- C = A_ij - S, staged in shared memory ------------------------------------
         // (A_ij still holds the covariance values written before this launch)
 #pragma unroll
@@ -128,7 +207,7 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
             const int r = Core::acc_row(f);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const int c = Core::acc_col(q);
+                const int c = Core::gated_col(wn, q) + 2 * t;       // column mapping of mainloop_gated
                 const double2 v = *reinterpret_cast<const double2*>(a.A + (row0 + r) * a.ld + col0 + c);
                 double2 o;
                 o.x = v.x - acc.v[f][q][0];
@@ -137,50 +216,125 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
             }
         }
         __syncthreads();
+        DF_STAMP(2);
 
         if (i == j) {
-            // ---- diagonal tile: Cholesky + inverse (potf2.cuh sweep) --------------------
+            // ---- diagonal tile: Cholesky + inverse by 2 x 2 recursion on 64 x 64 blocks ----
+            //   [A11    ]   L11 = chol(A11), D11 = L11^-1          (register-tiled sweep, 64 columns)
+            //   [A21 A22]   L21 = A21 D11^T ; A22 -= L21 L21^T     (DMMA from shared memory)
+            //               L22 = chol(A22), D22 = L22^-1          (second sweep)
+            //               (L^-1)21 = -D22 (L21 D11)              (two DMMA products)
+            // D11 lives in the unused upper-right quadrant of sC, D22 and L21 D11 in the B ring.
             const int tx = tid & 15, ty = tid >> 4;
-            double pa[8][8], pb[8][8];
-#pragma unroll
-            for (int r = 0; r < 8; r++)
-#pragma unroll
-                for (int c = 0; c < 8; c++)
-                    if (r >= c) {
-                        const int ii = ty + 16 * r, kk = tx + 16 * c;
-                        pa[r][c] = (kk <= ii) ? sC[ii * LDC + kk] : 0.0;
-                        pb[r][c] = (kk == ii) ? 1.0 : 0.0;
-                    }
-            abp::potf2_sweep<true>(pa, pb, sh, tx, ty, col0, a.info, sweep_phase);
-            if (tid < 32) {
-                double s = 0.0;
-                for (int q = tid; q < NB; q += 32) s += 2.0 * log(sdiag[q]);
-                s = ab_warp_sum(s);
-                if (tid == 0) a.logdet_parts[j] = s;
-            }
+            double* Aj = a.A + col0 * a.ld + col0;
             double* Dj = a.Dinv + (int64_t)j * NB * NB;
+            double* sD11 = sC + 64;                       // [n][k], ld LDC
+            double* sD22 = sBring;                        // [m][k], ld LDH
+            double* sM1 = sBring + 64 * LDH;              // [k][n], ld LDH
+            double logdet = 0.0;
+            for (int half = 0; half < 2; half++) {
+                const int ob = half * 64;
+                double pa[4][4], pb[4][4];
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int ii = ty + 16 * r;
-                const double si = sinv[ii];
+                for (int r = 0; r < 4; r++)
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const int kk = tx + 16 * c;
-                    if (r >= c) {
-                        a.A[(col0 + ii) * a.ld + col0 + kk] = (kk < ii) ? pa[r][c] * sinv[kk] : ((kk == ii) ? sdiag[ii] : 0.0);
-                        Dj[ii * NB + kk] = (kk <= ii) ? pb[r][c] * si : 0.0;
-                    } else {
-                        a.A[(col0 + ii) * a.ld + col0 + kk] = 0.0;
-                        Dj[ii * NB + kk] = 0.0;
+                    for (int c = 0; c < 4; c++)
+                        if (r >= c) {
+                            const int ii = ty + 16 * r, kk = tx + 16 * c;
+                            pa[r][c] = (kk <= ii) ? sC[(ob + ii) * LDC + ob + kk] : 0.0;
+                            pb[r][c] = (kk == ii) ? 1.0 : 0.0;
+                        }
+                abp::potf2_sweep<true, 4>(pa, pb, sh, tx, ty, col0 + ob, a.info, sweep_phase);
+                if (tid < 32) {
+                    double s = 0.0;
+                    for (int q = tid; q < 64; q += 32) s += 2.0 * log(sdiag[q]);
+                    logdet += ab_warp_sum(s);
+                }
+                double* sDh = half == 0 ? sD11 : sD22;
+                const int ldh = half == 0 ? LDC : LDH;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int ii = ty + 16 * r;
+                    const double si = sinv[ii];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const int kk = tx + 16 * c;
+                        double lv = 0.0, dv = 0.0;
+                        if (r >= c) {
+                            lv = (kk < ii) ? pa[r][c] * sinv[kk] : ((kk == ii) ? sdiag[ii] : 0.0);
+                            dv = (kk <= ii) ? pb[r][c] * si : 0.0;
+                        }
+                        Aj[(int64_t)(ob + ii) * a.ld + ob + kk] = lv;
+                        Dj[(ob + ii) * NB + ob + kk] = dv;
+                        sDh[ii * ldh + kk] = dv;
+                        if (half == 0) {                   // upper-right quadrants of L and L^-1 are zero
+                            Aj[(int64_t)ii * a.ld + 64 + kk] = 0.0;
+                            Dj[ii * NB + 64 + kk] = 0.0;
+                        }
                     }
                 }
+                __syncthreads();
+                if (half == 0) {
+                    // L21 = A21 D11^T
+                    double acc2[4][2][2];
+                    gemm64<true, 1>(acc2, sC + 64 * LDC, LDC, sD11, LDC, warp, lane);
+                    __syncthreads();                       // every warp has read A21
+#pragma unroll
+                    for (int f = 0; f < 4; f++)
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            const int r = wm64 * 32 + f * 8 + g, c = wn64 * 16 + q * 8 + 2 * t;
+                            const double2 v = make_double2(acc2[f][q][0], acc2[f][q][1]);
+                            *reinterpret_cast<double2*>(sC + (64 + r) * LDC + c) = v;
+                            *reinterpret_cast<double2*>(Aj + (int64_t)(64 + r) * a.ld + c) = v;
+                        }
+                    __syncthreads();
+                    // A22 -= L21 L21^T
+                    gemm64<true, 0>(acc2, sC + 64 * LDC, LDC, sC + 64 * LDC, LDC, warp, lane);
+#pragma unroll
+                    for (int f = 0; f < 4; f++)
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            const int r = wm64 * 32 + f * 8 + g, c = wn64 * 16 + q * 8 + 2 * t;
+                            double2* p = reinterpret_cast<double2*>(sC + (64 + r) * LDC + 64 + c);
+                            double2 v = *p;
+                            v.x -= acc2[f][q][0];
+                            v.y -= acc2[f][q][1];
+                            *p = v;
+                        }
+                    __syncthreads();
+                }
+            }
+            if (tid == 0) a.logdet_parts[j] = logdet;
+            {
+                // (L^-1)21 = -D22 (L21 D11)
+                double acc2[4][2][2];
+                gemm64<false, 2>(acc2, sC + 64 * LDC, LDC, sD11, LDC, warp, lane);       // M1 = L21 D11
+#pragma unroll
+                for (int f = 0; f < 4; f++)
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int r = wm64 * 32 + f * 8 + g, c = wn64 * 16 + q * 8 + 2 * t;
+                        *reinterpret_cast<double2*>(sM1 + r * LDH + c) = make_double2(acc2[f][q][0], acc2[f][q][1]);
+                    }
+                __syncthreads();
+                gemm64<false, 3>(acc2, sD22, LDH, sM1, LDH, warp, lane);
+#pragma unroll
+                for (int f = 0; f < 4; f++)
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int r = wm64 * 32 + f * 8 + g, c = wn64 * 16 + q * 8 + 2 * t;
+                        *reinterpret_cast<double2*>(Dj + (64 + r) * NB + c) = make_double2(-acc2[f][q][0], -acc2[f][q][1]);
+                    }
             }
         } else {
             // ---- off-diagonal tile: L_ij = C D_j^-T (A operand resident, D_j^-1 streamed) ----
             w.wait(j, j, seen_j);                                    // diagonal tile of column j is final
+            DF_STAMP(3);
             const double* Dj = a.Dinv + (int64_t)j * NB * NB;
             abg::Acc out;
             out.zero();
+            const int cb = (wm == 0) ? wn : 3 - wn;                  // output column block of this warp
             constexpr int NK = NB / Core::BK;
 #pragma unroll
             for (int s = 0; s < Core::STAGES - 1; s++) {
@@ -194,29 +348,42 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
                 const int nx = kc + Core::STAGES - 1;
                 if (nx < NK) Core::load_operand<true, NB>(sBring + (nx % Core::STAGES) * BSTAGE, Dj + nx * Core::BK, NB, tid);
                 abg::cp_async_commit();
-                // D_j^-1 is lower triangular: column block c of the output only needs k <= c
+                // D_j^-1 is lower triangular: output column c only needs k <= c.  Column blocks
+                // are dealt so that the two warps of every scheduler hold blocks cb and 3 - cb
+                // (equal work per scheduler); n-fragments are pruned at 8-column granularity.
 #pragma unroll
                 for (int kk = 0; kk < Core::BK / 4; kk++) {
                     const int k0 = kc * Core::BK + kk * 4;
-                    if (k0 > wn * 32 + 31) continue;                 // warp-uniform
+                    if (k0 > cb * 32 + 31) continue;                 // warp-uniform
                     double fa[8], fb[4];
 #pragma unroll
                     for (int f = 0; f < 8; f++) fa[f] = sC[(wm * 64 + f * 8 + g) * LDC + k0 + t];
 #pragma unroll
-                    for (int f = 0; f < 4; f++) fb[f] = sB[(wn * 32 + f * 8 + g) * Core::LDK + kk * 4 + t];
+                    for (int f = 0; f < 4; f++) fb[f] = sB[(cb * 32 + f * 8 + g) * Core::LDK + kk * 4 + t];
 #pragma unroll
-                    for (int f = 0; f < 8; f++)
+                    for (int q = 0; q < 4; q++) {
+                        if (k0 > cb * 32 + q * 8 + 7) continue;
 #pragma unroll
-                        for (int q = 0; q < 4; q++) abg::dmma884(out.v[f][q][0], out.v[f][q][1], fa[f], fb[q]);
+                        for (int f = 0; f < 8; f++) abg::dmma884(out.v[f][q][0], out.v[f][q][1], fa[f], fb[q]);
+                    }
                 }
             }
             abg::cp_async_wait<0>();
-            Core::store_tile(out, a.A + row0 * a.ld + col0, a.ld, 1.0, 0.0);
+#pragma unroll
+            for (int f = 0; f < 8; f++) {
+                const int r = wm * 64 + f * 8 + g;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    *reinterpret_cast<double2*>(a.A + (row0 + r) * a.ld + col0 + cb * 32 + q * 8 + 2 * t) =
+                        make_double2(out.v[f][q][0], out.v[f][q][1]);
+            }
         }
         // ---- publish: the tile (and D_j^-1) is final -------------------------------------
+        DF_STAMP(4);
         __threadfence();
         __syncthreads();
         if (tid == 0) st_release(a.prog + i, j + 1);
+        DF_STAMP(5);
     }
 }
 
@@ -257,6 +424,7 @@ int ab_launch_factor_dataflow(ab_gp* h) {
     a.abort_flag = ctrl + 1;
     a.prog = ctrl + 2;
     a.tasks = reinterpret_cast<const int2*>(h->df_tasks); a.ntasks = ntasks;
+    a.dbg = reinterpret_cast<unsigned long long*>(h->df_dbg);
     const int grid = ntasks < h->nsm ? ntasks : h->nsm;
     ab_prof_begin(h, AB_PROF_FACTOR);
     chol_dataflow_kernel<<<grid, Core::THREADS, DF_SMEM_BYTES, s>>>(a);

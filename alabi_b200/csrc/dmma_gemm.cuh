@@ -65,6 +65,7 @@ struct Core {
     using Acc = abg::Acc;
     static_assert(LDK % 16 == 4 && LDRA % 16 == 4 && LDRB % 16 == 4, "leading dimensions must be 4 (mod 16) doubles");
     static_assert(SMEM_BYTES <= 227 * 1024, "pipeline does not fit shared memory");
+    static_assert(STAGES >= 2 && STAGES <= 5, "mainloop_gated counts at most STAGES - 1 pending groups");
 
     // Copy one ROWS x BK operand chunk global -> shared (all threads, 16 B per cp.async).
     template <bool KMAJOR, int ROWS>
@@ -166,6 +167,84 @@ struct Core {
                 for (int kk = 0; kk < BK / 4; kk++) {
                     k4step(kk, std::false_type{}, -1);
                     if (ORDER_ == 1 && kk == 0) prefetch();
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+
+    // Main loop for operands that other CTAs are still producing (dataflow Cholesky):
+    // gate.ready(c) is a non-blocking test "chunk c may be loaded", gate.wait(c) blocks.
+    // Loads run ahead only while the gate is open; the loop blocks only when the chunk
+    // it must multiply next has not been issued, i.e. after everything already in
+    // shared memory has been consumed.  cp.async groups are counted per thread (one
+    // group per chunk), so warps may open the gate at different times.
+    // Column mapping differs from mainloop(): n-fragment q of warp column wn covers the
+    // 8 columns gated_col(wn, q) = 8 (wn + WN q) (interleaved), so that `lower_only`
+    // (a diagonal tile: only columns <= rows matter) halves the work of EVERY warp in
+    // the upper row half instead of idling half of them.
+    static __device__ __forceinline__ int gated_col(int wn, int q) { return 8 * (wn + WN * q); }
+
+    template <bool AK, bool BKM, typename Gate>
+    static __device__ __forceinline__ void mainloop_gated(Acc& acc, const double* __restrict__ A, int64_t lda,
+                                                          const double* __restrict__ B, int64_t ldb, int nk,
+                                                          double* smem, Gate& gate, bool lower_only) {
+        const int tid = threadIdx.x;
+        const int lane = tid & 31, warp = tid >> 5;
+        const int g = lane >> 2, t = lane & 3;
+        const int wm = warp / WN, wn = warp % WN;
+        const int64_t a_step = AK ? (int64_t)BK : (int64_t)BK * lda;
+        const int64_t b_step = BKM ? (int64_t)BK : (int64_t)BK * ldb;
+        static_assert(WN == 4 && TN == 128, "gated column interleave assumes 4 warp columns of 32");
+        const bool skip_upper = lower_only && wm == 0;    // columns 8 (wn + 4 q) >= 64 for q >= 2
+        int issued = 0;
+        auto issue = [&](int c) {
+            const int st = c % STAGES;
+            load_operand<AK, TM>(smem + st * STAGE_ELEMS, A + c * a_step, lda, tid);
+            load_operand<BKM, TN>(smem + st * STAGE_ELEMS + OPER_ELEMS, B + c * b_step, ldb, tid);
+            cp_async_commit();
+            issued = c + 1;
+        };
+        for (int kc = 0; kc < nk; kc++) {
+            if (issued <= kc) {
+                gate.wait(kc);
+                issue(kc);
+            }
+            switch (issued - kc - 1) {                 // groups younger than chunk kc's
+                case 0: cp_async_wait<0>(); break;
+                case 1: cp_async_wait<1>(); break;
+                case 2: cp_async_wait<2>(); break;
+                default: cp_async_wait<STAGES - 2>(); break;
+            }
+            __syncthreads();
+            const double* sA = smem + (kc % STAGES) * STAGE_ELEMS;
+            const double* sB = sA + OPER_ELEMS;
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; kk++) {
+                double a[8], b[4];
+#pragma unroll
+                for (int f = 0; f < 8; f++)
+                    a[f] = AK ? sA[(wm * 64 + f * 8 + g) * LDK + kk * 4 + t]
+                              : sA[(kk * 4 + t) * LDRA + wm * 64 + f * 8 + g];
+#pragma unroll
+                for (int f = 0; f < 4; f++)
+                    b[f] = BKM ? sB[(gated_col(wn, f) + g) * LDK + kk * 4 + t]
+                               : sB[(kk * 4 + t) * LDRB + gated_col(wn, f) + g];
+                if (skip_upper) {                      // rows 0..63 of a diagonal tile: columns < 64 only
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+                }
+                if (kk == 0) {
+                    // slot of chunk nx held chunk nx - STAGES, consumed before this iteration's barrier
+                    while (issued < nk && issued < kc + STAGES && gate.ready(issued)) issue(issued);
                 }
             }
         }

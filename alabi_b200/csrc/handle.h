@@ -50,6 +50,7 @@ struct ab_gp {
     int lookahead = 2;                    // factor schedule: 0 plain sweep, 1 look-ahead streams, 2 dataflow kernel
     void* df_tasks = nullptr;             // dataflow task list (device) for df_tasks_T block rows
     int df_tasks_T = 0;
+    void* df_dbg = nullptr;               // development: per-task time stamps of the dataflow kernel (caller-owned)
     bool factored = false, have_linv = false, have_kinv = false, have_alpha = false;
     int info = 0;
     double logdet = 0.0, quad = 0.0;

@@ -59,8 +59,8 @@ struct SweepShared {
 // arrives on the barrier, and only then applies the bulk of the rank-1 updates,
 // so the barrier / shared-memory / reciprocal latency of step j + 1 is hidden
 // behind the bulk of step j.  JRN == 8: last column, nothing to publish.
-template <bool FACTOR, int JR, int JRN>
-__device__ __forceinline__ void potf2_step(double (&a)[8][8], double (&b)[8][8], SweepShared& sh, int jm, int tx,
+template <bool FACTOR, int R, int JR, int JRN>
+__device__ __forceinline__ void potf2_step(double (&a)[R][R], double (&b)[R][R], SweepShared& sh, int jm, int tx,
                                            int ty, int64_t o, int* info, unsigned mbar, unsigned& phase) {
     const int j = JR * 16 + jm, buf = jm & 1;
     mbar_wait(mbar, phase & 1u);
@@ -77,12 +77,12 @@ __device__ __forceinline__ void potf2_step(double (&a)[8][8], double (&b)[8][8],
     // The triangular structure is enforced by zeroing OPERANDS, not by predicating the
     // FMAs: valid entries (A: i >= k > j, B: c <= j < i) only ever consume valid
     // entries; entries outside those regions may hold garbage and are never read back.
-    double ai[8], ak[8], xk[8];
+    double ai[R], ak[R], xk[R];
 #pragma unroll
-    for (int r = JR; r < 8; r++) ai[r] = sh.colA[buf][ty + 16 * r];
+    for (int r = JR; r < R; r++) ai[r] = sh.colA[buf][ty + 16 * r];
     if (FACTOR) {
 #pragma unroll
-        for (int c = JR; c < 8; c++) ak[c] = sh.colA[buf][tx + 16 * c] * ip;
+        for (int c = JR; c < R; c++) ak[c] = sh.colA[buf][tx + 16 * c] * ip;
         ak[JR] = (tx > jm) ? ak[JR] : 0.0;                      // columns k <= j are final
     }
 #pragma unroll
@@ -90,16 +90,16 @@ __device__ __forceinline__ void potf2_step(double (&a)[8][8], double (&b)[8][8],
     xk[JR] = (tx <= jm) ? xk[JR] : 0.0;                         // B[j][c] = 0 for c > j
     const double ab_jr = (ty > jm) ? ai[JR] : 0.0;              // rows i <= j of B are final
 
-    if (JRN < 8) {
-        constexpr int N = JRN < 8 ? JRN : 7;
+    if (JRN < R) {
+        constexpr int N = JRN < R ? JRN : R - 1;
         const int jn = (JRN == JR) ? jm + 1 : 0;
         if (FACTOR) {
 #pragma unroll
-            for (int r = N; r < 8; r++) a[r][N] = fma(-ai[r], ak[N], a[r][N]);
+            for (int r = N; r < R; r++) a[r][N] = fma(-ai[r], ak[N], a[r][N]);
         }
         if (tx == jn) {
 #pragma unroll
-            for (int r = N; r < 8; r++) sh.colA[buf ^ 1][ty + 16 * r] = a[r][N];
+            for (int r = N; r < R; r++) sh.colA[buf ^ 1][ty + 16 * r] = a[r][N];
         }
 #pragma unroll
         for (int c = 0; c <= JR; c++) b[N][c] = fma(-(N == JR ? ab_jr : ai[N]), xk[c], b[N][c]);
@@ -111,52 +111,47 @@ __device__ __forceinline__ void potf2_step(double (&a)[8][8], double (&b)[8][8],
     }
     if (FACTOR) {
 #pragma unroll
-        for (int c = JR; c < 8; c++)
+        for (int c = JR; c < R; c++)
             if (c != JRN) {
 #pragma unroll
-                for (int r = c; r < 8; r++) a[r][c] = fma(-ai[r], ak[c], a[r][c]);
+                for (int r = c; r < R; r++) a[r][c] = fma(-ai[r], ak[c], a[r][c]);
             }
     }
 #pragma unroll
-    for (int r = JR; r < 8; r++)
+    for (int r = JR; r < R; r++)
         if (r != JRN) {
 #pragma unroll
             for (int c = 0; c <= JR; c++) b[r][c] = fma(-(r == JR ? ab_jr : ai[r]), xk[c], b[r][c]);
         }
 }
 
-template <bool FACTOR, int JR>
-__device__ __forceinline__ void sweep16(double (&a)[8][8], double (&b)[8][8], SweepShared& sh, int tx, int ty,
+template <bool FACTOR, int R, int JR>
+__device__ __forceinline__ void sweep16(double (&a)[R][R], double (&b)[R][R], SweepShared& sh, int tx, int ty,
                                         int64_t o, int* info, unsigned mbar, unsigned& phase) {
-    for (int jm = 0; jm < 15; jm++) potf2_step<FACTOR, JR, JR>(a, b, sh, jm, tx, ty, o, info, mbar, phase);
-    potf2_step<FACTOR, JR, JR + 1>(a, b, sh, 15, tx, ty, o, info, mbar, phase);
+    for (int jm = 0; jm < 15; jm++) potf2_step<FACTOR, R, JR, JR>(a, b, sh, jm, tx, ty, o, info, mbar, phase);
+    potf2_step<FACTOR, R, JR, JR + 1>(a, b, sh, 15, tx, ty, o, info, mbar, phase);
+    if constexpr (JR + 1 < R) sweep16<FACTOR, R, JR + 1>(a, b, sh, tx, ty, o, info, mbar, phase);
 }
 
-// Whole 128-column sweep on the register-tiled block (a: block -> unscaled L columns,
-// b: identity -> unscaled L^-1 rows).  On return sh.sdiag = diag(L), sh.sinv = 1 / diag(L)
-// (after a __syncthreads inside).  All 256 threads; `phase` is the running count of
-// completed barrier phases of sh.mbar (kept by the caller across calls).
-template <bool FACTOR>
-__device__ __forceinline__ void potf2_sweep(double (&a)[8][8], double (&b)[8][8], SweepShared& sh, int tx, int ty,
+// Whole 16 R-column sweep on the register-tiled block (a: block -> unscaled L columns,
+// b: identity -> unscaled L^-1 rows); R = 8: 128 x 128, R = 4: 64 x 64 (same 16 x 16
+// thread grid, R x R cyclic entries per thread).  On return sh.sdiag = diag(L),
+// sh.sinv = 1 / diag(L) (after a __syncthreads inside).  All 256 threads; `phase` is
+// the running count of completed barrier phases of sh.mbar (kept by the caller).
+template <bool FACTOR, int R = 8>
+__device__ __forceinline__ void potf2_sweep(double (&a)[R][R], double (&b)[R][R], SweepShared& sh, int tx, int ty,
                                             int64_t o, int* info, unsigned& phase) {
     const unsigned mbar = (unsigned)__cvta_generic_to_shared(&sh.mbar);
     // publish column 0 of A and row 0 of B
     if (tx == 0) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) sh.colA[0][ty + 16 * r] = a[r][0];
+        for (int r = 0; r < R; r++) sh.colA[0][ty + 16 * r] = a[r][0];
     }
     if (ty == 0) sh.rowB[0][tx] = b[0][0];
     mbar_arrive(mbar);
-    sweep16<FACTOR, 0>(a, b, sh, tx, ty, o, info, mbar, phase);
-    sweep16<FACTOR, 1>(a, b, sh, tx, ty, o, info, mbar, phase);
-    sweep16<FACTOR, 2>(a, b, sh, tx, ty, o, info, mbar, phase);
-    sweep16<FACTOR, 3>(a, b, sh, tx, ty, o, info, mbar, phase);
-    sweep16<FACTOR, 4>(a, b, sh, tx, ty, o, info, mbar, phase);
-    sweep16<FACTOR, 5>(a, b, sh, tx, ty, o, info, mbar, phase);
-    sweep16<FACTOR, 6>(a, b, sh, tx, ty, o, info, mbar, phase);
-    sweep16<FACTOR, 7>(a, b, sh, tx, ty, o, info, mbar, phase);
+    sweep16<FACTOR, R, 0>(a, b, sh, tx, ty, o, info, mbar, phase);
     __syncthreads();
-    if (threadIdx.x < NB) {                           // pivots -> diagonal of L and its reciprocal
+    if (threadIdx.x < 16 * R) {                       // pivots -> diagonal of L and its reciprocal
         const double dj = FACTOR ? sqrt(sh.sdiag[threadIdx.x]) : sh.sdiag[threadIdx.x];
         sh.sdiag[threadIdx.x] = dj;
         sh.sinv[threadIdx.x] = 1.0 / dj;
@@ -195,7 +190,7 @@ potf2_inv_kernel(double* __restrict__ A, int64_t ld, int64_t o, double* __restri
             }
         }
     unsigned phase = 0;
-    potf2_sweep<FACTOR>(a, b, sh, tx, ty, o, info, phase);
+    potf2_sweep<FACTOR, 8>(a, b, sh, tx, ty, o, info, phase);
     double* sdiag = sh.sdiag;
     double* sinv = sh.sinv;
     if (tid < 32) {

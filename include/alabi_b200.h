@@ -70,6 +70,9 @@ int ab_gp_profile_read(ab_gp* h, int family, double* h_ms, long long* h_count);
 int ab_gp_create(ab_gp** out, int device, void* cuda_stream);
 int ab_gp_destroy(ab_gp* h);
 int ab_gp_set_lookahead(ab_gp* h, int enabled);
+/* development aid: device buffer (6 x uint64 per tile task, column-major task order) that the
+ * dataflow Cholesky fills with %globaltimer stamps; NULL (default) disables it */
+int ab_gp_debug_stamps(ab_gp* h, void* d_buf);
 
 /* Append ONE training point (d doubles on the device, same space as X) to a
  * factorised model in O(N^2): bordered Cholesky update instead of the full
