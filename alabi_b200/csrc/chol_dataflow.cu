@@ -204,10 +204,10 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
         // (A_ij still holds the covariance values written before this launch)
 #pragma unroll
         for (int f = 0; f < 8; f++) {
-            const int r = Core::acc_row(f);
+            const int r = Core::gated_row(wm, f) + g;               // row / column mapping of mainloop_gated
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const int c = Core::gated_col(wn, q) + 2 * t;       // column mapping of mainloop_gated
+                const int c = Core::gated_col(wn, q) + 2 * t;
                 const double2 v = *reinterpret_cast<const double2*>(a.A + (row0 + r) * a.ld + col0 + c);
                 double2 o;
                 o.x = v.x - acc.v[f][q][0];

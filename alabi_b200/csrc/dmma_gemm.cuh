@@ -62,6 +62,12 @@ struct Core {
     static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
     static constexpr int SMEM_BYTES = STAGES * STAGE_ELEMS * 8;
     static constexpr int KB = 128 / BK;           // chunks per 128-wide k block
+    // first row of m-fragment f of warp row wm.  (Warps w and w + 4 share a scheduler and
+    // are the two warp rows of one warp column, so contiguous rows already balance a
+    // triangular A block across schedulers; interleaving them was measured slower.)
+    static __device__ __forceinline__ int frag_row(int wm, int f) { return wm * 64 + f * 8; }
+    // mainloop_gated interleaves rows AND columns (see there)
+    static __device__ __forceinline__ int gated_row(int wm, int f) { return (f * WM + wm) * 8; }
     using Acc = abg::Acc;
     static_assert(LDK % 16 == 4 && LDRA % 16 == 4 && LDRB % 16 == 4, "leading dimensions must be 4 (mod 16) doubles");
     static_assert(SMEM_BYTES <= 227 * 1024, "pipeline does not fit shared memory");
@@ -138,22 +144,22 @@ struct Core {
                 double a[8], b[4];
 #pragma unroll
                 for (int f = 0; f < 8; f++)
-                    a[f] = AK ? sA[(wm * 64 + f * 8 + g) * LDK + kk * 4 + t]
-                              : sA[(kk * 4 + t) * LDRA + wm * 64 + f * 8 + g];
+                    a[f] = AK ? sA[(frag_row(wm, f) + g) * LDK + kk * 4 + t]
+                              : sA[(kk * 4 + t) * LDRA + frag_row(wm, f) + g];
 #pragma unroll
                 for (int f = 0; f < 4; f++)
                     b[f] = BKM ? sB[(wn * 32 + f * 8 + g) * LDK + kk * 4 + t]
                                : sB[(kk * 4 + t) * LDRB + wn * 32 + f * 8 + g];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    if (decltype(tri)::value && ktri > wm * 64 + i * 8 + 7) continue;
+                    if (decltype(tri)::value && ktri > frag_row(wm, i) + 7) continue;
 #pragma unroll
                     for (int j = 0; j < 4; j++) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
                 }
             };
             if (TRI_A && kc >= nk - KB) {            // chunk inside the triangular diagonal block
                 const int k0 = (kc - (nk - KB)) * BK;
-                if (k0 > wm * 64 + 63) {             // nothing left for this warp's rows
+                if (k0 > frag_row(wm, 7) + 7) {      // nothing left for this warp's rows
                     if (ORDER_ == 1) prefetch();
                 } else {
 #pragma unroll
@@ -197,7 +203,9 @@ struct Core {
         const int64_t a_step = AK ? (int64_t)BK : (int64_t)BK * lda;
         const int64_t b_step = BKM ? (int64_t)BK : (int64_t)BK * ldb;
         static_assert(WN == 4 && TN == 128, "gated column interleave assumes 4 warp columns of 32");
-        const bool skip_upper = lower_only && wm == 0;    // columns 8 (wn + 4 q) >= 64 for q >= 2
+        // rows and columns are both interleaved: m-fragment i holds rows 16 i + 8 wm, n-fragment q
+        // columns 32 q + 8 wn.  For a diagonal tile only (i, q) with 32 q <= 16 i + 15 matter.
+        const bool skip_upper = lower_only;
         int issued = 0;
         auto issue = [&](int c) {
             const int st = c % STAGES;
@@ -225,17 +233,18 @@ struct Core {
                 double a[8], b[4];
 #pragma unroll
                 for (int f = 0; f < 8; f++)
-                    a[f] = AK ? sA[(wm * 64 + f * 8 + g) * LDK + kk * 4 + t]
-                              : sA[(kk * 4 + t) * LDRA + wm * 64 + f * 8 + g];
+                    a[f] = AK ? sA[(gated_row(wm, f) + g) * LDK + kk * 4 + t]
+                              : sA[(kk * 4 + t) * LDRA + gated_row(wm, f) + g];
 #pragma unroll
                 for (int f = 0; f < 4; f++)
                     b[f] = BKM ? sB[(gated_col(wn, f) + g) * LDK + kk * 4 + t]
                                : sB[(kk * 4 + t) * LDRB + gated_col(wn, f) + g];
-                if (skip_upper) {                      // rows 0..63 of a diagonal tile: columns < 64 only
+                if (skip_upper) {                      // diagonal tile: fragments strictly above the diagonal are skipped
 #pragma unroll
                     for (int i = 0; i < 8; i++)
 #pragma unroll
-                        for (int j = 0; j < 2; j++) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
+                        for (int j = 0; j < 4; j++)
+                            if (32 * j <= 16 * i + 15) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 8; i++)
@@ -255,7 +264,7 @@ struct Core {
     // Element (row, col) owned by acc.v[i][j][e] inside the CTA tile.
     static __device__ __forceinline__ int acc_row(int i) {
         int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        return (warp / WN) * 64 + i * 8 + (lane >> 2);
+        return frag_row(warp / WN, i) + (lane >> 2);
     }
     static __device__ __forceinline__ int acc_col(int j) {
         int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
