@@ -64,6 +64,36 @@ __device__ __forceinline__ double ab_exp_neg(double x) {
     return (x > -707.0) ? res : 0.0;
 }
 
+// Table-free variant of ab_exp_neg for kernels with few resident warps (cov, gradient
+// tiles), where the L1 latency of the table load is not hidden:
+// n = rint(x log2 e), f = x - n ln2 (Cody-Waite), degree-13 Taylor on |f| <= 0.347
+// (remainder 4e-18), scaling by 2^n through the exponent field; exp(x) < 1e-307
+// flushes to 0.  Relative error ~2e-16, no slow-path call, no divergence.
+__device__ __forceinline__ double ab_exp_neg_poly(double x) {
+    const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52
+    double t = fma(x, 1.4426950408889634, SHIFT);
+    int n = __double2loint(t);
+    double nf = t - SHIFT;
+    double f = fma(nf, -6.93147180369123816490e-01, x);
+    f = fma(nf, -1.90821492927058770002e-10, f);
+    double p = 1.6059043836821613e-10;                       // 1/13!
+    p = fma(p, f, 2.0876756987868100e-09);                   // 1/12!
+    p = fma(p, f, 2.5052108385441720e-08);                   // 1/11!
+    p = fma(p, f, 2.7557319223985893e-07);                   // 1/10!
+    p = fma(p, f, 2.7557319223985888e-06);                   // 1/9!
+    p = fma(p, f, 2.4801587301587302e-05);                   // 1/8!
+    p = fma(p, f, 1.9841269841269841e-04);                   // 1/7!
+    p = fma(p, f, 1.3888888888888889e-03);                   // 1/6!
+    p = fma(p, f, 8.3333333333333332e-03);                   // 1/5!
+    p = fma(p, f, 4.1666666666666664e-02);                   // 1/4!
+    p = fma(p, f, 1.6666666666666666e-01);                   // 1/3!
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    double r = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    return (x > -707.0) ? r : 0.0;
+}
+
 // Branch-free sqrt(x) for finite x >= 0: MUFU.RSQ64H seed, two Newton steps on
 // 1/sqrt, one correction of the root (<= 1 ulp); x < 1e-290 returns 0.
 __device__ __forceinline__ double ab_sqrt_pos(double x) {
@@ -79,21 +109,26 @@ __device__ __forceinline__ double ab_sqrt_pos(double x) {
     return (x > 1e-290) ? s : 0.0;
 }
 
-template <int KIND>
+// TAB = true: table-based exp (fewest FP64 instructions; needs enough resident warps to
+// hide one L1 load), false: polynomial-only exp.  Both are ~1 ulp.
+template <bool TAB>
+__device__ __forceinline__ double ab_exp_sel(double x) { return TAB ? ab_exp_neg(x) : ab_exp_neg_poly(x); }
+
+template <int KIND, bool TAB = true>
 __device__ __forceinline__ double ab_radial(double r2) {
-    if (KIND == 0) return ab_exp_neg(-0.5 * r2);
-    if (KIND == 1) { double r = ab_sqrt_pos(3.0 * r2); return (1.0 + r) * ab_exp_neg(-r); }
+    if (KIND == 0) return ab_exp_sel<TAB>(-0.5 * r2);
+    if (KIND == 1) { double r = ab_sqrt_pos(3.0 * r2); return (1.0 + r) * ab_exp_sel<TAB>(-r); }
     double r = ab_sqrt_pos(5.0 * r2);
-    return (1.0 + r + r * r * 0.3333333333333333) * ab_exp_neg(-r);
+    return (1.0 + r + r * r * 0.3333333333333333) * ab_exp_sel<TAB>(-r);
 }
 
 // dk/d(r^2)
-template <int KIND>
+template <int KIND, bool TAB = true>
 __device__ __forceinline__ double ab_radial_grad(double r2) {
-    if (KIND == 0) return -0.5 * ab_exp_neg(-0.5 * r2);
-    if (KIND == 1) { double r = ab_sqrt_pos(3.0 * r2); return -1.5 * ab_exp_neg(-r); }
+    if (KIND == 0) return -0.5 * ab_exp_sel<TAB>(-0.5 * r2);
+    if (KIND == 1) { double r = ab_sqrt_pos(3.0 * r2); return -1.5 * ab_exp_sel<TAB>(-r); }
     double r = ab_sqrt_pos(5.0 * r2);
-    return -5.0 * (1.0 + r) * ab_exp_neg(-r) * 0.16666666666666666;
+    return -5.0 * (1.0 + r) * ab_exp_sel<TAB>(-r) * 0.16666666666666666;
 }
 
 #define AB_DISPATCH_KIND(kind, ...)                                   \

@@ -57,8 +57,8 @@ grad_tiles_kernel(const double* __restrict__ Kinv, int64_t ld, const double* __r
             } else d2[k] = 0.0;
         }
         const double a = wt * (sAi[r] * aj - Kinv[gi * ld + j0 + c]);
-        s_c = fma(a, kp.amp * ab_radial<KIND>(r2), s_c);
-        const double gk = -a * kp.amp * ab_radial_grad<KIND>(r2);
+        s_c = fma(a, kp.amp * ab_radial<KIND, false>(r2), s_c);
+        const double gk = -a * kp.amp * ab_radial_grad<KIND, false>(r2);
 #pragma unroll
         for (int k = 0; k < DMAX; k++)
             if (k < d) s_m[k] = fma(gk, d2[k], s_m[k]);

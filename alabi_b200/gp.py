@@ -401,12 +401,15 @@ class GP:
             m = tq.shape[0]
             mu = torch.empty(m, dtype=torch.float64, device=tq.device)
             var = torch.empty(m, dtype=torch.float64, device=tq.device) if want_var else None
-            _lib.check(hd.lib.ab_gp_predict(hd.h, _lib.ptr(tq), m, _lib.ptr(mu), _lib.ptr(var)), "ab_gp_predict")
+            if m > 0:
+                _lib.check(hd.lib.ab_gp_predict(hd.h, _lib.ptr(tq), m, _lib.ptr(mu), _lib.ptr(var)), "ab_gp_predict")
             return (mu, var) if want_var else mu
         xs = self.parse_samples(t)
         m = xs.shape[0]
         mu = np.empty(m, dtype=np.float64)
         var = np.empty(m, dtype=np.float64) if want_var else None
+        if m == 0:
+            return (mu, var) if want_var else mu
         _lib.check(hd.lib.ab_gp_predict_host(hd.h, _lib.ptr(xs), m, _lib.ptr(mu), _lib.ptr(var)), "ab_gp_predict_host")
         return (mu, var) if want_var else mu
 
@@ -444,6 +447,8 @@ class GP:
         m = cq.shape[0]
         b = np.ascontiguousarray(np.asarray(bounds, dtype=np.float64).reshape(-1))
         util = torch.empty(m, dtype=torch.float64, device=cq.device) if return_values else None
+        if m == 0:                                   # empty candidate set: no finite utility
+            return (-1, float("inf"), util) if return_values else (-1, float("inf"))
         idx, val = ctypes.c_int64(), ctypes.c_double()
         _lib.check(hd.lib.ab_gp_utility_argmin(hd.h, uid, _lib.ptr(cq), m, b.ctypes.data_as(_lib.c_double_p),
                                                float(y_best), float(zeta), _lib.ptr(util), ctypes.byref(idx),
