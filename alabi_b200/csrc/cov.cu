@@ -37,7 +37,7 @@ __global__ void scale_points_kernel(const double* __restrict__ X, int64_t m, int
 // diag_add, optional mirror; rows/cols >= n_valid become identity when
 // pad_identity (padding of the blocked factorisation).
 template <int KIND>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 cov_kernel(const double* __restrict__ AT, int64_t lda, int64_t na, const double* __restrict__ BT, int64_t ldb,
            int64_t nb, int64_t n_valid, KernParams kp, double* __restrict__ K, int64_t ld, int symmetric,
            int mirror, int pad_identity) {

@@ -406,10 +406,11 @@ class GP:
             return (mu, var) if want_var else mu
         xs = self.parse_samples(t)
         m = xs.shape[0]
+        if m == 0:
+            e = np.empty(0, dtype=np.float64)
+            return (e, e.copy()) if want_var else e
         mu = np.empty(m, dtype=np.float64)
         var = np.empty(m, dtype=np.float64) if want_var else None
-        if m == 0:
-            return (mu, var) if want_var else mu
         _lib.check(hd.lib.ab_gp_predict_host(hd.h, _lib.ptr(xs), m, _lib.ptr(mu), _lib.ptr(var)), "ab_gp_predict_host")
         return (mu, var) if want_var else mu
 
