@@ -66,19 +66,21 @@ __device__ __forceinline__ int member_of(const EnsArgs& A, int i, int s, unsigne
 }
 
 // grid barrier split in two: arrive as soon as this CTA's updates are published,
-// wait only when the next half-step needs the other CTAs' updates
+// wait only when the next half-step needs the other CTAs' updates.  Release / acquire
+// on the counter itself orders the walker updates (no separate fences).
 __device__ __forceinline__ void grid_arrive(unsigned long long* counter, unsigned long long& target) {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        __threadfence();
-        atomicAdd(counter, 1ULL);
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(counter), "l"(1ULL) : "memory");
     }
 }
 __device__ __forceinline__ void grid_wait(unsigned long long* counter, unsigned long long target) {
     if (threadIdx.x == 0) {
-        while (*((volatile unsigned long long*)counter) < target) { }
-        __threadfence();
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
+        } while (v < target);
     }
     __syncthreads();
 }
@@ -172,6 +174,9 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
     if (first < A.nsteps) prep(first, 0, blockIdx.x);
     for (int step = first; step < A.nsteps; step++) {
         const int nsplit = (step < 0) ? 1 : 2;
+        // row of the stored chain this step writes (-1: not stored)
+        const long long store_row = (A.chain && step >= 0 && (step + 1) % A.thin_by == 0)
+                                        ? (long long)((step + 1) / A.thin_by - 1) : -1;
         for (int split = 0; split < nsplit; split++) {
             const int n_items = (step < 0) ? nw : (split == 0 ? (nw + 1) / 2 : nw / 2);
             const int nbatch = (n_items + P * G - 1) / (P * G);
@@ -267,8 +272,12 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 if (prop_lane) {
                     const int e = lane, w = sW[unit][e];
                     if (w >= 0) {
+                        double pv[EW];                       // independent loads, then the fixed-order sum
+#pragma unroll
+                        for (int x = 0; x < EW; x++) pv[x] = (x < WS) ? sPart[unit * WS + x][e] : 0.0;
                         double s = 0.0;
-                        for (int x = 0; x < WS; x++) s += sPart[unit * WS + x][e];
+#pragma unroll
+                        for (int x = 0; x < EW; x++) s += pv[x];
                         double ys = fma(A.kp.amp, s, A.mean);
                         double y = (A.y_kind == 0) ? fma(ys, A.y_scale, A.y_off)
                                  : (A.y_kind == 1) ? -pow(10.0, ys) : pow(10.0, ys);
@@ -291,8 +300,8 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                                 for (int k = 0; k < d; k++) A.rec_q[r * d + k] = sQ[unit][e][k];
                                 A.rec_lp[r] = lp_q;
                             }
-                            if (A.chain && (step + 1) % A.thin_by == 0) {
-                                long long r = (long long)((step + 1) / A.thin_by - 1) * nw + w;
+                            if (store_row >= 0) {
+                                long long r = store_row * nw + w;
                                 for (int k = 0; k < d; k++)
                                     A.chain[r * d + k] = acc ? sQ[unit][e][k] : sS[unit][e][k];
                                 A.logp_chain[r] = lp_s;
