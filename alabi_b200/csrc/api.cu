@@ -145,6 +145,7 @@ int ab_gp_destroy(ab_gp* h) {
         if (b) cudaFree(b);
     if (h->d_info) cudaFree(h->d_info);
     if (h->df_tasks) cudaFree(h->df_tasks);
+    if (h->cov_items) cudaFree(h->cov_items);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->panel_stream) cudaStreamDestroy(h->panel_stream);
     cudaEvent_t evs[] = {h->ev_panel, h->ev_col, h->ev_fork, h->ev_join};

@@ -50,6 +50,8 @@ struct ab_gp {
     int lookahead = 2;                    // factor schedule: 0 plain sweep, 1 look-ahead streams, 2 dataflow kernel
     void* df_tasks = nullptr;             // dataflow task list (device) for df_tasks_T block rows
     int df_tasks_T = 0;
+    void* cov_items = nullptr;            // work list of cov_strip_kernel for cov_items_nt tile rows
+    int cov_items_nt = 0, cov_items_seg = 0, cov_items_count = 0;
     void* df_dbg = nullptr;               // development: per-task time stamps of the dataflow kernel (caller-owned)
     bool factored = false, have_linv = false, have_kinv = false, have_alpha = false;
     int info = 0;

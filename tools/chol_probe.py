@@ -31,6 +31,17 @@ for n in [int(s) for s in os.environ.get("PROBE_SIZES", "2048,4096,8192,16384").
         g._set_targets(y)
         L, alpha = g.export_state()
         Ls[la] = (L[:n, :n].clone(), alpha.clone())
+    import ctypes
+    lib.ab_gp_set_lookahead(h, 2)
+    lib.ab_gp_set_profiling(h, 1)
+    for _ in range(3):
+        lib.ab_gp_factor(h)
+    torch.cuda.synchronize()
+    ms, cnt = ctypes.c_double(), ctypes.c_longlong()
+    lib.ab_gp_profile_read(h, 0, ctypes.byref(ms), ctypes.byref(cnt))
+    res["cov_lower_ms"] = round(ms.value / max(cnt.value, 1), 4)
+    res["cov_lower_gbs"] = round(4.0 * n * n / (ms.value / max(cnt.value, 1) * 1e-3) * 1e-9, 1)
+    lib.ab_gp_set_profiling(h, 0)
     if len(Ls) == 2:
         res["max_abs_dL"] = float((Ls[1][0] - Ls[2][0]).abs().max())
         res["rel_dalpha"] = float((Ls[1][1] - Ls[2][1]).abs().max() / Ls[1][1].abs().max())
