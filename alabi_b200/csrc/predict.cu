@@ -98,51 +98,108 @@ __global__ void combine_splits_kernel(const double* __restrict__ partial, int64_
     mu[q_off + q] = fma(amp, s, mean);
 }
 
-// sigma^2 for the 128 queries of this CTA:  amp - sum_i ( sum_k Linv[i][k] P[k][q] )^2
-__global__ void __launch_bounds__(abg::THREADS, 1)
-predict_var_kernel(const double* __restrict__ Linv, int64_t ld, int T, const double* __restrict__ P, int64_t ldp,
-                   int64_t m, int64_t q_off, double amp, double* __restrict__ var) {
-    extern __shared__ __align__(16) double smem[];
-    const double* Bp = P + (int64_t)blockIdx.x * abg::BN;
-    double ss[4][2];
+// Per-thread sums of squares of one 128 x 128 product tile: blk[j][e] = sum over the 8
+// m-fragments of acc^2 (a chain that starts at zero for every row block).
+__device__ __forceinline__ void tile_thread_sq(const abg::Acc& acc, double (&blk)[4][2]) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) ss[j][0] = ss[j][1] = 0.0;
-    for (int i = 0; i < T; i++) {
-        abg::Acc acc;
-        acc.zero();
-        abg::mainloop<true, false, true>(acc, Linv + (int64_t)i * NB * ld, ld, Bp, ldp, (i + 1) * (NB / abg::BK), smem);
+    for (int j = 0; j < 4; j++) {
+        blk[j][0] = blk[j][1] = 0.0;
 #pragma unroll
-        for (int a = 0; a < 8; a++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                ss[j][0] = fma(acc.v[a][j][0], acc.v[a][j][0], ss[j][0]);
-                ss[j][1] = fma(acc.v[a][j][1], acc.v[a][j][1], ss[j][1]);
-            }
+        for (int a = 0; a < 8; a++) {
+            blk[j][0] = fma(acc.v[a][j][0], acc.v[a][j][0], blk[j][0]);
+            blk[j][1] = fma(acc.v[a][j][1], acc.v[a][j][1], blk[j][1]);
+        }
     }
-    // reduce over the 8 groupIDs of the warp, then over the two warps sharing the columns
+}
+
+// sigma^2 of the 128 queries of a tile from the per-thread totals: shuffle tree over the
+// 8 row groups of a warp, then the two warp rows through shared memory (`red`: 256 doubles).
+__device__ __forceinline__ void tile_finish_var(double (&tot)[4][2], double* red, int64_t q, int64_t m, double amp,
+                                                double* __restrict__ var) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < 4; j++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            double v = ss[j][e];
+            double v = tot[j][e];
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             v += __shfl_xor_sync(0xffffffffu, v, 8);
             v += __shfl_xor_sync(0xffffffffu, v, 16);
-            ss[j][e] = v;
+            tot[j][e] = v;
         }
-    double* red = smem;          // [2][128]
     if (lane < 4) {
 #pragma unroll
         for (int j = 0; j < 4; j++)
 #pragma unroll
-            for (int e = 0; e < 2; e++) red[(warp >> 2) * 128 + (warp & 3) * 32 + j * 8 + lane * 2 + e] = ss[j][e];
+            for (int e = 0; e < 2; e++) red[(warp >> 2) * 128 + (warp & 3) * 32 + j * 8 + lane * 2 + e] = tot[j][e];
     }
     __syncthreads();
-    if (threadIdx.x < 128) {
-        int64_t q = q_off + (int64_t)blockIdx.x * abg::BN + threadIdx.x;
-        if (q < m) var[q] = amp - (red[threadIdx.x] + red[128 + threadIdx.x]);
+    if (threadIdx.x < 128 && q < m) var[q] = amp - (red[threadIdx.x] + red[128 + threadIdx.x]);
+}
+
+// sigma^2 for the 128 queries of this CTA:  amp - sum_i ( sum_k Linv[i][k] P[k][q] )^2.
+// Canonical summation order (shared with the split path below, so both give identical
+// bits): per thread, per row block a chain over the m-fragments starting at zero; the
+// block values added in block order; then the reduction tree of tile_finish_var.
+__global__ void __launch_bounds__(abg::THREADS, 1)
+predict_var_kernel(const double* __restrict__ Linv, int64_t ld, int T, const double* __restrict__ P, int64_t ldp,
+                   int64_t m, int64_t q_off, double amp, double* __restrict__ var) {
+    extern __shared__ __align__(16) double smem[];
+    const double* Bp = P + (int64_t)blockIdx.x * abg::BN;
+    double tot[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; j++) tot[j][0] = tot[j][1] = 0.0;
+    for (int i = 0; i < T; i++) {
+        abg::Acc acc;
+        acc.zero();
+        abg::mainloop<true, false, true>(acc, Linv + (int64_t)i * NB * ld, ld, Bp, ldp, (i + 1) * (NB / abg::BK), smem);
+        double blk[4][2];
+        tile_thread_sq(acc, blk);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { tot[j][0] += blk[j][0]; tot[j][1] += blk[j][1]; }
     }
+    tile_finish_var(tot, smem, q_off + (int64_t)blockIdx.x * abg::BN + threadIdx.x, m, amp, var);
+}
+
+// Few query tiles (one-point calls of the acquisition polish, small batches): the loop
+// over row blocks of predict_var_kernel would run serially on a handful of SMs, so the
+// row blocks are spread over grid.y.  Each CTA stores its per-thread block values
+// (8 per thread); var_combine_kernel adds them in block order and finishes exactly like
+// predict_var_kernel.
+__global__ void __launch_bounds__(abg::THREADS, 1)
+predict_var_split_kernel(const double* __restrict__ Linv, int64_t ld, const double* __restrict__ P, int64_t ldp,
+                         double* __restrict__ part) {
+    extern __shared__ __align__(16) double smem[];
+    const int i = blockIdx.y;
+    const double* Bp = P + (int64_t)blockIdx.x * abg::BN;
+    abg::Acc acc;
+    acc.zero();
+    abg::mainloop<true, false, true>(acc, Linv + (int64_t)i * NB * ld, ld, Bp, ldp, (i + 1) * (NB / abg::BK), smem);
+    double blk[4][2];
+    tile_thread_sq(acc, blk);
+    double* dst = part + (((int64_t)i * gridDim.x + blockIdx.x) * abg::THREADS + threadIdx.x) * 8;
+#pragma unroll
+    for (int j = 0; j < 4; j++) *reinterpret_cast<double2*>(dst + 2 * j) = make_double2(blk[j][0], blk[j][1]);
+}
+
+// one CTA (256 threads) per query tile
+__global__ void __launch_bounds__(abg::THREADS)
+var_combine_kernel(const double* __restrict__ part, int T, int64_t m, int64_t q_off, double amp,
+                   double* __restrict__ var) {
+    __shared__ double red[256];
+    double tot[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; j++) tot[j][0] = tot[j][1] = 0.0;
+    for (int i = 0; i < T; i++) {
+        const double* src = part + (((int64_t)i * gridDim.x + blockIdx.x) * abg::THREADS + threadIdx.x) * 8;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double2 v = *reinterpret_cast<const double2*>(src + 2 * j);
+            tot[j][0] += v.x;
+            tot[j][1] += v.y;
+        }
+    }
+    tile_finish_var(tot, red, q_off + (int64_t)blockIdx.x * abg::BN + threadIdx.x, m, amp, var);
 }
 
 // ---------------------------------------------------------------------------
@@ -346,6 +403,24 @@ int launch_mean(ab_gp* h, int Dp, dim3 grid, const double* Xq, int64_t m, int64_
 
 }  // namespace
 
+
+// sigma^2 for `cnt` queries of the panel P: one CTA per 128 queries looping over the row
+// blocks, or (few query tiles) the row blocks spread over the grid
+static int launch_variance(ab_gp* h, int T, const double* P, int64_t ldp, int64_t m, int64_t q0, int64_t cnt,
+                           double* var, double* part) {
+    cudaStream_t s = h->stream;
+    const unsigned ntq = (unsigned)((cnt + abg::BN - 1) / abg::BN);
+    if (T > 1 && (int)ntq * 2 <= h->nsm && part) {
+        predict_var_split_kernel<<<dim3(ntq, T), abg::THREADS, abg::SMEM_BYTES, s>>>(h->Linv, h->npad, P, ldp, part);
+        var_combine_kernel<<<ntq, abg::THREADS, 0, s>>>(part, T, m, q0, h->kp.amp, var);
+        ab_count_launches(1);
+    } else {
+        predict_var_kernel<<<ntq, abg::THREADS, abg::SMEM_BYTES, s>>>(h->Linv, h->npad, T, P, ldp, m, q0, h->kp.amp, var);
+    }
+    AB_CHECK_LAUNCH();
+    return 0;
+}
+
 // queries per variance panel: one wave of CTAs (148 SMs x 128 queries)
 static const int64_t kPanelQueries = 148 * 128;
 
@@ -392,10 +467,13 @@ int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double*
     const int nsplit = (int)((h->npad + JCHUNK - 1) / JCHUNK);
     (void)nblk;
     const size_t panel_elems = (size_t)h->npad * ldp;
-    int rc = ab_ensure_scratch(h, (panel_elems + (size_t)nsplit * ldp) * sizeof(double));
+    const bool few = (int64_t)2 * ((mq + abg::BN - 1) / abg::BN) <= h->nsm;      // split-T variance path possible
+    int rc = ab_ensure_scratch(h, (panel_elems + (size_t)nsplit * ldp + (few ? (size_t)T * ldp * 16 : 0)) * sizeof(double));
     if (rc) return rc;
+    AB_CUDA(cudaFuncSetAttribute(predict_var_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));
     double* P = h->scratch;
     double* partial = h->scratch + panel_elems;
+    double* vpart = few ? partial + (size_t)nsplit * ldp : nullptr;
     for (int64_t q0 = 0; q0 < m; q0 += mq) {
         int64_t cnt = (m - q0 < mq) ? (m - q0) : mq;
         dim3 grid((unsigned)((cnt + QPB - 1) / QPB), (unsigned)nsplit);
@@ -409,10 +487,9 @@ int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double*
         }
         ab_prof_end(h, AB_PROF_PREDICT_PANEL);
         ab_prof_begin(h, AB_PROF_PREDICT_VAR);
-        predict_var_kernel<<<(unsigned)((cnt + abg::BN - 1) / abg::BN), abg::THREADS, abg::SMEM_BYTES, s>>>(
-            h->Linv, h->npad, T, P, ldp, m, q0, h->kp.amp, var);
+        rc = launch_variance(h, T, P, ldp, m, q0, cnt, var, vpart);
         ab_prof_end(h, AB_PROF_PREDICT_VAR);
-        AB_CHECK_LAUNCH();
+        if (rc) return rc;
         ab_count_launches(nsplit > 1 ? 3 : 2);
     }
     return 0;
@@ -457,8 +534,9 @@ int ab_launch_predict_grad(ab_gp* h, const double* Xq, int64_t m, double* mu, do
     const int64_t ldp = (mq + QPB - 1) / QPB * QPB;
     const int nsplit = (int)((h->npad + JCHUNK - 1) / JCHUNK);
     const size_t panel = (size_t)h->npad * ldp;
-    int rc = ab_ensure_scratch(h, (3 * panel + (size_t)nsplit * ldp * (1 + 2 * D)) * sizeof(double));
+    int rc = ab_ensure_scratch(h, (3 * panel + (size_t)nsplit * ldp * (1 + 2 * D) + (size_t)T * ldp * 16) * sizeof(double));
     if (rc) return rc;
+    AB_CUDA(cudaFuncSetAttribute(predict_var_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));
     double* P = h->scratch;
     double* W = P + panel;
     double* V = W + panel;
@@ -474,7 +552,8 @@ int ab_launch_predict_grad(ab_gp* h, const double* Xq, int64_t m, double* mu, do
                                                                               h->mean, mu, q0);
         }
         const unsigned ntq = (unsigned)((cnt + abg::BN - 1) / abg::BN);
-        predict_var_kernel<<<ntq, abg::THREADS, abg::SMEM_BYTES, s>>>(h->Linv, h->npad, T, P, ldp, m, q0, h->kp.amp, var);
+        rc = launch_variance(h, T, P, ldp, m, q0, cnt, var, gpartial + (size_t)nsplit * 2 * D * ldp);
+        if (rc) return rc;
         tri_gemm_kernel<false><<<dim3(ntq, T), abg::THREADS, abg::SMEM_BYTES, s>>>(h->Linv, h->npad, T, P, ldp, W);
         tri_gemm_kernel<true><<<dim3(ntq, T), abg::THREADS, abg::SMEM_BYTES, s>>>(h->Linv, h->npad, T, W, ldp, V);
         AB_CHECK_LAUNCH();

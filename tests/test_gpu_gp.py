@@ -243,3 +243,19 @@ def test_grad_utilities_match_reference_expressions():
                        for k in range(2)])
         np.testing.assert_allclose(gb, fd, rtol=2e-4, atol=1e-6)
     assert np.all(np.isinf(ut.grad_agp_utility(np.array([5.0, 0.0]), g, b)))
+
+
+def test_small_and_large_batches_give_identical_bits():
+    """Few query tiles take the split-over-row-blocks variance kernel, large batches the
+    one-CTA-per-tile kernel: same operations in the same order, so a query gets the same
+    mean and variance bits whatever batch it arrives in (one-point acquisition calls vs
+    candidate sweeps)."""
+    o, g, X, y, rng = make_pair("Matern52Kernel", 700, 3, seed=41)
+    t = rng.uniform(-1, 1, size=(12000, 3))
+    mu_big, var_big = g.predict(y, t, return_var=True)
+    for m in (1, 7, 130, 1000):
+        mu_s, var_s = g.predict(y, t[:m], return_var=True)
+        np.testing.assert_array_equal(mu_s, mu_big[:m])
+        np.testing.assert_array_equal(var_s, var_big[:m])
+    mu_o, var_o = o.predict(y, t[:50], return_var=True)
+    assert rel(mu_big[:50], mu_o) < 1e-9 and np.max(np.abs(var_big[:50] - var_o)) < 1e-9 * np.exp(o.log_const)
