@@ -443,6 +443,14 @@ int ab_gp_get_factor(ab_gp* h, double* d_L) {
     return 0;
 }
 
+int ab_gp_get_block_inverses(ab_gp* h, double* d_Dinv) {
+    AB_REQUIRE(h && d_Dinv, -1, "null argument");
+    AB_REQUIRE(h->factored, -2, "not factorised");
+    AB_CUDA(cudaSetDevice(h->device));
+    AB_CUDA(cudaMemcpyAsync(d_Dinv, h->Dinv, (size_t)h->npad * AB_NB * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
 int ab_gp_get_alpha(ab_gp* h, double* d_alpha) {
     AB_REQUIRE(h && d_alpha, -1, "null argument");
     AB_REQUIRE(h->have_alpha, -2, "targets not set");
@@ -467,6 +475,13 @@ int ab_gp_get_inverse(ab_gp* h, double* d_Kinv) {
 // Adopt a factor and alpha computed elsewhere (another GPU, after an NCCL
 // broadcast).  The diagonal-block inverses are rebuilt locally from L.
 int ab_gp_import_state(ab_gp* h, const double* d_L, const double* d_alpha) {
+    return ab_gp_import_state_full(h, d_L, nullptr, d_alpha);
+}
+
+// d_Dinv != NULL: adopt the sender's diagonal-block inverses as well, so that everything
+// derived from the factor (L^-1, K^-1, variances) has the SAME bits on every GPU; NULL:
+// rebuild them locally (same values up to rounding).
+int ab_gp_import_state_full(ab_gp* h, const double* d_L, const double* d_Dinv, const double* d_alpha) {
     AB_REQUIRE(h && d_L && d_alpha, -1, "null argument");
     AB_CUDA(cudaSetDevice(h->device));
     int rc = ensure_scaled(h);
@@ -474,8 +489,10 @@ int ab_gp_import_state(ab_gp* h, const double* d_L, const double* d_alpha) {
     AB_CUDA(cudaMemcpyAsync(h->L, d_L, (size_t)h->npad * h->npad * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     AB_CUDA(cudaMemsetAsync(h->alpha, 0, (size_t)h->npad * sizeof(double), h->stream));
     AB_CUDA(cudaMemcpyAsync(h->alpha, d_alpha, (size_t)h->n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    rc = ab_launch_rebuild_dinv(h);
+    rc = ab_launch_rebuild_dinv(h);                    // also the log-determinant parts
     if (rc) return rc;
+    if (d_Dinv)
+        AB_CUDA(cudaMemcpyAsync(h->Dinv, d_Dinv, (size_t)h->npad * AB_NB * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     h->factored = true;
     h->have_alpha = true;
     h->have_linv = h->have_kinv = false;

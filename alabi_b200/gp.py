@@ -467,7 +467,17 @@ class GP:
         _lib.check(hd.lib.ab_gp_get_alpha(hd.h, _lib.ptr(alpha)), "ab_gp_get_alpha")
         return L, alpha
 
-    def import_state(self, x, y, L, alpha, yerr=0.0):
+    def export_block_inverses(self):
+        """Inverses of the diagonal blocks of L, (npad/128) x 128 x 128 (broadcast with L so
+        that every replica derives L^-1 and variances with identical bits)."""
+        torch = _torch()
+        hd = self._hd
+        npad = hd.lib.ab_gp_padded_size(hd.h)
+        D = torch.empty((npad // 128, 128, 128), dtype=torch.float64, device=f"cuda:{hd.device}")
+        _lib.check(hd.lib.ab_gp_get_block_inverses(hd.h, _lib.ptr(D)), "ab_gp_get_block_inverses")
+        return D
+
+    def import_state(self, x, y, L, alpha, yerr=0.0, Dinv=None):
         """Adopt a factor computed on another GPU (after a broadcast)."""
         self._x = self.parse_samples(x)
         self._yerr2 = float(yerr) ** 2
@@ -475,7 +485,8 @@ class GP:
         self._mark_dirty()
         self._push()
         hd = self._hd
-        _lib.check(hd.lib.ab_gp_import_state(hd.h, _lib.ptr(L), _lib.ptr(alpha)), "ab_gp_import_state")
+        _lib.check(hd.lib.ab_gp_import_state_full(hd.h, _lib.ptr(L), _lib.ptr(Dinv), _lib.ptr(alpha)),
+                   "ab_gp_import_state_full")
         hd.stream.synchronize()
         self._y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
         self.computed = True

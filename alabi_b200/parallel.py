@@ -69,6 +69,7 @@ def broadcast_gp(gp, x=None, y=None, src=0):
     meta = [None]
     if rank == src:
         L, alpha = gp.export_state()
+        Dinv = gp.export_block_inverses()
         meta = [dict(vector=gp.get_parameter_vector(include_frozen=True), x=gp._x, y=gp._y, yerr2=gp._yerr2,
                      npad=int(L.shape[0]), n=int(alpha.shape[0]))]
     dist.broadcast_object_list(meta, src=src)
@@ -77,11 +78,13 @@ def broadcast_gp(gp, x=None, y=None, src=0):
     if rank != src:
         L = torch.empty((m["npad"], m["npad"]), dtype=torch.float64, device=dev)
         alpha = torch.empty(m["n"], dtype=torch.float64, device=dev)
+        Dinv = torch.empty((m["npad"] // 128, 128, 128), dtype=torch.float64, device=dev)
     dist.broadcast(L, src=src)
+    dist.broadcast(Dinv, src=src)          # same diagonal-block inverses => same L^-1 bits everywhere
     dist.broadcast(alpha, src=src)
     if rank != src:
         gp.set_parameter_vector(m["vector"], include_frozen=True)
-        gp.import_state(m["x"], m["y"], L, alpha, yerr=np.sqrt(m["yerr2"]))
+        gp.import_state(m["x"], m["y"], L, alpha, yerr=np.sqrt(m["yerr2"]), Dinv=Dinv)
     return gp
 
 

@@ -145,6 +145,11 @@ int ab_gp_get_factor(ab_gp* h, double* d_L /* npad x npad */);
 int ab_gp_get_alpha(ab_gp* h, double* d_alpha /* n */);
 int ab_gp_get_inverse(ab_gp* h, double* d_Kinv /* n x n, full symmetric */);
 int ab_gp_import_state(ab_gp* h, const double* d_L /* npad x npad */, const double* d_alpha /* n */);
+/* inverses of the 128 x 128 diagonal blocks of L ((npad/128) x 128 x 128), and an import that
+ * adopts them: with L, D^-1 and alpha from the training GPU every replica derives L^-1, K^-1
+ * and variances with identical bits (sharded results == single-GPU results) */
+int ab_gp_get_block_inverses(ab_gp* h, double* d_Dinv);
+int ab_gp_import_state_full(ab_gp* h, const double* d_L, const double* d_Dinv /* or NULL */, const double* d_alpha);
 
 /* K5: emcee.EnsembleSampler(...).run_mcmc over lnprob = surrogate mean + uniform
  * prior (alabi/core.py:2073-2100, 2319-2325). */
