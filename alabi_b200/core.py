@@ -451,7 +451,16 @@ class SurrogateModel(object):
                 else:
                     results = min([_optimize_fn(p) for p in p0], key=lambda r: r.fun)
             op_gp = self.set_hyperparameter_vector(cur, results.x)
-            op_gp.compute(_theta)
+            try:
+                op_gp.compute(_theta)
+            except np.linalg.LinAlgError:
+                # every restart ended on a hyper-vector whose covariance matrix does not
+                # factorise (fun = 1e25): the reference raises here (alabi/core.py:1313-1314);
+                # keeping the current hyper-parameters lets a long active-learning run go on
+                print(f"Warning: optimised GP hyper-parameters {np.asarray(results.x)} are not factorisable "
+                      f"(fun = {results.fun}); keeping the current ones")
+                op_gp = self.set_hyperparameter_vector(cur, current_hp)
+                op_gp.compute(_theta)
             if self.verbose:
                 print(f"-logL {nll(current_hp):.4f} -> {nll(results.x):.4f} | {results.nit} iterations | "
                       f"Success: {results.success}")
