@@ -63,6 +63,36 @@ append_row_kernel(double* __restrict__ L, int64_t ld, int64_t n0, const double* 
     if (threadIdx.x == 0) L[n0 * ld + n0] = lam;
 }
 
+// New row of L^-1 after the bordered update:  Linv'[n0][j] = -(1/s) sum_{i<n0} l_i Linv[i][j],
+// Linv'[n0][n0] = 1/s.  Column j per thread (rows are read coalesced), the row range split
+// over grid.y into fixed chunks; linv_row_finish adds the chunk sums in order.
+constexpr int LR_CHUNK = 1024;
+__global__ void __launch_bounds__(128)
+linv_row_partial_kernel(const double* __restrict__ Linv, int64_t ld, int64_t n0, const double* __restrict__ l,
+                        double* __restrict__ part, int64_t part_ld) {
+    const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.y * LR_CHUNK;
+    int64_t i1 = i0 + LR_CHUNK < n0 ? i0 + LR_CHUNK : n0;
+    double s = 0.0;
+    if (j < n0) {
+        int64_t ib = i0 > j ? i0 : j;                      // Linv is lower triangular: rows i >= j
+        for (int64_t i = ib; i < i1; i++) s = fma(l[i], Linv[i * ld + j], s);
+    }
+    part[(int64_t)blockIdx.y * part_ld + j] = s;
+}
+__global__ void linv_row_finish_kernel(double* __restrict__ Linv, int64_t ld, int64_t n0, const double* __restrict__ L,
+                                       const double* __restrict__ part, int64_t part_ld, int nchunk) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double inv_s = 1.0 / L[n0 * ld + n0];
+    if (j < n0) {
+        double s = 0.0;
+        for (int c = 0; c < nchunk; c++) s += part[(int64_t)c * part_ld + j];
+        Linv[n0 * ld + j] = -inv_s * s;
+    } else if (j == n0) {
+        Linv[n0 * ld + n0] = inv_s;
+    }
+}
+
 // new identity block rows [npad0, npad1) of the re-laid-out factor
 __global__ void pad_identity_rows_kernel(double* __restrict__ L, int64_t ld, int64_t r0) {
     const int64_t row = r0 + blockIdx.x;
@@ -163,9 +193,24 @@ extern "C" int ab_gp_append_point(ab_gp* h, const double* d_x) {
     rc = ab_launch_rebuild_dinv_block(h, (int)(n0 / NB));
     if (rc) { h->n = n0; return rc; }
     ab_count_launches(5);
+    bool keep_linv = false;
+    if (h->have_linv && h->Linv) {
+        // L^-1 follows in O(N^2) as well (its row n0 was the identity row of the padding)
+        const int nchunk = (int)((n0 + LR_CHUNK - 1) / LR_CHUNK);
+        rc = ab_ensure_scratch(h, 256 + ((size_t)(nchunk > 0 ? nchunk : 1) * ld + (size_t)(2 * (ld / NB) + 64)) * sizeof(double));
+        if (rc) { h->n = n0; return rc; }
+        double* part = h->scratch + 32 + (2 * (ld / NB) + 64);       // behind the solve's control words
+        if (nchunk > 0)
+            linv_row_partial_kernel<<<dim3((unsigned)(ld / 128), (unsigned)nchunk), 128, 0, s>>>(h->Linv, ld, n0, h->z, part, ld);
+        linv_row_finish_kernel<<<(unsigned)((n0 + 1 + 255) / 256), 256, 0, s>>>(h->Linv, ld, n0, h->L, part, ld, nchunk);
+        AB_CHECK_LAUNCH();
+        ab_count_launches(2);
+        keep_linv = true;
+    }
     AB_CUDA(cudaMemcpyAsync(h->h_pinned + 8, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, s));
     AB_CUDA(cudaStreamSynchronize(s));
-    h->have_linv = h->have_kinv = h->have_alpha = false;
+    h->have_linv = keep_linv;
+    h->have_kinv = h->have_alpha = false;
     if (*reinterpret_cast<int*>(h->h_pinned + 10) != 0) {
         ab_set_error("dataflow triangular solve watchdog fired");
         h->factored = false;
@@ -175,6 +220,7 @@ extern "C" int ab_gp_append_point(ab_gp* h, const double* d_x) {
     if (info != 0) {                                       // not positive definite with the new point
         h->info = info;
         h->factored = false;
+        h->have_linv = false;
         ab_set_error("matrix not positive definite after appending a point: pivot %d", info);
         return info;
     }
