@@ -16,6 +16,10 @@ surrogate-MCMC walker-steps/s (K5, 1000 walkers per GPU), is reported under
 afterwards every rank works on its own queries / sub-ensemble (weak scaling,
 no data-path collective).
 
+``kernels`` (N = 1 only) adds the covariance build, the Cholesky, both solves and the
+log-likelihood gradient at the training-set sizes of configs c4 (N = 8192, d = 10)
+and c5 (N = 16384, d = 20), each against its roof.
+
 ``--impl reference`` times the CPU oracle (NumPy/SciPy restatement of the
 george + emcee path, all host BLAS threads) on a bounded sample of the same
 workload and prints the same JSON line with ``"impl": "reference"``.
@@ -148,6 +152,75 @@ def cpu_reference_run(steps, warmup, sample_points=None, mcmc_steps=None):
                        f"with vectorised log-prob; NumPy/SciPy oracle, {cores} BLAS threads")
 
 
+def kernel_table(lib, dmma_peak_tflops):
+    """K1 / K2 at the training-set sizes of BASELINE configs c4 and c5 (rank 0, N = 1 only;
+    a few hundred ms of GPU time): covariance build, Cholesky, both triangular solves and
+    the log-likelihood gradient, each as absolute time and as a fraction of its roof
+    (HBM copy bandwidth from MEASURED_PEAKS.json, FP64 DMMA peak measured in this run)."""
+    import torch
+    import alabi_b200 as ab
+    from alabi_b200 import _lib
+    hbm = 6458.1
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:  # noqa: BLE001
+        pass
+
+    def ev(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+        return best
+    out = {"hbm_peak_gb_s": hbm, "fp64_tensor_peak_tflops": dmma_peak_tflops}
+    for name, n, d in (("c4", 8192, 10), ("c5", 16384, 20)):
+        rng = np.random.default_rng(n)
+        X = rng.uniform(-3, 3, size=(n, d))
+        y = -0.5 * np.sum((X / 1.5) ** 2, axis=1) + 0.01 * rng.normal(size=n)
+        g = ab.GP(kernel=ab.kernels.ExpSquaredKernel(metric=np.full(d, 2.25), ndim=d) * np.var(y), fit_mean=True,
+                  mean=np.median(y), white_noise=-6.0, fit_white_noise=True)
+        g.compute(X)
+        h = g._hd.h
+        lib.ab_gp_set_profiling(h, 1)
+        t_fac = ev(lambda: lib.ab_gp_factor(h))                      # covariance build + Cholesky
+        cms, ccnt = ctypes.c_double(), ctypes.c_longlong()
+        lib.ab_gp_profile_read(h, 0, ctypes.byref(cms), ctypes.byref(ccnt))
+        fms, fcnt = ctypes.c_double(), ctypes.c_longlong()
+        lib.ab_gp_profile_read(h, 1, ctypes.byref(fms), ctypes.byref(fcnt))
+        lib.ab_gp_set_profiling(h, 0)
+        t_cov = cms.value * 1e-3 / max(ccnt.value, 1)
+        t_chol = fms.value * 1e-3 / max(fcnt.value, 1)
+        yd = torch.from_numpy(y).cuda()
+        ll = ctypes.c_double()
+        t_solve = ev(lambda: lib.ab_gp_log_likelihood(h, _lib.ptr(yd), ctypes.byref(ll)))
+        gr = (ctypes.c_double * (d + 3))()
+
+        def full_grad():
+            lib.ab_gp_factor(h)
+            lib.ab_gp_grad_log_likelihood(h, _lib.ptr(yd), gr)
+        t_grad = ev(full_grad, reps=2)
+        out[name] = {
+            "n_train": n, "ndim": d,
+            "cov_build": {"ms": t_cov * 1e3, "gb_s": 4.0 * n * n / t_cov * 1e-9, "frac_hbm": 4.0 * n * n / t_cov * 1e-9 / hbm,
+                          "bytes": "4 N^2 (lower triangle written once)", "note": "FP64-ALU bound for d >= 4 (DESIGN.md)"},
+            "cholesky": {"ms": t_chol * 1e3, "tflops": n ** 3 / 3.0 / t_chol * 1e-12,
+                         "frac_fp64_tensor": n ** 3 / 3.0 / t_chol * 1e-12 / dmma_peak_tflops},
+            "compute_total_ms": t_fac * 1e3,
+            "solves_loglike_ms": t_solve * 1e3,
+            "factor_plus_gradient_ms": t_grad * 1e3,
+            "factor_plus_gradient_tflops": float(n) ** 3 / t_grad * 1e-12,
+        }
+        del g
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -170,6 +243,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-table", action="store_true",
+                    help="skip the K1 / K2 measurements at the c4 / c5 training-set sizes")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -320,6 +395,8 @@ def main():
                 "share_of_step": kms.value * 1e-3 / elapsed,
                 "panel_kernel_share_of_step": pms.value * 1e-3 / elapsed}
 
+    kernels = None if args.no_kernel_table else kernel_table(lib, peak.value)
+
     cpu = None
     if not args.no_cpu_baseline:
         r = cpu_reference_run(steps=2, warmup=1, sample_points=100000, mcmc_steps=10)
@@ -332,7 +409,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(m_e2e * NDIM * 8),
                     "d2h_bytes_per_step": int(m_e2e * 16)},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
-            "mcmc": mcmc}
+            "mcmc": mcmc, "kernels": kernels}
     sys.stdout.flush()
     os.dup2(_saved_stdout, 1)
     print(json.dumps(line), flush=True)
