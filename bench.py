@@ -395,7 +395,7 @@ def main():
                 "share_of_step": kms.value * 1e-3 / elapsed,
                 "panel_kernel_share_of_step": pms.value * 1e-3 / elapsed}
 
-    kernels = None if args.no_kernel_table else kernel_table(lib, peak.value)
+    kernels = None if (args.no_kernel_table or world > 1) else kernel_table(lib, peak.value)
 
     cpu = None
     if not args.no_cpu_baseline:
