@@ -95,10 +95,15 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
     double* sAl = sm + D * CH;       // [CH]
     // P proposals per unit (2: small ensembles, more units; 4: large ensembles, each
     // training point read from shared memory once per 4 kernel evaluations)
-    __shared__ double sQ[EW][P][D], sQs[EW][P][D];
-    __shared__ double sS[EW][P][D];              // current position of the walker being updated
-    __shared__ double sPart[EW][P], sLogZ[EW][P], sLogU[EW][P], sLps[EW][P], sZZ[EW][P];
-    __shared__ int sW[EW][P], sInside[EW][P], sPartner[EW][P];
+    // P = 32 ("wide"): ONE unit per CTA whose proposal e belongs to LANE e of every warp; the
+    // eight warps split the training points and read them as shared-memory broadcasts, so
+    // there is no cross-lane reduction and the proposal / accept phases use all 32 lanes.
+    constexpr bool WIDE = (P == 32);
+    constexpr int NU = WIDE ? 1 : EW;            // units per CTA the per-unit arrays must hold
+    __shared__ double sQ[NU][P][D], sQs[NU][P][D];
+    __shared__ double sS[NU][P][D];              // current position of the walker being updated
+    __shared__ double sPart[EW][P], sLogZ[NU][P], sLogU[NU][P], sLps[NU][P], sZZ[NU][P];
+    __shared__ int sW[NU][P], sInside[NU][P], sPartner[NU][P];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int WS = A.ws, G = EW / WS;
@@ -219,6 +224,48 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 __syncthreads();
                 if (A.dbg) t1 = clock64();
                 // ---- surrogate mean of the two proposals of this unit ------------
+                if constexpr (WIDE) {
+                    double qv[D];
+#pragma unroll
+                    for (int k = 0; k < D; k++) qv[k] = sQs[0][lane][k];
+                    double accw = 0.0;
+                    // cn is a multiple of 32 (resident: CH, rows >= n are zero with alpha = 0); every
+                    // 128-bit broadcast read serves two training points
+                    auto eval_wide = [&](const double* bX, const double* bAl, int cn) {
+                        const int per = cn / EW;
+                        const int j0 = warp * per, j1 = j0 + per;
+#pragma unroll 2
+                        for (int j = j0; j < j1; j += 2) {
+                            double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+                            for (int k = 0; k < D; k++) {
+                                const double2 xx = *reinterpret_cast<const double2*>(&bX[k * CH + j]);
+                                const double d0 = qv[k] - xx.x, d1 = qv[k] - xx.y;
+                                r0 = fma(d0, d0, r0);
+                                r1 = fma(d1, d1, r1);
+                            }
+                            const double2 al = *reinterpret_cast<const double2*>(&bAl[j]);
+                            accw = fma(ab_radial<KIND>(r0), al.x, accw);
+                            accw = fma(ab_radial<KIND>(r1), al.y, accw);
+                        }
+                    };
+                    if (resident) {
+                        eval_wide(sX, sAl, CH);
+                    } else {
+                        const int nch = (int)(A.npad / CH);
+                        issue_chunk(0, 0);
+                        for (int c = 0; c < nch; c++) {
+                            if (c + 1 < nch) issue_chunk((long long)(c + 1) * CH, (c + 1) & 1);
+                            else asm volatile("cp.async.commit_group;" ::: "memory");
+                            asm volatile("cp.async.wait_group 1;" ::: "memory");
+                            __syncthreads();
+                            const double* bX = sm + (c & 1) * BUF;
+                            eval_wide(bX, bX + D * CH, CH);
+                            __syncthreads();
+                        }
+                    }
+                    sPart[warp][lane] = accw;
+                } else {
                 double q[P][D], acc[P];
 #pragma unroll
                 for (int e = 0; e < P; e++) {
@@ -265,6 +312,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 for (int e = 0; e < P; e++) {
                     acc[e] = ab_warp_sum(acc[e]);
                     if (lane == 0) sPart[warp][e] = acc[e];
+                }
                 }
                 __syncthreads();
                 if (A.dbg) t2 = clock64();
@@ -372,6 +420,7 @@ int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
 // n_half: proposals of the larger half-step (or all walkers for a log-prob-only call)
 template <int KIND, int D>
 int launch_ens(ab_gp* h, EnsArgs& A, int n_half, int p) {
+    if (p == 32) return launch_ens_p<KIND, D, 32>(h, A, n_half);
     if (D <= 24 && p == 4) return launch_ens_p<KIND, (D <= 24 ? D : 2), 4>(h, A, n_half);
     return launch_ens_p<KIND, D, 2>(h, A, n_half);
 }
@@ -408,12 +457,16 @@ extern "C" int ab_ensemble_run(ab_gp* h, const ab_ensemble_config* cfg, double* 
     int n_half = (cfg->nwalkers + 1) / 2;
     if (cfg->init_logp && cfg->nsteps == 0) n_half = cfg->nwalkers;
     const int nsm = h->nsm;
-    int p = (h->d <= 24 && n_half >= 16 * nsm) ? 4 : 2;
-    if (cfg->reserved >= 2) p = (cfg->reserved == 4 && h->d <= 24) ? 4 : 2;        // development override
+    // proposals per unit: 2 (small ensembles, many units), 32 = one lane per proposal once
+    // there are enough proposals for one 32-wide unit per SM
+    int p = (n_half >= 16 * nsm) ? 32 : 2;
+    if (cfg->reserved >= 2)                                                        // development override
+        p = (cfg->reserved == 32) ? 32 : ((cfg->reserved == 4 && h->d <= 24) ? 4 : 2);
     // warps per unit: all 8 warps on one unit while that still fills the GPU
     const int units_half = (n_half + p - 1) / p;
     int ws = 1;
-    if (cfg->warps_per_unit > 0) ws = cfg->warps_per_unit;
+    if (p == 32) ws = 8;                       // wide unit = the whole CTA
+    else if (cfg->warps_per_unit > 0) ws = cfg->warps_per_unit;
     else while (ws < 8 && units_half * ws <= nsm * 8) ws *= 2;
     if (ws != 1 && ws != 2 && ws != 4 && ws != 8) { ab_set_error("warps_per_unit must be 1, 2, 4 or 8"); return -1; }
     A.ws = ws;

@@ -120,8 +120,9 @@ def test_non_finite_inputs_are_reported():
     assert not np.isfinite(g.log_likelihood(yn, quiet=True)) or g.log_likelihood(yn, quiet=True) == -np.inf
 
 
-def test_sampler_four_proposals_per_unit_replays():
-    """P = 4 proposals per unit (large-ensemble configuration) replayed on the CPU."""
+def test_sampler_proposals_per_unit_variants_replay():
+    """P = 2, 4 proposals per unit and the wide 32-proposal unit (one lane per proposal,
+    the large-ensemble configuration), each replayed on the CPU from the same draws."""
     import alabi_b200 as ab
     from alabi_b200.ensemble import EnsembleSampler, SurrogateLogProb
     rng = np.random.default_rng(8)
@@ -138,7 +139,7 @@ def test_sampler_four_proposals_per_unit_replays():
         inside = np.all((q > b[:, 0]) & (q < b[:, 1]), axis=1)
         return np.where(inside, o.predict(y, q), -np.inf)
     chains = []
-    for mode in (2, 4):
+    for mode in (2, 4, 32):
         s = EnsembleSampler(nw, d, lp, seed=21)
         s.debug_timing = mode                                   # development override: proposals per unit
         s.run_mcmc(p0, 25)

@@ -26,7 +26,7 @@ k = ab.kernels.ExpSquaredKernel(metric=np.full(d, 4.0), ndim=d) * np.var(y)
 g = ab.GP(kernel=k, fit_mean=True, mean=np.median(y), white_noise=-6.0, fit_white_noise=True)
 g.compute(X)
 lp = SurrogateLogProb(g, y, [(0, 1)] * d)
-for pp in (2, 4, 0):
+for pp in (4, 32, 0):
     s = EnsembleSampler(nw, d, lp, seed=1)
     s.debug_timing = pp
     s.run_mcmc(rng.uniform(0.3, 0.7, size=(nw, d)), 2, store=False)
