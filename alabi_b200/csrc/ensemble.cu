@@ -86,7 +86,7 @@ __device__ __forceinline__ void grid_wait(unsigned long long* counter, unsigned 
 }
 
 template <int KIND, int D, int EW, int P>
-__global__ void __launch_bounds__(EW * 32)
+__global__ void __launch_bounds__(EW * 32, (P == 32) ? 2 : 1)
 ensemble_kernel(const __grid_constant__ EnsArgs A) {
     constexpr int ETHREADS = EW * 32;
     extern __shared__ __align__(16) double sm[];

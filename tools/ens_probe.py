@@ -19,7 +19,7 @@ for wpu in (0, 4, 8):
 
 # c5-like per-GPU share: N = 16384, d = 20, 8192 walkers
 import time
-d, n, nw = 20, 16384, 8192
+d, n, nw = 20, 16384, int(os.environ.get('ENS_NW', '8192'))
 X = rng.uniform(0, 1, size=(n, d))
 y = -0.5 * np.sum(((X - 0.5) / 0.2) ** 2, axis=1)
 k = ab.kernels.ExpSquaredKernel(metric=np.full(d, 4.0), ndim=d) * np.var(y)
