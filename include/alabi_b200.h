@@ -161,7 +161,8 @@ typedef struct ab_ensemble_config {
     int randomize_split;   /* 1: coin per walker pair, 0: parity split */
     int warps_per_unit;    /* 0 = auto, else 1/2/4/8 */
     int y_kind;            /* y = ys*y_scale + y_offset (0), -10^ys (1), 10^ys (2) */
-    int reserved;
+    int reserved;            /* 0 in production.  Development aids: 1 = print per-phase cycle counts of
+                              * block 0 to stderr; 2 / 4 / 32 = force that many proposals per unit */
     double a;              /* stretch scale (emcee default 2.0) */
     uint64_t seed;
     int64_t first_step;    /* step counter of the first step (continuing chains) */
