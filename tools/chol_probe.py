@@ -8,7 +8,7 @@ from gpu_probe import ev_time
 
 lib = _lib.load()
 for n in [int(s) for s in os.environ.get("PROBE_SIZES", "2048,4096,8192,16384").split(",")]:
-    d = 10
+    d = int(os.environ.get("PROBE_D", "10"))
     rng = np.random.default_rng(n)
     X = rng.uniform(-1, 1, size=(n, d))
     y = -0.5 * np.sum(X ** 2, axis=1) + 0.01 * rng.normal(size=n)
