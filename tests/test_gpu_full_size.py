@@ -112,3 +112,28 @@ def test_sampler_large_ensemble_sharding_is_reproducible():
         runs.append(s.get_chain())
     assert np.array_equal(runs[0], runs[1]) and not np.array_equal(runs[0], runs[2])
     assert np.all(np.isfinite(runs[0])) and 0.0 < s.acceptance_fraction.mean() < 1.0
+
+
+def test_more_block_rows_than_sms():
+    """N = 20000 gives 157 block rows on a 148-SM GPU: the dataflow kernels hand several rows
+    to one CTA.  Checked through size-independent identities: K alpha = y - mean on sampled
+    rows, mu = y - wn alpha and 0 <= sigma^2 <= wn at training points."""
+    import alabi_b200 as ab
+    n, d = 20000, 6
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, size=(n, d))
+    y = -0.5 * np.sum(X ** 2, axis=1) + 0.01 * rng.normal(size=n)
+    wn = np.exp(-6.0)
+    g = ab.GP(kernel=ab.kernels.Matern52Kernel(metric=np.full(d, 0.5), ndim=d) * np.var(y), fit_mean=True,
+              mean=np.median(y), white_noise=-6.0, fit_white_noise=True)
+    g.compute(X)
+    assert np.isfinite(g.log_likelihood(y))
+    idx = rng.choice(n, 256, replace=False)
+    mu_t, var_t = g.predict(y, X[idx], return_var=True)
+    alpha = g._alpha
+    scale = np.max(np.abs(y - np.median(y)))
+    assert np.max(np.abs(mu_t - (y[idx] - wn * alpha[idx]))) < 1e-9 * scale
+    assert np.all(var_t > -1e-9 * np.var(y)) and np.all(var_t < wn + 1e-9 * np.var(y))
+    Krows = ogp.kernel_value("Matern52Kernel", X[idx], X, np.log(np.full(d, 0.5)), np.log(np.var(y) / d))
+    Krows[np.arange(len(idx)), idx] += wn
+    assert np.max(np.abs(Krows @ alpha - (y[idx] - np.median(y)))) < 1e-9 * scale
