@@ -102,7 +102,10 @@ struct Core {
     //   current k4-step are skipped (warp-uniform test).
     //   gate(c) is called by every thread right before it issues the loads of chunk c
     //   (the dataflow Cholesky waits there for the producer of that k block).
-    template <bool AK, bool BKM, bool TRI_A = false, typename Gate = NoGate>
+    //   MLIM < 16: only the first MLIM 8-row m-fragments of the 128-row A tile matter (the
+    //   rest is padding whose products are exactly zero); the per-warp-row fragment counts
+    //   are compile-time constants, selected once per chunk by the warp row.
+    template <bool AK, bool BKM, bool TRI_A = false, typename Gate = NoGate, int MLIM = 16>
     static __device__ __forceinline__ void mainloop(Acc& acc, const double* __restrict__ A, int64_t lda,
                                                     const double* __restrict__ B, int64_t ldb, int nk,
                                                     double* smem, Gate gate = Gate()) {
@@ -140,10 +143,11 @@ struct Core {
             if (ORDER_ == 0) prefetch();
             // one k4-step: fragment loads, then 32 DMMAs (TRI: only the m-fragments that
             // reach down to k offset `ktri` of the triangular block)
-            auto k4step = [&](int kk, auto tri, int ktri) {
+            auto k4step = [&](int kk, auto tri, int ktri, auto nfc) {
+                constexpr int NF = decltype(nfc)::value;             // m-fragments of this warp row that matter
                 double a[8], b[4];
 #pragma unroll
-                for (int f = 0; f < 8; f++)
+                for (int f = 0; f < NF; f++)
                     a[f] = AK ? sA[(frag_row(wm, f) + g) * LDK + kk * 4 + t]
                               : sA[(kk * 4 + t) * LDRA + frag_row(wm, f) + g];
 #pragma unroll
@@ -151,29 +155,37 @@ struct Core {
                     b[f] = BKM ? sB[(wn * 32 + f * 8 + g) * LDK + kk * 4 + t]
                                : sB[(kk * 4 + t) * LDRB + wn * 32 + f * 8 + g];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
+                for (int i = 0; i < NF; i++) {
                     if (decltype(tri)::value && ktri > frag_row(wm, i) + 7) continue;
 #pragma unroll
                     for (int j = 0; j < 4; j++) dmma884(acc.v[i][j][0], acc.v[i][j][1], a[i], b[j]);
                 }
             };
-            if (TRI_A && kc >= nk - KB) {            // chunk inside the triangular diagonal block
-                const int k0 = (kc - (nk - KB)) * BK;
-                if (k0 > frag_row(wm, 7) + 7) {      // nothing left for this warp's rows
-                    if (ORDER_ == 1) prefetch();
+            auto chunk = [&](auto nfc) {
+                if (TRI_A && kc >= nk - KB) {        // chunk inside the triangular diagonal block
+                    const int k0 = (kc - (nk - KB)) * BK;
+                    if (k0 > frag_row(wm, 7) + 7) {  // nothing left for this warp's rows
+                        if (ORDER_ == 1) prefetch();
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < BK / 4; kk++) {
+                            k4step(kk, std::true_type{}, k0 + kk * 4, nfc);
+                            if (ORDER_ == 1 && kk == 0) prefetch();
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int kk = 0; kk < BK / 4; kk++) {
-                        k4step(kk, std::true_type{}, k0 + kk * 4);
+                        k4step(kk, std::false_type{}, -1, nfc);
                         if (ORDER_ == 1 && kk == 0) prefetch();
                     }
                 }
+            };
+            if constexpr (MLIM >= 16 || WM != 2) {
+                chunk(std::integral_constant<int, 8>{});
             } else {
-#pragma unroll
-                for (int kk = 0; kk < BK / 4; kk++) {
-                    k4step(kk, std::false_type{}, -1);
-                    if (ORDER_ == 1 && kk == 0) prefetch();
-                }
+                if (wm == 0) chunk(std::integral_constant<int, (MLIM < 8 ? MLIM : 8)>{});
+                else chunk(std::integral_constant<int, (MLIM > 8 ? MLIM - 8 : 0)>{});
             }
         }
         cp_async_wait<0>();

@@ -141,6 +141,10 @@ __device__ __forceinline__ void tile_finish_var(double (&tot)[4][2], double* red
 // Canonical summation order (shared with the split path below, so both give identical
 // bits): per thread, per row block a chain over the m-fragments starting at zero; the
 // block values added in block order; then the reduction tree of tile_finish_var.
+// NL = number of 8-row groups of the LAST row block that hold training points (rows >= n of
+// L^-1 are identity padding and k* is zero there, so their products are exactly zero and
+// skipping them changes no bit of the result).
+template <int NL>
 __global__ void __launch_bounds__(abg::THREADS, 1)
 predict_var_kernel(const double* __restrict__ Linv, int64_t ld, int T, const double* __restrict__ P, int64_t ldp,
                    int64_t m, int64_t q_off, double amp, double* __restrict__ var) {
@@ -152,7 +156,11 @@ predict_var_kernel(const double* __restrict__ Linv, int64_t ld, int T, const dou
     for (int i = 0; i < T; i++) {
         abg::Acc acc;
         acc.zero();
-        abg::mainloop<true, false, true>(acc, Linv + (int64_t)i * NB * ld, ld, Bp, ldp, (i + 1) * (NB / abg::BK), smem);
+        if (NL < 16 && i == T - 1)
+            abg::Main::mainloop<true, false, true, abg::NoGate, NL>(acc, Linv + (int64_t)i * NB * ld, ld, Bp, ldp,
+                                                                   (i + 1) * (NB / abg::BK), smem);
+        else
+            abg::mainloop<true, false, true>(acc, Linv + (int64_t)i * NB * ld, ld, Bp, ldp, (i + 1) * (NB / abg::BK), smem);
         double blk[4][2];
         tile_thread_sq(acc, blk);
 #pragma unroll
@@ -415,7 +423,18 @@ static int launch_variance(ab_gp* h, int T, const double* P, int64_t ldp, int64_
         var_combine_kernel<<<ntq, abg::THREADS, 0, s>>>(part, T, m, q0, h->kp.amp, var);
         ab_count_launches(1);
     } else {
-        predict_var_kernel<<<ntq, abg::THREADS, abg::SMEM_BYTES, s>>>(h->Linv, h->npad, T, P, ldp, m, q0, h->kp.amp, var);
+        const int nl = (int)((h->n - (int64_t)(T - 1) * NB + 7) / 8);        // 1..16 row groups in the last block
+#define AB_PV(NLV)                                                                                                 \
+    case NLV:                                                                                                      \
+        AB_CUDA(cudaFuncSetAttribute(predict_var_kernel<NLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES)); \
+        predict_var_kernel<NLV><<<ntq, abg::THREADS, abg::SMEM_BYTES, s>>>(h->Linv, h->npad, T, P, ldp, m, q0, h->kp.amp, var); \
+        break
+        switch (nl) {
+            AB_PV(1); AB_PV(2); AB_PV(3); AB_PV(4); AB_PV(5); AB_PV(6); AB_PV(7); AB_PV(8);
+            AB_PV(9); AB_PV(10); AB_PV(11); AB_PV(12); AB_PV(13); AB_PV(14); AB_PV(15);
+            default: AB_PV(16);
+        }
+#undef AB_PV
     }
     AB_CHECK_LAUNCH();
     return 0;
@@ -454,7 +473,6 @@ int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double*
     }
     // mean + variance, processed in panels.  Panel width: whole waves of variance CTAs
     // (148 x 128 queries), as many as fit a ~2 GB cross-covariance panel.
-    AB_CUDA(cudaFuncSetAttribute(predict_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));
     const int T = (int)(h->npad / NB);
     int64_t waves = (int64_t)((2ULL << 30) / ((size_t)h->npad * kPanelQueries * sizeof(double)));
     if (waves < 1) waves = 1;
@@ -526,7 +544,6 @@ int ab_launch_predict_grad(ab_gp* h, const double* Xq, int64_t m, double* mu, do
     if (m <= 0) return 0;
     cudaStream_t s = h->stream;
     const int d = h->d, D = padded_dim(d);
-    AB_CUDA(cudaFuncSetAttribute(predict_var_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));
     AB_CUDA(cudaFuncSetAttribute(tri_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));
     AB_CUDA(cudaFuncSetAttribute(tri_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));
     const int T = (int)(h->npad / NB);
