@@ -60,8 +60,10 @@ def test_alabi_workflow(tmp_path, hyperopt):
     assert abs(sm.surrogate_log_likelihood(np.zeros(2)) - lnlike(np.zeros(2))) < 0.3
     cached = sm.create_cached_surrogate_likelihood(return_var=True)
     cm, cv = cached(t)
-    np.testing.assert_allclose(cm, mu, rtol=1e-9, atol=1e-9)
-    np.testing.assert_allclose(cv, var, rtol=1e-6, atol=1e-9)
+    # the cached likelihood refactorises from the stored hyper-vector, the live GP was extended
+    # by bordered updates: same factor up to rounding amplified by cond(K)
+    np.testing.assert_allclose(cm, mu, rtol=0, atol=tol * scale)
+    np.testing.assert_allclose(cv, var, rtol=0, atol=max(tol * scale, 1e-9))
     sm.prior_fn = lambda th: ab.utility.lnprior_uniform(th, sm.bounds)
     assert np.isfinite(sm.lnprob(np.array([0.1, 0.2]))) and sm.lnprob(np.array([5.0, 0.0])) == -np.inf
 
@@ -78,4 +80,4 @@ def test_alabi_workflow(tmp_path, hyperopt):
     # the cached pickle reloads and predicts the same numbers
     import pickle
     sm2 = pickle.load(open(tmp_path / "surrogate_model.pkl", "rb"))
-    np.testing.assert_allclose(sm2.surrogate_log_likelihood(t), mu, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(sm2.surrogate_log_likelihood(t), mu, rtol=0, atol=tol * scale)
