@@ -372,10 +372,43 @@ int ab_gp_predict_host(ab_gp* h, const double* h_Xq, int64_t m, double* h_mu, do
     double* dmu = h->io + nx;
     double* dvar = h_var ? dmu + m : nullptr;
     AB_CUDA(cudaMemcpyAsync(dq, h_Xq, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    rc = ab_gp_predict(h, dq, m, dmu, dvar);
+    const int64_t chunk = h_var ? ab_predict_panel_queries(h) : m;
+    if (m <= chunk) {
+        rc = ab_gp_predict(h, dq, m, dmu, dvar);
+        if (rc) return rc;
+        AB_CUDA(cudaMemcpyAsync(h_mu, dmu, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (h_var) AB_CUDA(cudaMemcpyAsync(h_var, dvar, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        AB_CUDA(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    // Large batches: the same panels ab_gp_predict would form (identical launches, identical
+    // bits), but the results of panel c - 1 travel to the host on the handle's second stream
+    // while panel c is computed; the (possibly blocking, pageable) copy is issued after the
+    // next panel has been enqueued.
+    cudaEvent_t ev[2] = {h->ev_fork, h->ev_join};
+    auto copy_out = [&](int64_t off, int64_t cnt, cudaEvent_t e) -> int {
+        AB_CUDA(cudaStreamWaitEvent(h->panel_stream, e, 0));
+        AB_CUDA(cudaMemcpyAsync(h_mu + off, dmu + off, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, h->panel_stream));
+        AB_CUDA(cudaMemcpyAsync(h_var + off, dvar + off, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, h->panel_stream));
+        return 0;
+    };
+    int64_t prev_off = -1, prev_cnt = 0;
+    int c = 0;
+    for (int64_t off = 0; off < m; off += chunk, c++) {
+        const int64_t cnt = (m - off < chunk) ? (m - off) : chunk;
+        rc = ab_gp_predict(h, dq + (size_t)off * h->d, cnt, dmu + off, dvar + off);
+        if (rc) return rc;
+        AB_CUDA(cudaEventRecord(ev[c & 1], h->stream));
+        if (prev_off >= 0) {
+            rc = copy_out(prev_off, prev_cnt, ev[(c - 1) & 1]);
+            if (rc) return rc;
+        }
+        prev_off = off;
+        prev_cnt = cnt;
+    }
+    rc = copy_out(prev_off, prev_cnt, ev[(c - 1) & 1]);
     if (rc) return rc;
-    AB_CUDA(cudaMemcpyAsync(h_mu, dmu, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (h_var) AB_CUDA(cudaMemcpyAsync(h_var, dvar, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    AB_CUDA(cudaStreamSynchronize(h->panel_stream));
     AB_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }

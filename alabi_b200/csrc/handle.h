@@ -85,6 +85,7 @@ int ab_launch_mirror_lower(ab_gp* h, double* A, int64_t ld);
 int ab_launch_grad(ab_gp* h, double* h_out);
 // predict.cu
 int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double* var);
+int64_t ab_predict_panel_queries(ab_gp* h);
 int ab_launch_predict_grad(ab_gp* h, const double* Xq, int64_t m, double* mu, double* var, double* dmu, double* dvar);
 int ab_launch_utility(ab_gp* h, int kind, const double* Xq, const double* mu, const double* var, int64_t m,
                       const double* h_bounds, double y_best, double zeta, double* util,

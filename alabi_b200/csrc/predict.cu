@@ -443,6 +443,14 @@ static int launch_variance(ab_gp* h, int T, const double* P, int64_t ldp, int64_
 // queries per variance panel: one wave of CTAs (148 SMs x 128 queries)
 static const int64_t kPanelQueries = 148 * 128;
 
+// queries per variance panel for the current training-set size (what ab_launch_predict uses)
+int64_t ab_predict_panel_queries(ab_gp* h) {
+    int64_t waves = (int64_t)((2ULL << 30) / ((size_t)h->npad * kPanelQueries * sizeof(double)));
+    if (waves < 1) waves = 1;
+    if (waves > 16) waves = 16;
+    return waves * kPanelQueries;
+}
+
 int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double* var) {
     if (m <= 0) return 0;
     cudaStream_t s = h->stream;

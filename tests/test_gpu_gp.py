@@ -259,3 +259,19 @@ def test_small_and_large_batches_give_identical_bits():
         np.testing.assert_array_equal(var_s, var_big[:m])
     mu_o, var_o = o.predict(y, t[:50], return_var=True)
     assert rel(mu_big[:50], mu_o) < 1e-9 and np.max(np.abs(var_big[:50] - var_o)) < 1e-9 * np.exp(o.log_const)
+
+
+def test_large_host_batch_overlapped_copies_identical():
+    """Host-buffer predicts larger than one variance panel are processed panel by panel with
+    the device -> host copies overlapped; the numbers must be the ones the device-tensor
+    path returns for the same queries."""
+    import torch
+    o, g, X, y, rng = make_pair("Matern32Kernel", 300, 2, seed=9)
+    m = 16 * 148 * 128 + 12345                      # more than the largest panel (16 waves)
+    t = rng.uniform(-1, 1, size=(m, 2))
+    mu_h, var_h = g.predict(y, t, return_var=True)
+    mu_d, var_d = g.predict(y, torch.from_numpy(t).cuda(), return_var=True)
+    np.testing.assert_array_equal(mu_h, mu_d.cpu().numpy())
+    np.testing.assert_array_equal(var_h, var_d.cpu().numpy())
+    mu_o, var_o = o.predict(y, t[-40:], return_var=True)
+    assert rel(mu_h[-40:], mu_o) < 1e-9 and np.max(np.abs(var_h[-40:] - var_o)) < 1e-9 * np.exp(o.log_const)
