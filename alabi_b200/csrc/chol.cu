@@ -1,6 +1,8 @@
-// K2: blocked right-looking FP64 Cholesky with DMMA trailing updates, plus the
-// solves, the triangular inverse and K^-1 that the log-likelihood, its gradient
-// and the predictive variance need.
+// K2: the multi-launch blocked right-looking FP64 Cholesky with DMMA trailing updates
+// (factor schedules 0 / 1, kept as a cross-check of the dataflow kernel in
+// chol_dataflow.cu, which is the default), plus the triangular inverse and K^-1 that
+// the log-likelihood gradient and the predictive variance need, and small solve /
+// reduction helpers.  The block triangular solves live in trsv_dataflow.cu.
 //
 // Replaces george BasicSolver.compute / apply_inverse / get_inverse (scipy
 // cholesky + cho_solve) reached from alabi/gp_utils.py:243, alabi/core.py:1158,

@@ -1,5 +1,8 @@
-// FP64 tensor-core GEMM core for sm_100a: 128x128 CTA tile, BK = 16, cp.async
-// multi-stage pipeline, DMMA.8x8x4 (mma.sync.m8n8k4.f64) warp tiles of 64x32.
+// FP64 tensor-core GEMM core for sm_100a: Core<BK, STAGES, ORDER, WM, WN> = a (64 WM) x
+// (32 WN) CTA tile (128 x 128 in the product configuration), cp.async multi-stage
+// pipeline, DMMA.8x8x4 (mma.sync.m8n8k4.f64) warp tiles of 64x32.  Three main loops:
+// mainloop (plain, optional triangular / padded-row pruning), mainloop_gated (operands
+// produced by other CTAs of the same kernel), plus the tile store / index helpers.
 //
 // On sm_100a every f64 mma shape lowers to DMMA.8x8x4 (checked with cuobjdump),
 // tcgen05 has no f64 kind, so this warp-level path IS the FP64 tensor pipe.

@@ -7,9 +7,12 @@
 // cooperative kernel; the two dependent half-updates of a step are separated
 // by a grid barrier, never by a host round trip.
 //
-// Work decomposition: a "unit" (1, 2, 4 or 8 warps) evaluates two proposals at
-// a time; its lanes stride over the training points (SoA in shared memory,
-// resident for the whole run when they fit), proposals sit in registers.
+// Work decomposition: small ensembles use "units" of 1, 2, 4 or 8 warps that evaluate
+// P = 2 (or 4) proposals at a time, lanes striding over the training points; large
+// ensembles use the wide unit (P = 32: one lane per proposal, the warps of a CTA split
+// the training points and read them as shared-memory broadcasts).  Training points are
+// SoA in shared memory, resident for the whole run when they fit, else streamed in
+// double-buffered cp.async chunks; proposals sit in registers.
 //
 // Random numbers: Philox4x32-10 keyed by the seed, counter = (global walker id,
 // step, stream, 0) — restated on the CPU in oracle/philox.py so a device chain
