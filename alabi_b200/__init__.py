@@ -10,8 +10,10 @@ from . import _lib, kernels
 from .gp import GP, LinAlgError
 from .ensemble import EnsembleSampler, SurrogateLogProb
 from .core import SurrogateModel, CachedSurrogateLikelihood
-from . import utility, gp_utils, mcmc_utils, benchmarks, parallel, nested
+from . import utility, gp_utils, mcmc_utils, benchmarks, parallel, nested, cache_utils
+from .cache_utils import load_model_cache
 
 __version__ = "0.1.0"
 __all__ = ["GP", "kernels", "LinAlgError", "EnsembleSampler", "SurrogateLogProb", "SurrogateModel",
-           "CachedSurrogateLikelihood", "utility", "gp_utils", "mcmc_utils", "benchmarks", "parallel", "nested"]
+           "CachedSurrogateLikelihood", "utility", "gp_utils", "mcmc_utils", "benchmarks", "parallel", "nested",
+           "cache_utils", "load_model_cache"]

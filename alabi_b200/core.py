@@ -127,6 +127,17 @@ class SurrogateModel(object):
             if os.path.exists(tmp):
                 os.remove(tmp)
             raise
+        # human-readable report next to the pickle (alabi/core.py:394-404)
+        from . import cache_utils
+        if hasattr(self, "gp"):
+            try:
+                cache_utils.write_report_gp(self, file)
+            except Exception as e:  # noqa: BLE001 - the reference reports and goes on
+                print(f"Error writing GP report: {e}")
+        if getattr(self, "emcee_run", False):
+            cache_utils.write_report_emcee(self, file)
+        if getattr(self, "dynesty_run", False):
+            cache_utils.write_report_dynesty(self, file)
 
     # -- data / scalers ---------------------------------------------------------------
     def theta(self):

@@ -77,7 +77,11 @@ def test_alabi_workflow(tmp_path, hyperopt):
     assert abs(dz[:, 0].std() - 0.6) < 0.12 and abs(dz[:, 1].std() - 0.9) < 0.15
     want_logz = np.log(2 * np.pi * 0.6 * 0.9 / 36.0)
     assert abs(sm.dynesty_logz - want_logz) < 0.35
-    # the cached pickle reloads and predicts the same numbers
-    import pickle
-    sm2 = pickle.load(open(tmp_path / "surrogate_model.pkl", "rb"))
+    # the cached pickle reloads and predicts the same numbers; the text report has all sections
+    sm.save()
+    report = open(tmp_path / "surrogate_model.txt").read()
+    for needle in ("GP summary", "GP final hyperparameters", "emcee summary", "Mean acceptance fraction",
+                   "dynesty summary", "Total weighted samples", "Summary statistics"):
+        assert needle in report
+    sm2 = ab.load_model_cache(str(tmp_path))
     np.testing.assert_allclose(sm2.surrogate_log_likelihood(t), mu, rtol=0, atol=tol * scale)

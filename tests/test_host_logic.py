@@ -201,3 +201,25 @@ def test_shard_range_covers_everything():
             assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
             sizes = [hi - lo for lo, hi in ranges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_report_writers_cpu(tmp_path):
+    """cache_utils report sections from a stand-in model (no GPU needed)."""
+    from types import SimpleNamespace
+    from alabi_b200 import cache_utils as cu
+    gp = SimpleNamespace(get_parameter_names=lambda: ("mean:value", "kernel:k1:log_constant"),
+                         get_parameter_vector=lambda: np.array([0.5, -1.0]))
+    sm = SimpleNamespace(gp=gp, kernel_name="ExpSquaredKernel", bounds=[(-1, 1)] * 2, fit_mean=True, fit_amp=True,
+                         fit_white_noise=False, white_noise=-12, ntrain=60, ninit_train=50, nactive=10, ntest=20,
+                         training_results={"test_mse": [0.3, 0.1]}, ndim=2, labels=["a", "b"], nwalkers=40, nsteps=100,
+                         acc_frac=0.5, autcorr_time=12.0, iburn=10, ithin=2, emcee_runtime=1.2,
+                         emcee_samples=np.random.default_rng(0).normal(size=(500, 2)), dynesty_runtime=0.4,
+                         dynesty_samples=np.random.default_rng(1).normal(size=(300, 2)))
+    f = str(tmp_path / "model")
+    cu.write_report_gp(sm, f)
+    cu.write_report_emcee(sm, f)
+    cu.write_report_dynesty(sm, f)
+    txt = open(f + ".txt").read()
+    assert txt.count("=" * 66) == 6 and "Kernel: ExpSquaredKernel" in txt and "[mean:value] \t0.5" in txt
+    assert "Final test error (MSE): 0.1" in txt and "Number of walkers: 40" in txt and "a = " in txt
+    assert "Total weighted samples: 300" in txt
