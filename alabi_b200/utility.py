@@ -131,6 +131,61 @@ def lnprior_uniform(x, bounds):
     return 0
 
 
+def prior_sampler_normal(prior_data, bounds, nsample=1):
+    """Truncated-normal prior draws (alabi/utility.py:130-175): dimensions whose
+    ``prior_data[i]`` is ``(mean, std)`` are normal, ``(None, None)`` uniform; rejection
+    keeps every draw inside ``bounds``."""
+    b = np.asarray(bounds, dtype=np.float64)
+    rng = np.random.default_rng()
+    out = np.empty((int(nsample), len(b)))
+    for i, (mu, sd) in enumerate(prior_data):
+        if mu is None or sd is None:
+            out[:, i] = rng.uniform(b[i, 0], b[i, 1], size=int(nsample))
+            continue
+        col = rng.normal(mu, sd, size=int(nsample))
+        bad = (col < b[i, 0]) | (col > b[i, 1])
+        while np.any(bad):
+            col[bad] = rng.normal(mu, sd, size=int(bad.sum()))
+            bad = (col < b[i, 0]) | (col > b[i, 1])
+        out[:, i] = col
+    return out
+
+
+def lnprior_normal(x, bounds, data):
+    """Uniform box times independent normals (alabi/utility.py:370-378); ``data[i]`` is
+    ``(mean, std)`` or ``(None, None)``.  The normal terms use scipy's ``norm.logpdf``
+    expression, added in dimension order (the device sampler adds them the same way)."""
+    lnp = lnprior_uniform(x, bounds)
+    x = np.asarray(x, dtype=np.float64).flatten()
+    for i in range(len(x)):
+        if data[i][0] is not None:
+            z = (x[i] - data[i][0]) / data[i][1]
+            lnp += (-(z * z) / 2.0 - 0.9189385332046727) - np.log(data[i][1])
+    return lnp
+
+
+def prior_transform_normal(x, bounds, data):
+    """Unit cube -> prior draws for nested sampling (alabi/utility.py:381-486): uniform
+    dimensions map linearly onto ``bounds``; normal ones through the (untruncated, as in
+    the reference) inverse normal CDF.  1-D or (nsamples, ndim)."""
+    from scipy.stats import norm as _norm
+    x = np.asarray(x, dtype=float)
+    bounds = np.asarray(bounds)
+    if x.ndim not in (1, 2):
+        raise ValueError(f"x must be 1D or 2D array, got {x.ndim}D array with shape {x.shape}")
+    ndim = x.shape[-1]
+    if len(bounds) != ndim or len(data) != ndim:
+        raise ValueError(f"Bounds length ({len(bounds)}) and data length ({len(data)}) "
+                         f"must match x dimensions ({ndim})")
+    out = np.zeros(x.shape)
+    for i, (lo, hi) in enumerate(bounds):
+        if data[i][0] is None:
+            out[..., i] = (hi - lo) * x[..., i] + lo
+        else:
+            out[..., i] = _norm.ppf(x[..., i], data[i][0], data[i][1])
+    return out
+
+
 def prior_transform_uniform(theta, bounds):
     """Unit hypercube -> box: (hi - lo) * u + lo; 1-D or (nsamples, ndim)."""
     theta = np.asarray(theta, dtype=float)
@@ -183,6 +238,34 @@ def jones_utility(theta, predict_gp, bounds, y_best, zeta=0.01):
     return float(-((mu - y_best - zeta) * norm.cdf(z) + std * norm.pdf(z)))
 
 
+def numerical_kernel_gradient(xs, x_train, gp, h=1e-6):
+    """Central difference of k(xs, x_train) w.r.t. the single query point ``xs``
+    (alabi/utility.py:511-556), shape (n_train, d).  Kept for API compatibility; the
+    acquisition gradients below use the analytic derivative on the device."""
+    xs = np.atleast_2d(np.asarray(xs, dtype=np.float64))
+    if xs.shape[0] != 1:
+        raise ValueError("This function handles single query point only")
+    x_train = np.atleast_2d(np.asarray(x_train, dtype=np.float64))
+    out = np.zeros((x_train.shape[0], x_train.shape[1]))
+    for i in range(x_train.shape[1]):
+        step = np.zeros(x_train.shape[1])
+        step[i] = h
+        kp = gp.kernel.get_value(xs + step, x_train).ravel()
+        km = gp.kernel.get_value(xs - step, x_train).ravel()
+        out[:, i] = (kp - km) / (2.0 * h)
+    return out
+
+
+def grad_gp_mean_prediction(xs, gp):
+    """d mu / dx at one query point (alabi/utility.py:558-583), from ``GP.predict_grad``."""
+    return gp.predict_grad(gp._y, np.asarray(xs, dtype=np.float64).reshape(1, -1))[2][0]
+
+
+def grad_gp_var_prediction(xs, gp):
+    """d sigma^2 / dx at one query point (alabi/utility.py:586-621), from ``GP.predict_grad``."""
+    return gp.predict_grad(gp._y, np.asarray(xs, dtype=np.float64).reshape(1, -1))[3][0]
+
+
 def grad_agp_utility(theta, gp, bounds):
     """alabi/utility.py:704-726: -(d mu + 0.5 d sigma^2) (the reference's expression,
     kept as is), inf outside the prior box.  d mu and d sigma^2 come from the device
@@ -231,6 +314,11 @@ def _minimize_single(obj_fn, bounds, x0, method, options, grad_obj_fn=None):
         return np.nan, np.nan
     print("Warning: Acquisition function optimization infinite fail", x_opt, f_opt)
     return np.nan, np.nan
+
+
+def minimize_objective_single(idx, obj_fn, bounds, starting_point, method, options, grad_obj_fn=None):
+    """One restart of ``minimize_objective`` (alabi/utility.py:969-1027)."""
+    return _minimize_single(obj_fn, bounds, starting_point, method, options, grad_obj_fn)
 
 
 def minimize_objective(obj_fn, bounds=None, nopt=1, method="l-bfgs-b", ps=None, options=None,

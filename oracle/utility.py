@@ -8,6 +8,8 @@ Vectorised restatements (one value per candidate row) of:
 
 * ``lnprior_uniform``           alabi/utility.py:218-275  (strict inequalities)
 * ``prior_transform_uniform``   alabi/utility.py:278-345
+* ``lnprior_normal``            alabi/utility.py:370-378  (uniform box + independent normals)
+* ``prior_transform_normal``    alabi/utility.py:381-486  (untruncated inverse normal CDF)
 * ``logsubexp``                 alabi/utility.py:489-504
 * ``agp_utility``               alabi/utility.py:629-701
 * ``bape_utility``              alabi/utility.py:729-810
@@ -37,6 +39,33 @@ def prior_transform_uniform(u, bounds):
     u = np.asarray(u, dtype=np.float64)
     b = np.asarray(bounds, dtype=np.float64)
     return (b[:, 1] - b[:, 0]) * u + b[:, 0]
+
+
+LOG_SQRT_2PI = 0.9189385332046727      # scipy.stats.norm's _norm_pdf_logC = log(sqrt(2 pi))
+
+
+def lnprior_normal(theta, bounds, mu, sd):
+    """Box prior plus independent normals; ``mu[k]`` NaN marks a uniform dimension.  The
+    normal terms are added in dimension order with scipy's ``norm.logpdf`` expression
+    ((-z*z/2 - log sqrt(2 pi)) - log sd, z = (x - mu)/sd), one value per row."""
+    theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+    lnp = lnprior_uniform(theta, bounds).copy()
+    for k, (m, s) in enumerate(zip(mu, sd)):
+        if not np.isnan(m):
+            z = (theta[:, k] - m) / s
+            lnp = lnp + ((-(z * z) / 2.0 - LOG_SQRT_2PI) - np.log(s))
+    return lnp
+
+
+def prior_transform_normal(u, bounds, mu, sd):
+    from scipy.special import ndtri
+    u = np.asarray(u, dtype=np.float64)
+    b = np.asarray(bounds, dtype=np.float64)
+    out = (b[:, 1] - b[:, 0]) * u + b[:, 0]
+    for k, (m, s) in enumerate(zip(mu, sd)):
+        if not np.isnan(m):
+            out[..., k] = ndtri(u[..., k]) * s + m
+    return out
 
 
 def logsubexp(x1, x2):

@@ -126,6 +126,20 @@ def main():
              xs=xs, shells=np.array([bm.gaussian_shells_fn(x) for x in xs]),
              xe=xe, eggbox=np.array([bm.eggbox_fn(x) for x in xe]),
              xg=xe, gaussian_2d=np.array([bm.gaussian_2d_fn(x) for x in xe]))
+    # ---- normal / mixed priors (own generator so the files above keep their bits) ----
+    rng2 = np.random.default_rng(20261019)
+    pb = np.array([(-2.0, 2.0), (0.0, 10.0), (-1.0, 1.0), (3.0, 4.0)])
+    pdata = [(None, None), (5.0, 1.5), (0.2, 0.05), (None, None)]
+    px = rng2.uniform(pb[:, 0] - 0.2, pb[:, 1] + 0.2, size=(300, 4))
+    px[:3] = [[-2.0, 5.0, 0.2, 3.5], [0.0, 10.0, 1.0, 4.0], [0.0, 5.0, 0.2, 3.5]]
+    with np.errstate(all="ignore"):
+        lnpn = np.array([ut.lnprior_normal(x, pb, pdata) for x in px])
+    pu = rng2.uniform(size=(64, 4))
+    ptn = ut.prior_transform_normal(pu, pb, pdata)
+    ptn1 = ut.prior_transform_normal(pu[0], pb, pdata)
+    np.savez(os.path.join(HERE, "priors_golden.npz"), bounds=pb,
+             data=np.array([[np.nan if v is None else v for v in t] for t in pdata]),
+             x=px, lnprior_normal=lnpn, u=pu, prior_transform_normal=ptn, prior_transform_normal_1d=ptn1)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

@@ -86,6 +86,22 @@ def test_host_utilities_match_reference_golden():
         assert mcmc_utils.estimate_burnin(S()) == (int(bt[0]), int(bt[1]))
 
 
+def test_host_normal_priors_match_reference_golden():
+    from alabi_b200 import utility as ut
+    g = np.load(os.path.join(GOLDEN, "priors_golden.npz"))
+    b = g["bounds"]
+    data = [(None, None) if np.isnan(m) else (float(m), float(s)) for m, s in g["data"]]
+    for x, w in zip(g["x"], g["lnprior_normal"]):
+        assert ut.lnprior_normal(x, b, data) == w
+    np.testing.assert_array_equal(ut.prior_transform_normal(g["u"], b, data), g["prior_transform_normal"])
+    np.testing.assert_array_equal(ut.prior_transform_normal(g["u"][0], b, data), g["prior_transform_normal_1d"])
+    with pytest.raises(ValueError):
+        ut.prior_transform_normal(g["u"][:, :3], b, data)
+    draws = ut.prior_sampler_normal(data, b, nsample=2000)
+    assert draws.shape == (2000, 4) and np.all((draws > b[:, 0]) & (draws < b[:, 1]))
+    assert abs(draws[:, 1].mean() - 5.0) < 0.2 and abs(draws[:, 2].std() - 0.05) < 0.01
+
+
 def test_autocorr_and_samplers_host_side():
     from alabi_b200 import utility as ut, mcmc_utils
     from oracle import emcee as oem

@@ -35,6 +35,15 @@ def test_logsubexp_and_prior_transform():
     assert _eq(ou.prior_transform_uniform(g["u"][0], g["bounds"]), g["prior_transform_1d"])
 
 
+def test_normal_priors_vs_reference():
+    g = np.load(os.path.join(GOLDEN, "priors_golden.npz"))
+    mu, sd = g["data"][:, 0], g["data"][:, 1]
+    assert _eq(ou.lnprior_normal(g["x"], g["bounds"], mu, sd), g["lnprior_normal"])
+    assert np.isinf(g["lnprior_normal"]).sum() > 20 and np.isfinite(g["lnprior_normal"]).sum() > 20
+    assert _eq(ou.prior_transform_normal(g["u"], g["bounds"], mu, sd), g["prior_transform_normal"])
+    assert _eq(ou.prior_transform_normal(g["u"][0], g["bounds"], mu, sd), g["prior_transform_normal_1d"])
+
+
 def test_regulariser_and_burnin():
     g = np.load(os.path.join(GOLDEN, "utility_golden.npz"))
     lidx = list(g["lidx"])
