@@ -25,13 +25,16 @@ class EnsembleConfig(ctypes.Structure):
                 ("a", ctypes.c_double), ("seed", ctypes.c_uint64), ("first_step", ctypes.c_int64),
                 ("walker_offset", ctypes.c_int64), ("y_scale", ctypes.c_double), ("y_offset", ctypes.c_double),
                 ("lo", ctypes.c_double * MAX_DIM), ("hi", ctypes.c_double * MAX_DIM),
-                ("theta_scale", ctypes.c_double * MAX_DIM), ("theta_offset", ctypes.c_double * MAX_DIM)]
+                ("theta_scale", ctypes.c_double * MAX_DIM), ("theta_offset", ctypes.c_double * MAX_DIM),
+                ("use_normal_prior", ctypes.c_int), ("reserved2", ctypes.c_int),
+                ("prior_mu", ctypes.c_double * MAX_DIM), ("prior_sd", ctypes.c_double * MAX_DIM)]
 
 
 # name -> (restype, argtypes); every symbol include/alabi_b200.h declares
 _P = ctypes.c_void_p
 SIGNATURES = {
     "ab_version": (ctypes.c_int, []),
+    "ab_sizeof_ensemble_config": (ctypes.c_int, []),
     "ab_last_error": (ctypes.c_char_p, []),
     "ab_device_sm_count": (ctypes.c_int, [ctypes.c_int]),
     "ab_launch_counter": (ctypes.c_longlong, []),
@@ -91,6 +94,9 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.ab_sizeof_ensemble_config() != ctypes.sizeof(EnsembleConfig):
+        raise AlabiB200Error(f"{LIB_PATH} is stale: ab_ensemble_config is {lib.ab_sizeof_ensemble_config()} bytes there, "
+                             f"{ctypes.sizeof(EnsembleConfig)} here — rebuild with `python -m alabi_b200.build`")
     _lib = lib
     return lib
 

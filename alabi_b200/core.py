@@ -576,8 +576,8 @@ class SurrogateModel(object):
         return CachedSurrogateLikelihood(gp_iter, _yc, self.theta_scaler, self.y_scaler, self.ndim,
                                          return_var=return_var)
 
-    def _device_log_prob(self, iter=-1):
-        """SurrogateLogProb (GP mean + uniform prior) for the device sampler."""
+    def _device_log_prob(self, iter=-1, bounds=None, prior_data=None):
+        """SurrogateLogProb (GP mean + uniform or box-times-normal prior) for the device sampler."""
         _tc, _yc, hp = self._conditioning(iter) if len(self.training_results["iteration"]) > 0 else \
             (self._theta, self._y, self.gp.get_parameter_vector())
         gp = self.gp
@@ -587,7 +587,27 @@ class SurrogateModel(object):
             gp.compute(_tc)
         ts, to = ut.scaler_affine(self.theta_scaler, self.ndim)
         yk, ys, yo = ut.scaler_affine(self.y_scaler, self.ndim, inverse=True)
-        return SurrogateLogProb(gp, _yc, self.bounds, ts, to, yk, ys, yo)
+        return SurrogateLogProb(gp, _yc, self.bounds if bounds is None else bounds, ts, to, yk, ys, yo,
+                                prior_data=prior_data)
+
+    @staticmethod
+    def _device_prior(prior_fn):
+        """(bounds, prior_data) of a prior the device sampler evaluates itself: a
+        ``functools.partial`` of ``ut.lnprior_uniform`` (bounds) or ``ut.lnprior_normal``
+        (bounds, data) -- the two priors the reference ships (alabi/utility.py:218-275,
+        370-378).  Any other callable is host Python and cannot run inside the kernel."""
+        fn = getattr(prior_fn, "func", None)
+        name = getattr(fn, "__name__", None)
+        if not isinstance(prior_fn, partial) or name not in ("lnprior_uniform", "lnprior_normal"):
+            raise NotImplementedError("alabi_b200.run_emcee evaluates the prior on the GPU: pass "
+                                      "functools.partial(ut.lnprior_uniform, bounds=...) or "
+                                      "functools.partial(ut.lnprior_normal, bounds=..., data=...)")
+        names = ("bounds",) if name == "lnprior_uniform" else ("bounds", "data")
+        kw = dict(zip(names, prior_fn.args))          # positional after x
+        kw.update(prior_fn.keywords or {})
+        if "bounds" not in kw or (name == "lnprior_normal" and "data" not in kw):
+            raise ValueError(f"{name}: the partial must bind {names}")
+        return np.asarray(kw["bounds"], dtype=np.float64), (kw.get("data") if name == "lnprior_normal" else None)
 
     # -- active learning (alabi/core.py:1587-1865) -----------------------------------------------
     def find_next_point(self, nopt=3, optimizer_kwargs={}, ncand=None):
@@ -717,20 +737,27 @@ class SurrogateModel(object):
                   samples_file=None, min_ess=int(1e4)):
         """Ensemble MCMC on the surrogate posterior.  With the default likelihood
         (the surrogate) and prior (uniform box) every step runs on the device
-        (K5).  Custom Python ``like_fn`` / ``prior_fn`` cannot run inside a CUDA
-        kernel and are rejected."""
+        (K5).  ``prior_fn`` may also be a ``functools.partial`` of ``ut.lnprior_uniform``
+        or ``ut.lnprior_normal`` (box times independent normals): both are evaluated inside
+        the kernel.  Other Python ``like_fn`` / ``prior_fn`` callables cannot run inside a
+        CUDA kernel and are rejected."""
         if like_fn is not None and like_fn not in (self.surrogate_log_likelihood, "surrogate"):
             raise NotImplementedError("alabi_b200.run_emcee samples the GP surrogate on the GPU; a custom Python "
                                       "like_fn is outside the accelerated path")
-        if prior_fn is not None:
-            raise NotImplementedError("alabi_b200.run_emcee supports the default uniform prior (bounds) only")
         self.like_fn_name, self.like_fn = "surrogate", self.surrogate_log_likelihood
-        self.prior_fn = partial(ut.lnprior_uniform, bounds=self.bounds)
-        self.prior_fn_comment = f"Default uniform prior. \nPrior function: ut.prior_fn_uniform\n\twith bounds {self.bounds}"
+        if prior_fn is None:
+            pbounds, pdata = self.bounds, None
+            self.prior_fn = partial(ut.lnprior_uniform, bounds=self.bounds)
+            self.prior_fn_comment = f"Default uniform prior. \nPrior function: ut.prior_fn_uniform\n\twith bounds {self.bounds}"
+        else:
+            pbounds, pdata = self._device_prior(prior_fn)
+            self.prior_fn = prior_fn
+            self.prior_fn_comment = prior_fn_comment if prior_fn_comment is not None else \
+                f"User defined prior.Prior function: {prior_fn.func.__name__}"
         self.nwalkers = int(10 * self.ndim) if nwalkers is None else int(nwalkers)
         self.nsteps = int(nsteps)
         p0 = ut.prior_sampler(nsample=self.nwalkers, bounds=self.bounds, sampler="uniform", random_state=None)
-        lp = self._device_log_prob(-1)
+        lp = self._device_log_prob(-1, bounds=pbounds, prior_data=pdata)
         if self.verbose:
             print(f"Running emcee-compatible GPU sampler with {self.nwalkers} walkers for {self.nsteps} steps...")
         all_chains, all_times, accumulated, run_number = [], [], 0, 1

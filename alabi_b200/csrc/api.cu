@@ -99,6 +99,7 @@ static int ensure_kinv(ab_gp* h) {
 extern "C" {
 
 int ab_version(void) { return 100; }
+int ab_sizeof_ensemble_config(void) { return (int)sizeof(ab_ensemble_config); }
 const char* ab_last_error(void) { return g_err; }
 
 int ab_device_sm_count(int device) {

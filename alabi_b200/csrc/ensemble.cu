@@ -19,6 +19,7 @@
 // can be replayed exactly.  The red/blue split flips one fair coin per walker
 // pair (2i, 2i+1): balanced, position independent, no compaction needed.
 #include <stdio.h>
+#include <cmath>
 #include "handle.h"
 #include "alabi_b200.h"
 
@@ -41,6 +42,10 @@ struct EnsArgs {
     long long first_step, walker_offset;
     double lo[AB_MAX_DIM], hi[AB_MAX_DIM], t_scale[AB_MAX_DIM], t_off[AB_MAX_DIM];
     int y_kind; double y_scale, y_off;
+    // independent normal priors (use_normal: any; pr_sd[k] <= 0: dimension k is uniform);
+    // pr_c[k] = log sqrt(2 pi) + log sd, the constant of norm.logpdf
+    int use_normal;
+    double pr_mu[AB_MAX_DIM], pr_sd[AB_MAX_DIM], pr_lsd[AB_MAX_DIM];
 };
 
 struct U4 { unsigned x, y, z, w; };
@@ -107,6 +112,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
     __shared__ double sS[NU][P][D];              // current position of the walker being updated
     __shared__ double sPart[EW][P], sLogZ[NU][P], sLogU[NU][P], sLps[NU][P], sZZ[NU][P];
     __shared__ int sW[NU][P], sInside[NU][P], sPartner[NU][P];
+    __shared__ double sPrior[NU][P];             // ln of the normal part of the prior at the proposal
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int WS = A.ws, G = EW / WS;
@@ -219,6 +225,18 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                                 if (inside >= 0 && !((q > A.lo[k]) && (q < A.hi[k]))) inside = 0;
                                 sQs[unit][e][k] = fma(q, A.t_scale[k], A.t_off[k]) * A.kp.inv_len[k];
                             }
+                        }
+                        if (A.use_normal) {
+                            // scipy's norm.logpdf term by term, in dimension order (oracle/utility.py)
+                            double pr = 0.0;
+                            for (int k = 0; k < d; k++) {
+                                if (A.pr_sd[k] > 0.0) {
+                                    const double z = __ddiv_rn(__dsub_rn(sQ[unit][e][k], A.pr_mu[k]), A.pr_sd[k]);
+                                    pr = __dadd_rn(pr, __dsub_rn(__dsub_rn(-__dmul_rn(z, z) * 0.5, 0.9189385332046727),
+                                                                 A.pr_lsd[k]));
+                                }
+                            }
+                            sPrior[unit][e] = pr;
                         }
                     }
                     for (int k = (w < 0 ? 0 : d); k < D; k++) { sQ[unit][e][k] = 0.0; sQs[unit][e][k] = 0.0; }
@@ -333,6 +351,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                         double y = (A.y_kind == 0) ? fma(ys, A.y_scale, A.y_off)
                                  : (A.y_kind == 1) ? -pow(10.0, ys) : pow(10.0, ys);
                         const int inside = sInside[unit][e];
+                        if (A.use_normal) y = __dadd_rn(y, sPrior[unit][e]);
                         double lp_q = (inside == 1) ? y : -INFINITY;
                         if (inside == 1 && isnan(y)) atomicExch(A.nan_flag, 1);
                         if (step < 0) {
@@ -456,6 +475,19 @@ extern "C" int ab_ensemble_run(ab_gp* h, const ab_ensemble_config* cfg, double* 
         A.t_scale[k] = cfg->theta_scale[k]; A.t_off[k] = cfg->theta_offset[k];
     }
     A.y_kind = cfg->y_kind; A.y_scale = cfg->y_scale; A.y_off = cfg->y_offset;
+    A.use_normal = 0;
+    if (cfg->use_normal_prior) {
+        for (int k = 0; k < h->d; k++) {
+            A.pr_mu[k] = cfg->prior_mu[k]; A.pr_sd[k] = cfg->prior_sd[k];
+            if (cfg->prior_sd[k] > 0.0) {
+                if (!std::isfinite(cfg->prior_mu[k]) || !std::isfinite(cfg->prior_sd[k])) {
+                    ab_set_error("ab_ensemble_run: non-finite normal prior"); return -1;
+                }
+                A.pr_lsd[k] = std::log(cfg->prior_sd[k]);
+                A.use_normal = 1;
+            }
+        }
+    }
     // proposals per half-step; P = 4 per unit once 2 per unit would need several passes per CTA
     int n_half = (cfg->nwalkers + 1) / 2;
     if (cfg->init_logp && cfg->nsteps == 0) n_half = cfg->nwalkers;

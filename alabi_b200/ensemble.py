@@ -6,7 +6,8 @@ Mirrors the protocol alabi uses (alabi/core.py:2319-2387, alabi/mcmc_utils.py:45
 ``get_last_sample().coords``, ``acceptance_fraction``, ``get_autocorr_time``.
 
 ``log_prob_fn`` must be a :class:`SurrogateLogProb` (GP predictive mean +
-uniform prior box, i.e. ``SurrogateModel.lnprob`` of alabi/core.py:2073-2100):
+uniform prior box, optionally times independent normals as in ``ut.lnprior_normal``,
+i.e. ``SurrogateModel.lnprob`` of alabi/core.py:2073-2100):
 the whole step then runs on the device with no host round trip.  A plain
 Python callable cannot be evaluated inside a CUDA kernel; it is rejected
 instead of silently falling back to a CPU sampler.
@@ -34,12 +35,15 @@ class State:
 
 class SurrogateLogProb:
     """ln P(theta) = GP mean(theta_scaler(theta)) mapped back by the y scaler,
-    plus a uniform prior on the open box ``bounds`` (unscaled theta).
+    plus a uniform prior on the open box ``bounds`` (unscaled theta) and, with
+    ``prior_data = [(mean, std) | (None, None), ...]``, independent normal priors on the
+    dimensions that name a mean (``ut.lnprior_normal``, alabi/utility.py:370-378).
 
     theta_scaled = theta * theta_scale + theta_offset;
     y = ys * y_scale + y_offset (y_kind 0), -10**ys (1) or 10**ys (2)."""
 
-    def __init__(self, gp, y, bounds, theta_scale=None, theta_offset=None, y_kind=0, y_scale=1.0, y_offset=0.0):
+    def __init__(self, gp, y, bounds, theta_scale=None, theta_offset=None, y_kind=0, y_scale=1.0, y_offset=0.0,
+                 prior_data=None):
         self.gp = gp
         self.y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
         self.bounds = np.asarray(bounds, dtype=np.float64).reshape(-1, 2)
@@ -47,6 +51,17 @@ class SurrogateLogProb:
         self.theta_scale = np.ones(d) if theta_scale is None else np.asarray(theta_scale, dtype=np.float64).reshape(d)
         self.theta_offset = np.zeros(d) if theta_offset is None else np.asarray(theta_offset, dtype=np.float64).reshape(d)
         self.y_kind, self.y_scale, self.y_offset = int(y_kind), float(y_scale), float(y_offset)
+        # normal priors: mean / std per dimension, std = 0 marks a uniform dimension
+        self.prior_mu, self.prior_sd = np.zeros(d), np.zeros(d)
+        if prior_data is not None:
+            if len(prior_data) != d:
+                raise ValueError("prior_data needs one (mean, std) pair per dimension")
+            for k, (m, sd) in enumerate(prior_data):
+                if m is not None:
+                    if sd is None or not (np.isfinite(m) and np.isfinite(sd) and sd > 0):
+                        raise ValueError(f"prior_data[{k}]: a normal prior needs a finite mean and std > 0")
+                    self.prior_mu[k], self.prior_sd[k] = float(m), float(sd)
+        self.use_normal_prior = bool(np.any(self.prior_sd > 0))
 
     def __call__(self, theta):
         """Host-callable form (one device predict per call) for callers that
@@ -57,6 +72,9 @@ class SurrogateLogProb:
         ys = self.gp.predict(self.y, t * self.theta_scale + self.theta_offset, return_cov=False)
         yv = ys * self.y_scale + self.y_offset if self.y_kind == 0 else (-10.0 ** ys if self.y_kind == 1 else 10.0 ** ys)
         inside = np.all((t > self.bounds[:, 0]) & (t < self.bounds[:, 1]), axis=1)
+        for k in np.nonzero(self.prior_sd > 0)[0]:
+            z = (t[:, k] - self.prior_mu[k]) / self.prior_sd[k]
+            yv = yv + ((-(z * z) / 2.0 - 0.9189385332046727) - np.log(self.prior_sd[k]))
         lp = np.where(inside, yv, -np.inf)
         return lp[0] if one else lp
 
@@ -105,6 +123,8 @@ class EnsembleSampler:
         for k in range(self.ndim):
             cfg.lo[k], cfg.hi[k] = lp.bounds[k, 0], lp.bounds[k, 1]
             cfg.theta_scale[k], cfg.theta_offset[k] = lp.theta_scale[k], lp.theta_offset[k]
+            cfg.prior_mu[k], cfg.prior_sd[k] = lp.prior_mu[k], lp.prior_sd[k]
+        cfg.use_normal_prior = int(lp.use_normal_prior)
         return cfg
 
     def run_mcmc(self, initial_state, nsteps, progress=False, thin_by=1, store=True, record_proposals=False,

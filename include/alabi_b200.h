@@ -51,6 +51,8 @@ extern "C" {
 typedef struct ab_gp ab_gp;
 
 int ab_version(void);
+/* sizeof(ab_ensemble_config) as compiled: a binding checks its mirror of the struct against it */
+int ab_sizeof_ensemble_config(void);
 const char* ab_last_error(void);
 /* multiprocessor count of `device`, < 0 on error (also proves a usable GPU) */
 int ab_device_sm_count(int device);
@@ -152,7 +154,7 @@ int ab_gp_get_block_inverses(ab_gp* h, double* d_Dinv);
 int ab_gp_import_state_full(ab_gp* h, const double* d_L, const double* d_Dinv /* or NULL */, const double* d_alpha);
 
 /* K5: emcee.EnsembleSampler(...).run_mcmc over lnprob = surrogate mean + uniform
- * prior (alabi/core.py:2073-2100, 2319-2325). */
+ * (optionally times independent normal) prior (alabi/core.py:2073-2100, 2319-2325). */
 typedef struct ab_ensemble_config {
     int nwalkers;
     int nsteps;            /* ensemble steps to run in this call */
@@ -170,6 +172,12 @@ typedef struct ab_ensemble_config {
     double y_scale, y_offset;
     double lo[AB_MAX_DIM_PUBLIC], hi[AB_MAX_DIM_PUBLIC];                    /* prior box, unscaled theta */
     double theta_scale[AB_MAX_DIM_PUBLIC], theta_offset[AB_MAX_DIM_PUBLIC]; /* theta_scaled = theta*scale + offset */
+    /* optional independent normal priors on top of the box (ut.lnprior_normal,
+     * alabi/utility.py:370-378): use_normal_prior != 0 adds norm.logpdf(theta_k; prior_mu[k],
+     * prior_sd[k]) for every k with prior_sd[k] > 0 (prior_sd[k] <= 0: uniform dimension) */
+    int use_normal_prior;
+    int reserved2;
+    double prior_mu[AB_MAX_DIM_PUBLIC], prior_sd[AB_MAX_DIM_PUBLIC];
 } ab_ensemble_config;
 
 /* d_coords (nwalkers x d) and d_logp (nwalkers) are in/out state; d_naccept is

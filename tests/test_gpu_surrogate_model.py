@@ -85,3 +85,13 @@ def test_alabi_workflow(tmp_path, hyperopt):
         assert needle in report
     sm2 = ab.load_model_cache(str(tmp_path))
     np.testing.assert_allclose(sm2.surrogate_log_likelihood(t), mu, rtol=0, atol=tol * scale)
+    # a box-times-normal prior (ut.lnprior_normal) is evaluated inside the sampler kernel:
+    # N(0.5, 0.3) on theta_0 against the sigma = 0.6 likelihood -> posterior N(0.4, 0.268)
+    from functools import partial
+    sm.run_emcee(prior_fn=partial(ab.utility.lnprior_normal, bounds=sm.bounds, data=[(0.5, 0.3), (None, None)]),
+                 nwalkers=40, nsteps=800, min_ess=500)
+    sn = sm.emcee_samples
+    assert abs(sn[:, 0].mean() - 0.4) < 0.08 and abs(sn[:, 0].std() - 0.268) < 0.06
+    assert abs(sn[:, 1].std() - 0.9) < 0.15
+    with pytest.raises(NotImplementedError):
+        sm.run_emcee(prior_fn=lambda th: 0.0, nwalkers=40, nsteps=10)

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.ab_version() == 100
-    assert ctypes.sizeof(_lib.EnsembleConfig) == 8 * 4 + 8 * 6 + 4 * 32 * 8
+    assert ctypes.sizeof(_lib.EnsembleConfig) == lib.ab_sizeof_ensemble_config() == 8 * 4 + 8 * 6 + 4 * 32 * 8 + 8 + 2 * 32 * 8
 
 
 def test_product_fails_loudly_without_gpu():
@@ -100,6 +100,32 @@ def test_host_normal_priors_match_reference_golden():
     draws = ut.prior_sampler_normal(data, b, nsample=2000)
     assert draws.shape == (2000, 4) and np.all((draws > b[:, 0]) & (draws < b[:, 1]))
     assert abs(draws[:, 1].mean() - 5.0) < 0.2 and abs(draws[:, 2].std() - 0.05) < 0.01
+
+
+def test_device_prior_recognition():
+    """run_emcee's prior_fn: partials of the two shipped priors are translated for the
+    kernel, anything else is refused (no silent CPU sampler)."""
+    from functools import partial
+    from alabi_b200 import utility as ut
+    from alabi_b200.core import SurrogateModel
+    from alabi_b200.ensemble import SurrogateLogProb
+    b = [(-1.0, 1.0), (0.0, 2.0)]
+    data = [(0.1, 0.2), (None, None)]
+    pb, pd = SurrogateModel._device_prior(partial(ut.lnprior_normal, bounds=b, data=data))
+    assert pb.shape == (2, 2) and pd == data
+    pb, pd = SurrogateModel._device_prior(partial(ut.lnprior_normal, b, data))
+    assert pb.shape == (2, 2) and pd == data
+    pb, pd = SurrogateModel._device_prior(partial(ut.lnprior_uniform, bounds=b))
+    assert pd is None and np.array_equal(pb, np.asarray(b))
+    with pytest.raises(NotImplementedError):
+        SurrogateModel._device_prior(lambda x: 0.0)
+    with pytest.raises(ValueError):
+        SurrogateModel._device_prior(partial(ut.lnprior_normal, bounds=b))
+    lp = SurrogateLogProb(None, np.zeros(3), b, prior_data=data)
+    assert lp.use_normal_prior and lp.prior_sd[0] == 0.2 and lp.prior_sd[1] == 0.0
+    assert not SurrogateLogProb(None, np.zeros(3), b).use_normal_prior
+    with pytest.raises(ValueError):
+        SurrogateLogProb(None, np.zeros(3), b, prior_data=[(0.0, -1.0), (None, None)])
 
 
 def test_autocorr_and_samplers_host_side():
