@@ -3,6 +3,8 @@ alabi/gp_utils.py, driving the GPU GP (``alabi_b200.GP``) instead of george.
 
 * ``configure_gp``                       alabi/gp_utils.py:170-248
 * ``regularization_term / _gradient``    alabi/gp_utils.py:30-108
+* ``optimize_gp`` (ML restarts)          alabi/gp_utils.py:251-447 (+ ``_nll`` / ``_grad_nll`` :111-167)
+* ``weighted_mse_by_probability``        alabi/gp_utils.py:450-508
 * ``optimize_gp_kfold_cv`` (3 stages)    alabi/gp_utils.py:511-1231
 * stage-2 / stage-3 candidate clouds     alabi/gp_utils.py:1234-1367
 """
@@ -12,7 +14,8 @@ import numpy as np
 
 from .gp import GP
 
-__all__ = ["configure_gp", "optimize_gp_kfold_cv", "regularization_term", "regularization_gradient"]
+__all__ = ["configure_gp", "optimize_gp", "optimize_gp_kfold_cv", "regularization_term", "regularization_gradient",
+           "weighted_mse_by_probability"]
 
 
 def regularization_term(hparams, lengthscale_indices, amp_0=1.0, mu_0=1.0, sigma_0=2.0):
@@ -63,6 +66,100 @@ def configure_gp(theta, y, kernel, fit_amp=True, fit_mean=True, fit_white_noise=
         print(f"configure_gp error: {e}")
         return None
     return gp
+
+
+def _nll(p, gp, y, gp_hyper_prior):
+    """Negative log marginal likelihood at hyper-vector ``p``; inf outside the hyper-prior
+    or when K(p) does not factorise (alabi/gp_utils.py:111-140)."""
+    if not np.isfinite(gp_hyper_prior(p)):
+        return np.inf
+    try:
+        gp.set_parameter_vector(p)
+    except np.linalg.LinAlgError:
+        return np.inf
+    ll = gp.log_likelihood(y, quiet=True)
+    return -ll if np.isfinite(ll) else np.inf
+
+
+def _grad_nll(p, gp, y):
+    """Gradient of ``_nll`` (alabi/gp_utils.py:143-167); one factorisation + K^-1 on the device."""
+    gp.set_parameter_vector(p)
+    return -gp.grad_log_likelihood(y, quiet=True)
+
+
+def optimize_gp(gp, _theta, _y, gp_hyper_prior, p0, bounds=None, method="l-bfgs-b", optimizer_kwargs=None,
+                regularize=True, amp_0=1.0, mu_0=1.0, sigma_0=2.0, lengthscale_indices=None):
+    """Maximum-marginal-likelihood hyper-parameters from one start (``p0`` 1-D) or several
+    (``p0`` 2-D: the restart with the largest log-likelihood wins), alabi/gp_utils.py:251-447.
+    Every objective / gradient evaluation is a device factorisation (K1 + K2); scipy only
+    drives.  Failed restarts and a failed single run leave the initial vector in place."""
+    from scipy.optimize import minimize
+    import warnings
+    init_hp = np.array(gp.get_parameter_vector(), dtype=np.float64)
+    _y = np.asarray(_y, dtype=np.float64).reshape(-1)
+    p0 = np.asarray(p0, dtype=np.float64)
+    if regularize and lengthscale_indices is None:
+        # as in the reference, positions are taken in the KERNEL's name list (they are then
+        # applied to the full GP vector; pass lengthscale_indices to address it exactly)
+        lengthscale_indices = [i for i, nm in enumerate(gp.kernel.get_parameter_names()) if "metric:log_m" in nm.lower()]
+        if len(lengthscale_indices) == 0:
+            warnings.warn("Could not infer lengthscale indices from kernel; regularisation is not applied.")
+            regularize = False
+    if method not in ("newton-cg", "bfgs", "l-bfgs-b", "powell", "nelder-mead"):
+        print(f"Warning: {method} not a valid method. Using 'l-bfgs-b' optimizer instead.")
+        method = "l-bfgs-b"
+    if method == "bfgs":
+        bounds = None
+    reg = (lambda p: regularization_term(p, lengthscale_indices, amp_0=amp_0, mu_0=mu_0, sigma_0=sigma_0)) \
+        if regularize else (lambda p: 0.0)
+    reg_grad = (lambda p: regularization_gradient(p, lengthscale_indices, amp_0=amp_0, mu_0=mu_0, sigma_0=sigma_0)) \
+        if regularize else (lambda p: 0.0)
+    obj = lambda p: _nll(p, gp, _y, gp_hyper_prior) + reg(p)
+    jac = (lambda p: _grad_nll(p, gp, _y) + reg_grad(p)) if method in ("newton-cg", "l-bfgs-b") else None
+
+    def restore():
+        gp.set_parameter_vector(init_hp)
+        gp.recompute()
+
+    if p0.ndim > 1 and p0.shape[0] > 1:
+        found, mll = [], []
+        for i, x0 in enumerate(p0):
+            try:
+                r = minimize(obj, x0, method=method, jac=jac, bounds=bounds, options=optimizer_kwargs)
+                if np.isfinite(gp_hyper_prior(r.x)):
+                    gp.set_parameter_vector(r.x)
+                    found.append(np.array(r.x))
+                    mll.append(gp.log_likelihood(_y, quiet=True))
+                    continue
+                print(f"\nWarning: GP hyperparameter optimization restart {i} failed. Solution failed prior bounds.\n")
+            except Exception as e:  # noqa: BLE001 - mirrors the reference's catch-all
+                print(f"\nWarning: GP hyperparameter optimization restart {i} failed with error: {e}\n")
+            found.append(init_hp)
+            mll.append(-np.inf)
+        if len(mll) > 0 and max(mll) > -np.inf:
+            gp.set_parameter_vector(found[int(np.argmax(mll))])
+            gp.recompute()
+        else:
+            print("\nWarning: All hyperparameter optimizations failed. Using initial values.\n")
+            restore()
+        return gp
+    try:
+        r = minimize(obj, p0.reshape(-1), method=method, jac=jac, bounds=bounds, options=optimizer_kwargs)
+        if r.success and np.isfinite(gp_hyper_prior(r.x)):
+            gp.set_parameter_vector(r.x)
+            gp.recompute()
+        else:
+            print("\nWarning: GP hyperparameter optimization failed. Using initial values.\n")
+            restore()
+    except Exception as e:  # noqa: BLE001
+        print(f"\nWarning: GP hyperparameter optimization failed with error: {e}. Using initial values.\n")
+        restore()
+    return gp
+
+
+def weighted_mse_by_probability(y_true, y_pred, weight_method="exponential", temperature=1.0):
+    """MSE weighted towards high-likelihood points (alabi/gp_utils.py:450-508)."""
+    return _weighted_mse(np.asarray(y_true), np.asarray(y_pred), weight_method, temperature)
 
 
 def _weighted_mse(y_true, y_pred, method="exponential", temperature=1.0):

@@ -140,6 +140,24 @@ def main():
     np.savez(os.path.join(HERE, "priors_golden.npz"), bounds=pb,
              data=np.array([[np.nan if v is None else v for v in t] for t in pdata]),
              x=px, lnprior_normal=lnpn, u=pu, prior_transform_normal=ptn, prior_transform_normal_1d=ptn1)
+    # ---- remaining benchmark functions -------------------------------------------
+    rng3 = np.random.default_rng(20261020)
+    x1d = rng3.uniform(-2, 1, size=40)
+    bmat = rng3.uniform(0.5, 2.0, size=(4, 3))
+    xnd = rng3.normal(0, 1, size=(16, 10))
+    xm = rng3.uniform(0, 5, size=(32, 2))
+    means = [np.array([0.0, 0.0, 0.0]), np.array([1.0, -1.0, 0.5])]
+    covs = [np.eye(3) * 0.5, np.diag([0.2, 0.4, 0.9])]
+    xg3 = rng3.normal(0, 1, size=(12, 3))
+    np.savez(os.path.join(HERE, "benchmarks2_golden.npz"),
+             x1d=x1d, test1d=bm.test1d_fn(x1d), bmat=bmat, xnd=xnd,
+             rosenbrock_nd=bm.rosenbrock_nd(xnd, 0.7, bmat), rosenbrock_nd_1=bm.rosenbrock_nd(xnd[0], 0.7, bmat),
+             xm=xm, multimodal=np.array([bm.multimodal_fn(x) for x in xm]),
+             logcirc=bm.logcirc(xm, np.array([3.5, 0.0])),
+             xg3=xg3, mmg=bm.multimodal_gaussian_nd(xg3, means, covs, [0.3, 0.6]),
+             wy=xnd[:, 0], wp=xnd[:, 1],
+             wmse=np.array([gpu.weighted_mse_by_probability(xnd[:, 0], xnd[:, 1], weight_method=m, temperature=1.7)
+                            for m in ("exponential", "linear", "softmax", "rank")]))
     print("wrote", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 

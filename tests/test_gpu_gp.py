@@ -275,3 +275,30 @@ def test_large_host_batch_overlapped_copies_identical():
     np.testing.assert_array_equal(var_h, var_d.cpu().numpy())
     mu_o, var_o = o.predict(y, t[-40:], return_var=True)
     assert rel(mu_h[-40:], mu_o) < 1e-9 and np.max(np.abs(var_h[-40:] - var_o)) < 1e-9 * np.exp(o.log_const)
+
+
+@pytest.mark.parametrize("kind,nstart", [("ExpSquaredKernel", 1), ("Matern52Kernel", 3)])
+def test_optimize_gp_ml_restarts(kind, nstart):
+    """gp_utils.optimize_gp (alabi/gp_utils.py:251-447) drives the device objective and
+    gradient; the same driver on the oracle GP from the same starts reaches the same
+    regularised optimum."""
+    from alabi_b200 import gp_utils, utility as ut
+    o, g, X, y, rng = make_pair(kind, 220, 2, seed=5)
+    P = len(g.get_parameter_vector())
+    hp_bounds = [(-10.0, 10.0)] * P
+    prior = lambda p: ut.lnprior_uniform(p, hp_bounds)
+    lidx = [i for i, nm in enumerate(g.get_parameter_names()) if "log_M" in nm]
+    base = np.array(g.get_parameter_vector())
+    p0 = base if nstart == 1 else np.vstack([base] + [base + rng.normal(0, 0.3, size=P) for _ in range(nstart - 1)])
+    obj = lambda gp_, p: gp_utils._nll(p, gp_, y, prior) + gp_utils.regularization_term(p, lidx)
+    f0 = obj(g, base)
+    gp_utils.optimize_gp(g, X, y, prior, p0, bounds=hp_bounds, lengthscale_indices=lidx)
+    gp_utils.optimize_gp(o, X, y, prior, p0, bounds=hp_bounds, lengthscale_indices=lidx)
+    pg, po = np.array(g.get_parameter_vector()), np.array(o.get_parameter_vector())
+    fg, fo = obj(g, pg), obj(o, po)
+    assert fg < f0 - 1e-3 and np.all(np.abs(pg) <= 10.0)
+    assert abs(fg - fo) <= 1e-6 * max(1.0, abs(fo)), (fg, fo)
+    np.testing.assert_allclose(pg, po, rtol=0, atol=2e-3)
+    # device objective at the oracle's optimum equals the oracle's value there (1e-9)
+    assert abs(obj(g, po) - fo) <= 1e-9 * max(1.0, abs(fo))
+    assert g.computed and abs(g.log_likelihood(y) - o.log_likelihood(y)) <= 1e-5 * abs(o.log_likelihood(y))

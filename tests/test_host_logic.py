@@ -102,6 +102,30 @@ def test_host_normal_priors_match_reference_golden():
     assert abs(draws[:, 1].mean() - 5.0) < 0.2 and abs(draws[:, 2].std() - 0.05) < 0.01
 
 
+def test_benchmark_functions_match_reference_golden():
+    from alabi_b200 import benchmarks as bm
+    g = np.load(os.path.join(GOLDEN, "benchmarks2_golden.npz"))
+    np.testing.assert_array_equal(bm.test1d_fn(g["x1d"]), g["test1d"])
+    np.testing.assert_allclose(bm.rosenbrock_nd(g["xnd"], 0.7, g["bmat"]), g["rosenbrock_nd"], rtol=1e-13)
+    np.testing.assert_allclose(bm.rosenbrock_nd(g["xnd"][0], 0.7, g["bmat"]), g["rosenbrock_nd_1"], rtol=1e-13)
+    np.testing.assert_allclose([bm.multimodal_fn(x) for x in g["xm"]], g["multimodal"], rtol=1e-13)
+    np.testing.assert_allclose(bm.logcirc(g["xm"], np.array([3.5, 0.0])), g["logcirc"], rtol=1e-13)
+    means = [np.array([0.0, 0.0, 0.0]), np.array([1.0, -1.0, 0.5])]
+    covs = [np.eye(3) * 0.5, np.diag([0.2, 0.4, 0.9])]
+    np.testing.assert_allclose(bm.multimodal_gaussian_nd(g["xg3"], means, covs, [0.3, 0.6]), g["mmg"], rtol=1e-12)
+    from alabi_b200 import gp_utils
+    for m, w in zip(("exponential", "linear", "softmax", "rank"), g["wmse"]):
+        np.testing.assert_allclose(gp_utils.weighted_mse_by_probability(g["wy"], g["wp"], m, 1.7), w, rtol=1e-13)
+    g1 = np.load(os.path.join(GOLDEN, "benchmarks_golden.npz"))
+    np.testing.assert_allclose([bm.rosenbrock_fn(x) for x in g1["xr"]], g1["rosenbrock"], rtol=1e-13)
+    np.testing.assert_allclose([bm.gaussian_shells_fn(x) for x in g1["xs"]], g1["shells"], rtol=1e-13)
+    np.testing.assert_allclose([bm.eggbox_fn(x) for x in g1["xe"]], g1["eggbox"], rtol=1e-13)
+    np.testing.assert_allclose([bm.gaussian_2d_fn(x) for x in g1["xe"]], g1["gaussian_2d"], rtol=1e-12)
+    for name in ("test1d", "rosenbrock", "gaussian_shells", "eggbox", "multimodal", "gaussian_2d"):
+        d = getattr(bm, name)
+        assert callable(d["fn"]) and len(d["bounds"]) >= 1
+
+
 def test_device_prior_recognition():
     """run_emcee's prior_fn: partials of the two shipped priors are translated for the
     kernel, anything else is refused (no silent CPU sampler)."""
