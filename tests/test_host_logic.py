@@ -26,6 +26,27 @@ def test_library_exports_every_declared_symbol():
     assert ctypes.sizeof(_lib.EnsembleConfig) == lib.ab_sizeof_ensemble_config() == 8 * 4 + 8 * 6 + 4 * 32 * 8 + 8 + 2 * 32 * 8
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/alabi_b200.h is a C99 header (no C++ / torch types): a C program compiled with
+    gcc against it links to the library and sees the same struct size as the ctypes mirror."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from alabi_b200 import _lib
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "alabi_b200.h"\n'
+                   'int main(void){ printf("%d %d %d\\n", ab_version(), ab_sizeof_ensemble_config(),'
+                   ' (int)sizeof(ab_ensemble_config)); return 0; }\n')
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L", libdir, "-lalabi_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    import ctypes
+    assert out == ["100", str(ctypes.sizeof(_lib.EnsembleConfig)), str(ctypes.sizeof(_lib.EnsembleConfig))]
+
+
 def test_product_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
