@@ -71,6 +71,8 @@ SIGNATURES = {
     "ab_gp_get_block_inverses": (ctypes.c_int, [_P, _P]),
     "ab_gp_import_state_full": (ctypes.c_int, [_P, _P, _P, _P]),
     "ab_ensemble_run": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P]),
+    "ab_ensemble_launch": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P]),
+    "ab_ensemble_finish": (ctypes.c_int, [_P]),
 }
 
 _lib = None

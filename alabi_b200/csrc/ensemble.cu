@@ -449,10 +449,11 @@ int launch_ens(ab_gp* h, EnsArgs& A, int n_half, int p) {
 
 }  // namespace
 
-extern "C" int ab_ensemble_run(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords, double* d_logp,
-                               long long* d_naccept, double* d_chain, double* d_logp_chain, double* d_rec_q,
-                               double* d_rec_lp) {
+extern "C" int ab_ensemble_launch(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords, double* d_logp,
+                                  long long* d_naccept, double* d_chain, double* d_logp_chain, double* d_rec_q,
+                                  double* d_rec_lp) {
     if (!h || !cfg) { ab_set_error("null argument"); return -1; }
+    if (h->ens_pending) { ab_set_error("ab_ensemble_launch: the previous run was not finished (ab_ensemble_finish)"); return -1; }
     if (!h->have_alpha) { ab_set_error("ab_ensemble_run: targets not set (call ab_gp_set_targets)"); return -2; }
     if (cfg->nwalkers < 2 || cfg->nsteps < 0 || cfg->thin_by < 1) { ab_set_error("bad ensemble configuration"); return -1; }
     AB_CUDA(cudaSetDevice(h->device));
@@ -518,15 +519,32 @@ extern "C" int ab_ensemble_run(ab_gp* h, const ab_ensemble_config* cfg, double* 
 #undef AB_ENS
     if (rc) return rc;
     AB_CUDA(cudaMemcpyAsync(h->h_pinned, h->scratch, 256, cudaMemcpyDeviceToHost, h->stream));
+    h->ens_pending = true; h->ens_dbg = A.dbg != nullptr; h->ens_ws = A.ws;
+    return 0;
+}
+
+extern "C" int ab_ensemble_finish(ab_gp* h) {
+    if (!h) { ab_set_error("null argument"); return -1; }
+    if (!h->ens_pending) { ab_set_error("ab_ensemble_finish: no run was launched"); return -1; }
+    h->ens_pending = false;
+    AB_CUDA(cudaSetDevice(h->device));
     AB_CUDA(cudaStreamSynchronize(h->stream));
-    if (A.dbg) {
+    if (h->ens_dbg) {
         const long long* dd = reinterpret_cast<const long long*>(h->h_pinned + 16);
         fprintf(stderr, "[ensemble dbg] cycles/half-step: proposal %.0f compute %.0f accept %.0f barrier %.0f (n=%lld, ws=%d)\n",
-                (double)dd[0] / dd[4], (double)dd[1] / dd[4], (double)dd[2] / dd[4], (double)dd[3] / dd[4], dd[4], A.ws);
+                (double)dd[0] / dd[4], (double)dd[1] / dd[4], (double)dd[2] / dd[4], (double)dd[3] / dd[4], dd[4], h->ens_ws);
     }
     if (reinterpret_cast<int*>(h->h_pinned + 1)[0] != 0) {
         ab_set_error("Probability function returned NaN");
         return 1;
     }
     return 0;
+}
+
+extern "C" int ab_ensemble_run(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords, double* d_logp,
+                               long long* d_naccept, double* d_chain, double* d_logp_chain, double* d_rec_q,
+                               double* d_rec_lp) {
+    int rc = ab_ensemble_launch(h, cfg, d_coords, d_logp, d_naccept, d_chain, d_logp_chain, d_rec_q, d_rec_lp);
+    if (rc) return rc;
+    return ab_ensemble_finish(h);
 }

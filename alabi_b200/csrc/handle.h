@@ -56,6 +56,9 @@ struct ab_gp {
     bool factored = false, have_linv = false, have_kinv = false, have_alpha = false;
     int info = 0;
     double logdet = 0.0, quad = 0.0;
+    // ab_ensemble_launch -> ab_ensemble_finish
+    bool ens_pending = false, ens_dbg = false;
+    int ens_ws = 0;
 };
 
 int ab_ensure_scratch(ab_gp* h, size_t bytes);

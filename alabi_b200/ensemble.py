@@ -161,10 +161,19 @@ class EnsembleSampler:
         cfg = self._config(total, thin_by, not have_lp, walker_offset)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record(hd.stream)
-        rc = _lib.check(hd.lib.ab_ensemble_run(hd.h, ctypes.byref(cfg), _lib.ptr(coords), _lib.ptr(logp), _lib.ptr(nacc),
-                                               _lib.ptr(chain), _lib.ptr(lpc), _lib.ptr(rq), _lib.ptr(rl)),
-                        "ab_ensemble_run")
+        _lib.check(hd.lib.ab_ensemble_launch(hd.h, ctypes.byref(cfg), _lib.ptr(coords), _lib.ptr(logp), _lib.ptr(nacc),
+                                             _lib.ptr(chain), _lib.ptr(lpc), _lib.ptr(rq), _lib.ptr(rl)),
+                   "ab_ensemble_launch")
         t1.record(hd.stream)
+        # the whole chain is now enqueued: page-lock the host staging for it (tens of ms for a
+        # c2-sized chain, reused by torch's caching host allocator afterwards) while it runs
+        hbufs = None
+        try:
+            if store:
+                hbufs = (torch.empty(chain.shape, dtype=chain.dtype, pin_memory=True),
+                         torch.empty(lpc.shape, dtype=lpc.dtype, pin_memory=True))
+        finally:
+            rc = _lib.check(hd.lib.ab_ensemble_finish(hd.h), "ab_ensemble_finish")
         t1.synchronize()
         self.last_run_device_seconds = t0.elapsed_time(t1) * 1e-3
         if rc == 1:
@@ -174,11 +183,10 @@ class EnsembleSampler:
         if store:
             # device -> pinned host staging (torch's caching host allocator reuses the block);
             # a first run adopts the staging array instead of copying it again
-            def to_host(t):
-                hbuf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                hbuf.copy_(t)
-                return hbuf.numpy()
-            ch, lh = to_host(chain), to_host(lpc)
+            hbufs[0].copy_(chain, non_blocking=True)
+            hbufs[1].copy_(lpc, non_blocking=True)
+            torch.cuda.current_stream(chain.device).synchronize()
+            ch, lh = hbufs[0].numpy(), hbufs[1].numpy()
             self._chain = ch if len(self._chain) == 0 else np.concatenate([self._chain, ch])
             self._log_prob = lh if len(self._log_prob) == 0 else np.concatenate([self._log_prob, lh])
             self.iteration += int(nsteps)

@@ -187,6 +187,14 @@ typedef struct ab_ensemble_config {
 int ab_ensemble_run(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords, double* d_logp,
                     long long* d_naccept, double* d_chain, double* d_logp_chain, double* d_rec_q,
                     double* d_rec_lp);
+/* The same run in two calls: ab_ensemble_launch enqueues the whole chain on the handle's stream
+ * and returns; ab_ensemble_finish waits for it and returns 0, or 1 when a log-probability was NaN
+ * (emcee raises ValueError there).  Between the two the host is free, e.g. to page-lock the
+ * buffers the chain is copied into.  One run in flight per handle. */
+int ab_ensemble_launch(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords, double* d_logp,
+                       long long* d_naccept, double* d_chain, double* d_logp_chain, double* d_rec_q,
+                       double* d_rec_lp);
+int ab_ensemble_finish(ab_gp* h);
 
 #ifdef __cplusplus
 }
