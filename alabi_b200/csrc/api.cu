@@ -168,6 +168,12 @@ int ab_gp_set_lookahead(ab_gp* h, int enabled) {
     return 0;
 }
 
+int ab_gp_set_few_query_path(ab_gp* h, int enabled) {
+    AB_REQUIRE(h, -1, "null handle");
+    h->few_path = enabled != 0;
+    return 0;
+}
+
 int ab_gp_set_inputs(ab_gp* h, const double* d_X, int64_t n, int d) {
     AB_REQUIRE(h && d_X, -1, "ab_gp_set_inputs: null argument");
     AB_REQUIRE(n >= 1 && d >= 1 && d <= AB_MAX_DIM, -1, "ab_gp_set_inputs: need n >= 1 and 1 <= d <= %d (n=%lld d=%d)",

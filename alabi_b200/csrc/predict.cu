@@ -390,6 +390,207 @@ argmin_final_kernel(const double* __restrict__ bval, const long long* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------
+// Few queries (m <= FEW_MQ: the one-point calls of the acquisition polish, host-driven
+// samplers).  The batched kernels above give one query to one THREAD (mean) and 128 queries
+// to one DMMA tile (variance), so a single query costs as much as 256 / 128 of them and runs
+// as long serial chains: 225 us at N = 1000, 670 us at N = 4000.  This path spreads ONE
+// query over the machine and reproduces the batched kernels' operations in their canonical
+// order, so a query keeps identical bits in any batch:
+//   few_cross_kernel   one training point per thread: k*_j for every query (same r^2 chain,
+//                      same radial function), panel P[j][q]; then one thread per query runs
+//                      the 512-point FMA chain of its split from shared memory
+//   few_gemv_kernel    z = L^-1 k*: one warp per 32 rows, lane = row, sequential FMA chain over
+//                      k ascending -- the order in which DMMA.8x8x4 accumulates a row of the
+//                      product (k4-steps in order, k0..k3 chained inside an instruction)
+//   few_finish_kernel  squares of z summed exactly like tile_thread_sq / tile_finish_var
+//                      (per (warp row, row group): chain over the 8 m-fragments per row
+//                      block, blocks in order, xor tree over the row groups, warp rows 0 + 1),
+//                      and the split sums of the mean in split order
+// ---------------------------------------------------------------------------
+constexpr int FEW_MQ = 8;
+
+template <int KIND, int D>
+__global__ void __launch_bounds__(JCHUNK)
+few_cross_kernel(const double* __restrict__ Xq, int m, const double* __restrict__ Xs, const double* __restrict__ alpha,
+                 int64_t n, int64_t npad, KernParams kp, double* __restrict__ P, double* __restrict__ partial) {
+    __shared__ double sQ[FEW_MQ][D];
+    __shared__ double sK[FEW_MQ][JCHUNK];
+    __shared__ double sAl[JCHUNK];
+    const int tid = threadIdx.x, d = kp.d;
+    const int64_t j = (int64_t)blockIdx.x * JCHUNK + tid;
+    if (tid < FEW_MQ * D) {
+        const int q = tid / D, k = tid - q * D;
+        sQ[q][k] = (k < d && q < m) ? Xq[(int64_t)q * d + k] * kp.inv_len[k] : 0.0;
+    }
+    double x[D];
+#pragma unroll
+    for (int k = 0; k < D; k++) x[k] = (k < d && j < npad) ? Xs[j * d + k] : 0.0;
+    sAl[tid] = (j < n) ? alpha[j] : 0.0;
+    __syncthreads();
+    for (int q = 0; q < FEW_MQ; q++) {
+        double kq = 0.0;
+        if (q < m) {
+            double r = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                const double df = sQ[q][k] - x[k];
+                r = fma(df, df, r);
+            }
+            kq = ab_radial<KIND>(r);
+        }
+        sK[q][tid] = kq;
+        if (P && j < npad) P[j * FEW_MQ + q] = (q < m && j < n) ? kp.amp * kq : 0.0;
+    }
+    __syncthreads();
+    if (tid < m) {
+        const int64_t jtot = P ? npad : n;          // as predict_mean_kernel: the panel pass also walks the padding
+        const int64_t jbeg = (int64_t)blockIdx.x * JCHUNK;
+        const int tn = (int)((jtot - jbeg < JCHUNK) ? (jtot - jbeg) : JCHUNK);
+        double ma = 0.0;
+        for (int jj = 0; jj < tn; jj++) ma = fma(sK[tid][jj], sAl[jj], ma);
+        partial[(int64_t)blockIdx.x * FEW_MQ + tid] = ma;
+    }
+}
+
+template <int MQ>
+__global__ void __launch_bounds__(32)
+few_gemv_kernel(const double* __restrict__ Linv, int64_t ld, const double* __restrict__ P, double* __restrict__ Z) {
+    constexpr int ST = 4, LP = 34;                  // stages; row pitch (double2 reads of 8 lanes hit 32 distinct banks)
+    __shared__ __align__(16) double sL[ST][32 * LP];
+    __shared__ __align__(16) double sP[ST][32 * FEW_MQ];
+    const int lane = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int nt = (int)blockIdx.x + 1;             // 32-wide k tiles up to and including the diagonal one
+    auto issue = [&](int t) {
+        if (t < nt) {
+            const int st = t % ST;
+            const int64_t k0 = (int64_t)t * 32;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int c = lane + 32 * i, row = c >> 4, c16 = c & 15;
+                abg::cp_async16(&sL[st][row * LP + 2 * c16], Linv + (r0 + row) * ld + k0 + 2 * c16);
+            }
+#pragma unroll
+            for (int i = 0; i < FEW_MQ / 2 / 2; i++) {       // 32 rows x 4 chunks of 16 B: the whole FEW_MQ-wide panel rows
+                const int c = lane + 32 * i * 2;
+                abg::cp_async16(&sP[st][2 * c], P + k0 * FEW_MQ + 2 * c);
+                abg::cp_async16(&sP[st][2 * (c + 32)], P + k0 * FEW_MQ + 2 * (c + 32));
+            }
+        }
+        abg::cp_async_commit();
+    };
+    double z[MQ];
+#pragma unroll
+    for (int q = 0; q < MQ; q++) z[q] = 0.0;
+#pragma unroll
+    for (int t = 0; t < ST - 1; t++) issue(t);
+    for (int t = 0; t < nt; t++) {
+        abg::cp_async_wait<ST - 2>();
+        __syncwarp();
+        issue(t + ST - 1);
+        const double* bl = &sL[t % ST][lane * LP];
+        const double* bp = sP[t % ST];
+        const int lim = (t == nt - 1) ? lane + 1 : 32;      // diagonal tile: k <= row
+#pragma unroll 4
+        for (int kk = 0; kk < 32; kk += 2) {
+            const double2 a = *reinterpret_cast<const double2*>(bl + kk);
+            if (kk < lim) {
+#pragma unroll
+                for (int q = 0; q < MQ; q++) z[q] = fma(a.x, bp[kk * FEW_MQ + q], z[q]);
+            }
+            if (kk + 1 < lim) {
+#pragma unroll
+                for (int q = 0; q < MQ; q++) z[q] = fma(a.y, bp[(kk + 1) * FEW_MQ + q], z[q]);
+            }
+        }
+        __syncwarp();
+    }
+    abg::cp_async_wait<0>();
+#pragma unroll
+    for (int q = 0; q < MQ; q++) Z[(int64_t)q * ld + r0 + lane] = z[q];
+}
+
+// 128 threads: thread = (query q, warp row wm, row group g)
+__global__ void __launch_bounds__(16 * FEW_MQ)
+few_finish_kernel(const double* __restrict__ Z, int64_t npad, int T, const double* __restrict__ partial, int nsplit,
+                  int m, double amp, double mean, double* __restrict__ mu, double* __restrict__ var) {
+    __shared__ double sR[FEW_MQ][2];
+    const int tid = threadIdx.x, q = tid >> 4, wm = (tid >> 3) & 1, g = tid & 7;
+    if (Z) {
+        double tot = 0.0;
+        const double* zq = Z + (int64_t)q * npad;
+        for (int i = 0; i < T; i++) {
+            double blk = 0.0;
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+                const double v = (q < m) ? zq[(int64_t)i * NB + wm * 64 + a * 8 + g] : 0.0;
+                blk = fma(v, v, blk);
+            }
+            tot += blk;
+        }
+        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+        if (g == 0) sR[q][wm] = tot;
+    }
+    __syncthreads();
+    if (tid < m) {
+        double s = 0.0;
+        for (int p = 0; p < nsplit; p++) s += partial[(int64_t)p * FEW_MQ + tid];
+        mu[tid] = fma(amp, s, mean);
+        if (Z) var[tid] = amp - (sR[tid][0] + sR[tid][1]);
+    }
+}
+
+template <int KIND>
+int launch_few_cross(ab_gp* h, int Dp, int nsplit, const double* Xq, int m, double* P, double* partial) {
+#define AB_FC(DD)                                                                                              \
+    few_cross_kernel<KIND, DD><<<nsplit, JCHUNK, 0, h->stream>>>(Xq, m, h->Xs, h->alpha, h->n, h->npad, h->kp, P, partial)
+    if (Dp <= 2) AB_FC(2);
+    else if (Dp <= 4) AB_FC(4);
+    else if (Dp <= 8) AB_FC(8);
+    else if (Dp <= 12) AB_FC(12);
+    else if (Dp <= 16) AB_FC(16);
+    else if (Dp <= 20) AB_FC(20);
+    else if (Dp <= 24) AB_FC(24);
+    else AB_FC(32);
+#undef AB_FC
+    AB_CHECK_LAUNCH();
+    return 0;
+}
+
+// mean (and variance) of m <= FEW_MQ queries; 2 (mean) or 3 launches
+int launch_few(ab_gp* h, const double* Xq, int m, double* mu, double* var) {
+    cudaStream_t s = h->stream;
+    const int T = (int)(h->npad / NB);
+    const int nsplit = (int)(((var ? h->npad : h->n) + JCHUNK - 1) / JCHUNK);
+    const size_t need = ((size_t)h->npad * FEW_MQ * 2 + (size_t)nsplit * FEW_MQ) * sizeof(double);
+    int rc = ab_ensure_scratch(h, need);
+    if (rc) return rc;
+    double* P = var ? h->scratch : nullptr;                      // npad x FEW_MQ
+    double* Z = h->scratch + (size_t)h->npad * FEW_MQ;           // FEW_MQ x npad
+    double* partial = Z + (size_t)h->npad * FEW_MQ;
+    ab_prof_begin(h, AB_PROF_PREDICT_PANEL);
+    AB_DISPATCH_KIND(h->kp.kind, rc = (launch_few_cross<KIND>(h, h->d, nsplit, Xq, m, P, partial)));
+    ab_prof_end(h, AB_PROF_PREDICT_PANEL);
+    if (rc) return rc;
+    if (var) {
+        ab_prof_begin(h, AB_PROF_PREDICT_VAR);
+        const unsigned nb = (unsigned)(h->npad / 32);
+        if (m == 1) few_gemv_kernel<1><<<nb, 32, 0, s>>>(h->Linv, h->npad, P, Z);
+        else if (m == 2) few_gemv_kernel<2><<<nb, 32, 0, s>>>(h->Linv, h->npad, P, Z);
+        else if (m <= 4) few_gemv_kernel<4><<<nb, 32, 0, s>>>(h->Linv, h->npad, P, Z);
+        else few_gemv_kernel<8><<<nb, 32, 0, s>>>(h->Linv, h->npad, P, Z);
+        ab_prof_end(h, AB_PROF_PREDICT_VAR);
+        AB_CHECK_LAUNCH();
+    }
+    few_finish_kernel<<<1, 16 * FEW_MQ, 0, s>>>(var ? Z : nullptr, h->npad, T, partial, nsplit, m, h->kp.amp, h->mean, mu, var);
+    AB_CHECK_LAUNCH();
+    ab_count_launches(var ? 3 : 2);
+    return 0;
+}
+
 template <int KIND, bool STORE>
 int launch_mean(ab_gp* h, int Dp, dim3 grid, const double* Xq, int64_t m, int64_t q_off, double* mu, double* P,
                 int64_t ldp, int nsplit, double* partial, int64_t part_ld) {
@@ -453,6 +654,7 @@ int64_t ab_predict_panel_queries(ab_gp* h) {
 
 int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double* var) {
     if (m <= 0) return 0;
+    if (m <= FEW_MQ && h->few_path) return launch_few(h, Xq, (int)m, mu, var);
     cudaStream_t s = h->stream;
     const int d = h->d;
     if (!var) {

@@ -72,6 +72,10 @@ int ab_gp_profile_read(ab_gp* h, int family, double* h_ms, long long* h_count);
 int ab_gp_create(ab_gp** out, int device, void* cuda_stream);
 int ab_gp_destroy(ab_gp* h);
 int ab_gp_set_lookahead(ab_gp* h, int enabled);
+/* predictions of <= 8 queries (GP.predict with M = 1 inside optimisers and samplers,
+ * alabi/utility.py:629-946) use kernels that spread one query over the GPU and reproduce the
+ * batched kernels' bits; 0 sends them through the batched kernels (cross-check), default 1 */
+int ab_gp_set_few_query_path(ab_gp* h, int enabled);
 /* development aid: device buffer (6 x uint64 per tile task, column-major task order) that the
  * dataflow Cholesky fills with %globaltimer stamps; NULL (default) disables it */
 int ab_gp_debug_stamps(ab_gp* h, void* d_buf);

@@ -261,6 +261,45 @@ def test_small_and_large_batches_give_identical_bits():
     assert rel(mu_big[:50], mu_o) < 1e-9 and np.max(np.abs(var_big[:50] - var_o)) < 1e-9 * np.exp(o.log_const)
 
 
+@pytest.mark.parametrize("kind,n,d", [("ExpSquaredKernel", 50, 2), ("Matern32Kernel", 150, 2), ("Matern52Kernel", 333, 5),
+                                      ("ExpSquaredKernel", 1000, 3), ("Matern32Kernel", 1300, 10), ("Matern52Kernel", 2100, 12)])
+def test_few_query_path_reproduces_batched_bits(kind, n, d):
+    """m <= 8 queries run on kernels that spread one query over the GPU (few_cross / few_gemv /
+    few_finish): same mean and variance BITS as the batched kernels (path switched off, and the
+    same queries inside a large batch), for mean-only and mean+variance calls, and parity with
+    the oracle to 1e-9."""
+    o, g, X, y, rng = make_pair(kind, n, d, seed=n + 3)
+    t = rng.uniform(-1.05, 1.05, size=(3000, d))
+    t[3] = X[7]                                         # a training point (variance ~ 0)
+    mu_big, var_big = g.predict(y, t, return_var=True)
+    hd = g._hd
+    for m in (1, 2, 3, 4, 5, 8):
+        hd.lib.ab_gp_set_few_query_path(hd.h, 1)
+        mu_f, var_f = g.predict(y, t[:m], return_var=True)
+        mu_only = g.predict(y, t[:m], return_cov=False)
+        hd.lib.ab_gp_set_few_query_path(hd.h, 0)
+        mu_b, var_b = g.predict(y, t[:m], return_var=True)
+        hd.lib.ab_gp_set_few_query_path(hd.h, 1)
+        np.testing.assert_array_equal(mu_f, mu_b)
+        np.testing.assert_array_equal(var_f, var_b)
+        np.testing.assert_array_equal(mu_f, mu_big[:m])
+        np.testing.assert_array_equal(var_f, var_big[:m])
+        np.testing.assert_array_equal(mu_only, mu_f)
+    # single queries taken from anywhere in the batch
+    for i in (11, 257, 2999):
+        mu1, var1 = g.predict(y, t[i:i + 1], return_var=True)
+        assert mu1[0] == mu_big[i] and var1[0] == var_big[i]
+    mu_o, var_o = o.predict(y, t[:8], return_var=True)
+    mu_f, var_f = g.predict(y, t[:8], return_var=True)
+    assert rel(mu_f, mu_o) < 1e-9 and np.max(np.abs(var_f - var_o)) < 1e-9 * np.exp(o.log_const)
+    # utilities over a handful of candidates take the same path
+    b = np.array([(-1.0, 1.0)] * d)
+    idx, val = g.utility_argmin(y, t[:6], b, algorithm="bape")
+    inside = ou.in_bounds(t[:6], b)
+    want = ou.utility("bape", mu_big[:6], var_big[:6], inside, 0.0)
+    assert idx == ou.first_argmin(want)
+
+
 def test_large_host_batch_overlapped_copies_identical():
     """Host-buffer predicts larger than one variance panel are processed panel by panel with
     the device -> host copies overlapped; the numbers must be the ones the device-tensor
