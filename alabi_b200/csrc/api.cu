@@ -129,7 +129,7 @@ int ab_gp_create(ab_gp** out, int device, void* cuda_stream) {
     AB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     AB_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     AB_CUDA(cudaMalloc(&h->d_info, sizeof(int)));
-    AB_CUDA(cudaMallocHost(&h->h_pinned, 4096));
+    AB_CUDA(cudaMallocHost(&h->h_pinned, 8192));   // [0, 512): scalars / flags / partial sums; [512, 1024): few-query staging
     int rc = ab_ensure_scratch(h, 1 << 20);
     if (rc) return rc;
     *out = h;
@@ -378,6 +378,20 @@ int ab_gp_predict_host(ab_gp* h, const double* h_Xq, int64_t m, double* h_mu, do
     double* dq = h->io;
     double* dmu = h->io + nx;
     double* dvar = h_var ? dmu + m : nullptr;
+    if (m <= 8) {
+        // one-point calls of optimisers / samplers: inputs and results travel through the handle's
+        // page-locked block (one asynchronous copy each way instead of three pageable ones)
+        double* st = h->h_pinned + 512;
+        memcpy(st, h_Xq, nx * sizeof(double));
+        AB_CUDA(cudaMemcpyAsync(dq, st, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        rc = ab_gp_predict(h, dq, m, dmu, dvar);
+        if (rc) return rc;
+        AB_CUDA(cudaMemcpyAsync(st + 256, dmu, (size_t)(h_var ? 2 : 1) * m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        AB_CUDA(cudaStreamSynchronize(h->stream));
+        memcpy(h_mu, st + 256, (size_t)m * sizeof(double));
+        if (h_var) memcpy(h_var, st + 256 + m, (size_t)m * sizeof(double));
+        return 0;
+    }
     AB_CUDA(cudaMemcpyAsync(dq, h_Xq, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     const int64_t chunk = h_var ? ab_predict_panel_queries(h) : m;
     if (m <= chunk) {

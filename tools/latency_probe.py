@@ -27,4 +27,5 @@ for n, d in ((150, 2), (1000, 2), (4000, 2)):
           f"C host call mean+var {per_call(lambda: hd.lib.ab_gp_predict_host(hd.h, _lib.ptr(x1), 1, _lib.ptr(mu), _lib.ptr(var))):.0f} us | "
           f"C host call mean {per_call(lambda: hd.lib.ab_gp_predict_host(hd.h, _lib.ptr(x1), 1, _lib.ptr(mu), None)):.0f} us | "
           f"C device call mean+var (no sync) {per_call(lambda: hd.lib.ab_gp_predict(hd.h, _lib.ptr(xd), 1, _lib.ptr(mud), _lib.ptr(vard))):.0f} us | "
+          f"predict_grad {per_call(lambda: g.predict_grad(y, x1), 500):.0f} us | "
           f"bape_utility {per_call(lambda: ut.bape_utility(x1[0], lambda q: g.predict(y, q, return_var=True), b)):.0f} us")
