@@ -409,6 +409,7 @@ argmin_final_kernel(const double* __restrict__ bval, const long long* __restrict
 //                      and the split sums of the mean in split order
 // ---------------------------------------------------------------------------
 constexpr int FEW_MQ = 8;
+int padded_dim(int d);
 
 template <int KIND, int D>
 __global__ void __launch_bounds__(JCHUNK)
@@ -543,6 +544,151 @@ few_finish_kernel(const double* __restrict__ Z, int64_t npad, int T, const doubl
     }
 }
 
+// v = L^-T z for the few-query gradient path: lane = column i, chain over k ascending from the
+// diagonal (the order of tri_gemm_kernel<true>); Linv rows are read as coalesced 256-byte pieces
+template <int MQ>
+__global__ void __launch_bounds__(32)
+few_gemv_t_kernel(const double* __restrict__ Linv, int64_t ld, const double* __restrict__ Z, double* __restrict__ V) {
+    constexpr int ST = 4;
+    __shared__ __align__(16) double sL[ST][32 * 32];
+    __shared__ __align__(16) double sZ[ST][MQ * 32];
+    const int lane = threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.x * 32;
+    const int nt = (int)((ld - i0) / 32);           // k tiles from the diagonal one to the last row
+    auto issue = [&](int t) {
+        if (t < nt) {
+            const int st = t % ST;
+            const int64_t k0 = i0 + (int64_t)t * 32;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int c = lane + 32 * i, row = c >> 4, c16 = c & 15;
+                abg::cp_async16(&sL[st][row * 32 + 2 * c16], Linv + (k0 + row) * ld + i0 + 2 * c16);
+            }
+            for (int c = lane; c < MQ * 16; c += 32) {
+                const int q = c >> 4, c16 = c & 15;
+                abg::cp_async16(&sZ[st][q * 32 + 2 * c16], Z + (int64_t)q * ld + k0 + 2 * c16);
+            }
+        }
+        abg::cp_async_commit();
+    };
+    double v[MQ];
+#pragma unroll
+    for (int q = 0; q < MQ; q++) v[q] = 0.0;
+#pragma unroll
+    for (int t = 0; t < ST - 1; t++) issue(t);
+    for (int t = 0; t < nt; t++) {
+        abg::cp_async_wait<ST - 2>();
+        __syncwarp();
+        issue(t + ST - 1);
+        const double* bl = sL[t % ST];
+        const double* bz = sZ[t % ST];
+        const int first = (t == 0) ? lane : 0;      // diagonal tile: k >= column
+#pragma unroll 4
+        for (int kk = 0; kk < 32; kk++) {
+            if (kk >= first) {
+                const double a = bl[kk * 32 + lane];
+#pragma unroll
+                for (int q = 0; q < MQ; q++) v[q] = fma(a, bz[q * 32 + kk], v[q]);
+            }
+        }
+        __syncwarp();
+    }
+    abg::cp_async_wait<0>();
+#pragma unroll
+    for (int q = 0; q < MQ; q++) V[(int64_t)q * ld + i0 + lane] = v[q];
+}
+
+// derivative reduction of predict_grad_kernel for few queries: one CTA per 512-point split;
+// per 64-point piece all threads evaluate k'(r^2) for (query, point), then one thread per
+// (query, mean | variance, dimension) extends its FMA chain over the piece in point order
+template <int KIND, int D>
+__global__ void __launch_bounds__(512)
+few_grad_kernel(const double* __restrict__ Xq, int m, const double* __restrict__ Xs, const double* __restrict__ alpha,
+                const double* __restrict__ V, int64_t ldv, int64_t n, int64_t npad, KernParams kp,
+                double* __restrict__ gpart) {
+    constexpr int PS = 64;
+    __shared__ double sQ[FEW_MQ][D];
+    __shared__ double sX[PS * D];
+    __shared__ double sG[FEW_MQ][PS], sV[FEW_MQ][PS], sAl[PS];
+    const int tid = threadIdx.x, d = kp.d;
+    if (tid < FEW_MQ * D) {
+        const int q = tid / D, k = tid - q * D;
+        sQ[q][k] = (k < d && q < m) ? Xq[(int64_t)q * d + k] * kp.inv_len[k] : 0.0;
+    }
+    const int64_t jbeg = (int64_t)blockIdx.x * JCHUNK;
+    const int64_t jend = jbeg + JCHUNK < n ? jbeg + JCHUNK : n;
+    const int cq = tid / (2 * D), crem = tid - cq * 2 * D, ckind = crem / D, ck = crem - ckind * D;
+    const bool chain = cq < m && ck < d;
+    const int ejj = tid & (PS - 1), eq = tid / PS;       // evaluation role: (point, query)
+    double acc = 0.0;
+    for (int64_t j0 = jbeg; j0 < jend; j0 += PS) {
+        __syncthreads();
+        for (int idx = tid; idx < PS * D; idx += 512) {
+            const int jj = idx / D, k = idx - jj * D;
+            sX[idx] = (k < d && j0 + jj < npad) ? Xs[(j0 + jj) * d + k] : 0.0;
+        }
+        if (tid < PS) sAl[tid] = (j0 + tid < n) ? alpha[j0 + tid] : 0.0;
+        __syncthreads();
+        {
+            double g = 0.0, vv = 0.0;
+            if (eq < m && j0 + ejj < n) {
+                double r2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const double df = sQ[eq][k] - sX[ejj * D + k];
+                    r2 = fma(df, df, r2);
+                }
+                g = ab_radial_grad<KIND>(r2);
+                vv = V[(int64_t)eq * ldv + j0 + ejj];
+            }
+            sG[eq][ejj] = g;
+            sV[eq][ejj] = vv;
+        }
+        __syncthreads();
+        if (chain) {
+            const int tn = (int)((jend - j0 < PS) ? (jend - j0) : PS);
+            for (int jj = 0; jj < tn; jj++) {
+                const double df = sQ[cq][ck] - sX[jj * D + ck];
+                const double c = (ckind == 0 ? sAl[jj] : sV[cq][jj]) * sG[cq][jj];
+                acc = fma(c, df, acc);
+            }
+        }
+    }
+    if (chain) gpart[((int64_t)blockIdx.x * 2 * D + ckind * D + ck) * FEW_MQ + cq] = acc;
+}
+
+__global__ void few_grad_finish_kernel(const double* __restrict__ gpart, int nsplit, int D, int m, KernParams kp,
+                                       double* __restrict__ dmu, double* __restrict__ dvar) {
+    const int d = kp.d, idx = threadIdx.x;
+    if (idx >= m * d) return;
+    const int q = idx / d, k = idx - q * d;
+    double sm = 0.0, sv = 0.0;
+    for (int p = 0; p < nsplit; p++) {
+        sm += gpart[((int64_t)p * 2 * D + k) * FEW_MQ + q];
+        sv += gpart[((int64_t)p * 2 * D + D + k) * FEW_MQ + q];
+    }
+    const double f = 2.0 * kp.amp * kp.inv_len[k];
+    dmu[(int64_t)q * d + k] = f * sm;
+    dvar[(int64_t)q * d + k] = -2.0 * f * sv;
+}
+
+template <int KIND>
+int launch_few_grad(ab_gp* h, int Dp, int nsplit, const double* Xq, int m, const double* V, double* gpart) {
+#define AB_FG(DD)                                                                                               \
+    few_grad_kernel<KIND, DD><<<nsplit, 512, 0, h->stream>>>(Xq, m, h->Xs, h->alpha, V, h->npad, h->n, h->npad, h->kp, gpart)
+    if (Dp <= 2) AB_FG(2);
+    else if (Dp <= 4) AB_FG(4);
+    else if (Dp <= 8) AB_FG(8);
+    else if (Dp <= 12) AB_FG(12);
+    else if (Dp <= 16) AB_FG(16);
+    else if (Dp <= 20) AB_FG(20);
+    else if (Dp <= 24) AB_FG(24);
+    else AB_FG(32);
+#undef AB_FG
+    AB_CHECK_LAUNCH();
+    return 0;
+}
+
 template <int KIND>
 int launch_few_cross(ab_gp* h, int Dp, int nsplit, const double* Xq, int m, double* P, double* partial) {
 #define AB_FC(DD)                                                                                              \
@@ -560,17 +706,21 @@ int launch_few_cross(ab_gp* h, int Dp, int nsplit, const double* Xq, int m, doub
     return 0;
 }
 
-// mean (and variance) of m <= FEW_MQ queries; 2 (mean) or 3 launches
-int launch_few(ab_gp* h, const double* Xq, int m, double* mu, double* var) {
+// mean (and variance, and their gradients w.r.t. the query) of m <= FEW_MQ queries;
+// 2 (mean), 3 (+ variance) or 6 (+ gradients) launches
+int launch_few(ab_gp* h, const double* Xq, int m, double* mu, double* var, double* dmu = nullptr, double* dvar = nullptr) {
     cudaStream_t s = h->stream;
     const int T = (int)(h->npad / NB);
     const int nsplit = (int)(((var ? h->npad : h->n) + JCHUNK - 1) / JCHUNK);
-    const size_t need = ((size_t)h->npad * FEW_MQ * 2 + (size_t)nsplit * FEW_MQ) * sizeof(double);
+    const int nsplit_g = (int)((h->n + JCHUNK - 1) / JCHUNK);
+    const size_t need = ((size_t)h->npad * FEW_MQ * 3 + (size_t)nsplit * FEW_MQ + (size_t)nsplit_g * 2 * AB_MAX_DIM * FEW_MQ) * sizeof(double);
     int rc = ab_ensure_scratch(h, need);
     if (rc) return rc;
     double* P = var ? h->scratch : nullptr;                      // npad x FEW_MQ
     double* Z = h->scratch + (size_t)h->npad * FEW_MQ;           // FEW_MQ x npad
-    double* partial = Z + (size_t)h->npad * FEW_MQ;
+    double* V = Z + (size_t)h->npad * FEW_MQ;                    // FEW_MQ x npad
+    double* partial = V + (size_t)h->npad * FEW_MQ;
+    double* gpart = partial + (size_t)nsplit * FEW_MQ;
     ab_prof_begin(h, AB_PROF_PREDICT_PANEL);
     AB_DISPATCH_KIND(h->kp.kind, rc = (launch_few_cross<KIND>(h, h->d, nsplit, Xq, m, P, partial)));
     ab_prof_end(h, AB_PROF_PREDICT_PANEL);
@@ -588,6 +738,20 @@ int launch_few(ab_gp* h, const double* Xq, int m, double* mu, double* var) {
     few_finish_kernel<<<1, 16 * FEW_MQ, 0, s>>>(var ? Z : nullptr, h->npad, T, partial, nsplit, m, h->kp.amp, h->mean, mu, var);
     AB_CHECK_LAUNCH();
     ab_count_launches(var ? 3 : 2);
+    if (var && dmu && dvar) {
+        const unsigned nb = (unsigned)(h->npad / 32);
+        if (m == 1) few_gemv_t_kernel<1><<<nb, 32, 0, s>>>(h->Linv, h->npad, Z, V);
+        else if (m == 2) few_gemv_t_kernel<2><<<nb, 32, 0, s>>>(h->Linv, h->npad, Z, V);
+        else if (m <= 4) few_gemv_t_kernel<4><<<nb, 32, 0, s>>>(h->Linv, h->npad, Z, V);
+        else few_gemv_t_kernel<8><<<nb, 32, 0, s>>>(h->Linv, h->npad, Z, V);
+        AB_CHECK_LAUNCH();
+        const int Dp = padded_dim(h->d);
+        AB_DISPATCH_KIND(h->kp.kind, rc = (launch_few_grad<KIND>(h, h->d, nsplit_g, Xq, m, V, gpart)));
+        if (rc) return rc;
+        few_grad_finish_kernel<<<1, FEW_MQ * AB_MAX_DIM, 0, s>>>(gpart, nsplit_g, Dp, m, h->kp, dmu, dvar);
+        AB_CHECK_LAUNCH();
+        ab_count_launches(3);
+    }
     return 0;
 }
 
@@ -743,15 +907,18 @@ static int launch_grad_points(ab_gp* h, int Dp, dim3 grid, const double* Xq, int
     return 0;
 }
 
-static int padded_dim(int d) {
+namespace {
+int padded_dim(int d) {
     const int opts[] = {2, 4, 8, 12, 16, 20, 24, 32};
     for (int o : opts) if (d <= o) return o;
     return 32;
 }
+}  // namespace
 
 // mean, variance and their gradients w.r.t. the query coordinates (row-major m x d)
 int ab_launch_predict_grad(ab_gp* h, const double* Xq, int64_t m, double* mu, double* var, double* dmu, double* dvar) {
     if (m <= 0) return 0;
+    if (m <= FEW_MQ && h->few_path) return launch_few(h, Xq, (int)m, mu, var, dmu, dvar);
     cudaStream_t s = h->stream;
     const int d = h->d, D = padded_dim(d);
     AB_CUDA(cudaFuncSetAttribute(tri_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));

@@ -426,13 +426,15 @@ class GP:
         tq = self._dev(self.parse_samples(t))
         m, d = tq.shape
         dev = tq.device
-        mu = torch.empty(m, dtype=torch.float64, device=dev)
-        var = torch.empty(m, dtype=torch.float64, device=dev)
-        dmu = torch.empty((m, d), dtype=torch.float64, device=dev)
-        dvar = torch.empty((m, d), dtype=torch.float64, device=dev)
-        _lib.check(hd.lib.ab_gp_predict_grad(hd.h, _lib.ptr(tq), m, _lib.ptr(mu), _lib.ptr(var), _lib.ptr(dmu),
-                                             _lib.ptr(dvar)), "ab_gp_predict_grad")
-        return mu.cpu().numpy(), var.cpu().numpy(), dmu.cpu().numpy(), dvar.cpu().numpy()
+        # one device block for the four results, one copy back (the polish calls this per point)
+        out = torch.empty(m * (2 + 2 * d), dtype=torch.float64, device=dev)
+        mu, var = out[:m], out[m:2 * m]
+        dmu, dvar = out[2 * m:2 * m + m * d], out[2 * m + m * d:]
+        if m > 0:
+            _lib.check(hd.lib.ab_gp_predict_grad(hd.h, _lib.ptr(tq), m, _lib.ptr(mu), _lib.ptr(var), _lib.ptr(dmu),
+                                                 _lib.ptr(dvar)), "ab_gp_predict_grad")
+        host = out.cpu().numpy()
+        return (host[:m], host[m:2 * m], host[2 * m:2 * m + m * d].reshape(m, d), host[2 * m + m * d:].reshape(m, d))
 
     # -- batched acquisition (K4) -------------------------------------------------------------------
     def utility_argmin(self, y, candidates, bounds, algorithm="bape", y_best=0.0, zeta=0.01, return_values=False):

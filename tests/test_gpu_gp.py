@@ -285,6 +285,17 @@ def test_few_query_path_reproduces_batched_bits(kind, n, d):
         np.testing.assert_array_equal(mu_f, mu_big[:m])
         np.testing.assert_array_equal(var_f, var_big[:m])
         np.testing.assert_array_equal(mu_only, mu_f)
+    # gradients w.r.t. the query point (the default L-BFGS polish calls them one point at a time)
+    big = g.predict_grad(y, t[:300])
+    for m in (1, 3, 8):
+        hd.lib.ab_gp_set_few_query_path(hd.h, 1)
+        few = g.predict_grad(y, t[:m])
+        hd.lib.ab_gp_set_few_query_path(hd.h, 0)
+        bat = g.predict_grad(y, t[:m])
+        hd.lib.ab_gp_set_few_query_path(hd.h, 1)
+        for a, b_, c in zip(few, bat, big):
+            np.testing.assert_array_equal(a, b_)
+            np.testing.assert_array_equal(a, c[:m])
     # single queries taken from anywhere in the batch
     for i in (11, 257, 2999):
         mu1, var1 = g.predict(y, t[i:i + 1], return_var=True)
