@@ -521,14 +521,23 @@ few_finish_kernel(const double* __restrict__ Z, int64_t npad, int T, const doubl
     if (Z) {
         double tot = 0.0;
         const double* zq = Z + (int64_t)q * npad;
-        for (int i = 0; i < T; i++) {
-            double blk = 0.0;
+        // loads of four row blocks are issued together (they do not depend on the chain)
+        for (int i0 = 0; i0 < T; i0 += 4) {
+            double v[4][8];
 #pragma unroll
-            for (int a = 0; a < 8; a++) {
-                const double v = (q < m) ? zq[(int64_t)i * NB + wm * 64 + a * 8 + g] : 0.0;
-                blk = fma(v, v, blk);
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int a = 0; a < 8; a++)
+                    v[u][a] = (q < m && i0 + u < T) ? zq[(int64_t)(i0 + u) * NB + wm * 64 + a * 8 + g] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (i0 + u < T) {
+                    double blk = 0.0;
+#pragma unroll
+                    for (int a = 0; a < 8; a++) blk = fma(v[u][a], v[u][a], blk);
+                    tot += blk;
+                }
             }
-            tot += blk;
         }
         tot += __shfl_xor_sync(0xffffffffu, tot, 1);
         tot += __shfl_xor_sync(0xffffffffu, tot, 2);
