@@ -163,4 +163,6 @@ class Product(Kernel):
 
     def spec(self):
         kid, _, lm = self.k2.spec()
-        return kid, float(np.exp(self.k1.log_constant)), lm
+        with np.errstate(over="ignore"):      # an optimiser may stray to exp(...) = inf: K is then not factorisable
+            amp = float(np.exp(self.k1.log_constant))
+        return kid, amp, lm
