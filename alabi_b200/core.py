@@ -71,6 +71,33 @@ class CachedSurrogateLikelihood:
         return (yp[0], vp[0]) if one else (yp, vp)
 
 
+class _SharedPoint:
+    """One-entry cache in front of ``GP.predict_grad`` for the acquisition polish: scipy
+    evaluates the utility and then its gradient at the same point, and the device call
+    that yields d mu / d sigma^2 also yields mu and sigma^2."""
+
+    def __init__(self, gp, y):
+        self.gp, self._y = gp, y
+        self._key, self._val = None, None
+
+    def _eval(self, xs):
+        xs = np.ascontiguousarray(np.asarray(xs, dtype=np.float64).reshape(1, -1))
+        key = xs.tobytes()
+        if key != self._key:
+            self._val = self.gp.predict_grad(self._y, xs)
+            self._key = key
+        return self._val
+
+    def predict(self, xs):
+        if np.asarray(xs).size != self.gp.kernel.ndim:          # not a single point: plain batched predict
+            return self.gp.predict(self._y, xs, return_var=True)
+        r = self._eval(xs)
+        return r[0], r[1]
+
+    def predict_grad(self, y, xs):
+        return self._eval(xs)
+
+
 class SurrogateModel(object):
     def __init__(self, lnlike_fn=None, bounds=None, param_names=None, cache=True, savedir="results/",
                  model_name="surrogate_model", verbose=True, ncore=1, pool_method="forkserver",
@@ -636,7 +663,13 @@ class SurrogateModel(object):
                 grad_obj_fn = None                      # alabi/core.py:1613-1618
                 if getattr(self, "grad_utility", None) is not None:
                     self.gp._set_targets(self._y)
+                    # the optimiser asks for the utility and its gradient at the same point: both
+                    # are served by ONE device call (same kernels, same bits as separate calls)
                     grad_obj_fn = partial(self.grad_utility, gp=self.gp, bounds=self._bounds)
+                    if str(self.obj_opt_method).lower() in ("l-bfgs-b", "bfgs", "cg", "newton-cg", "tnc", "slsqp", "trust-constr"):
+                        shared = _SharedPoint(self.gp, self._y)     # methods that do use the gradient
+                        obj_fn = partial(obj_fn.func, **{**obj_fn.keywords, "predict_gp": shared.predict})
+                        grad_obj_fn = partial(self.grad_utility, gp=shared, bounds=self._bounds)
                 tp, fp = ut.minimize_objective(obj_fn, bounds=self._bounds, nopt=len(order),
                                                method=self.obj_opt_method, options=optimizer_kwargs or None,
                                                grad_obj_fn=grad_obj_fn, starting_points=cand[order])

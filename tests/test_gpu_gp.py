@@ -356,3 +356,32 @@ def test_optimize_gp_ml_restarts(kind, nstart, reg):
     # device objective at the oracle's optimum equals the oracle's value there (1e-9)
     assert abs(obj(g, po) - fo) <= 1e-9 * max(1.0, abs(fo))
     assert g.computed and abs(g.log_likelihood(y) - o.log_likelihood(y)) <= 1e-5 * abs(o.log_likelihood(y))
+
+
+def test_shared_point_cache_serves_utility_and_gradient():
+    """find_next_point's one-entry cache: the utility and its gradient at one point come from one
+    predict_grad call, with the bits of separate predict / predict_grad calls."""
+    from alabi_b200 import utility as ut
+    from alabi_b200.core import _SharedPoint
+    o, g, X, y, rng = make_pair("Matern32Kernel", 260, 3, seed=12)
+    b = np.array([(-1.0, 1.0)] * 3)
+    sp = _SharedPoint(g, y)
+    calls = {"n": 0}
+    real = g.predict_grad
+
+    def counting(yy, xs):
+        calls["n"] += 1
+        return real(yy, xs)
+    g.predict_grad = counting
+    g._set_targets(y)
+    for x in rng.uniform(-0.9, 0.9, size=(5, 3)):
+        u_direct = ut.bape_utility(x, lambda q: g.predict(y, q, return_var=True), b)
+        n0 = calls["n"]
+        u = ut.bape_utility(x, sp.predict, b)
+        gr = ut.grad_bape_utility(x, sp, b)
+        assert calls["n"] == n0 + 1                       # one device call for both
+        gr_direct = ut.grad_bape_utility(x, g, b)
+        assert u == u_direct
+        np.testing.assert_array_equal(gr, gr_direct)
+    mu, var = sp.predict(X[:10])                          # batches pass straight through
+    assert mu.shape == (10,) and var.shape == (10,)
