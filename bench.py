@@ -18,7 +18,9 @@ no data-path collective).
 
 ``kernels`` (N = 1 only) adds the covariance build, the Cholesky, both solves and the
 log-likelihood gradient at the training-set sizes of configs c4 (N = 8192, d = 10)
-and c5 (N = 16384, d = 20), each against its roof.
+and c5 (N = 16384, d = 20), each against its roof, and ``one_point_calls_c2``: the
+end-to-end latency of the reference's M = 1 calls (``GP.predict`` / ``GP.predict_grad`` on one
+host point) on the c2 model.
 
 ``--impl reference`` times the CPU oracle (NumPy/SciPy restatement of the
 george + emcee path, all host BLAS threads) on a bounded sample of the same
@@ -396,6 +398,24 @@ def main():
                 "panel_kernel_share_of_step": pms.value * 1e-3 / elapsed}
 
     kernels = None if (args.no_kernel_table or world > 1) else kernel_table(lib, peak.value)
+    if kernels is not None:
+        # the reference's M = 1 calls (acquisition polish, host samplers) on the c2 model, end to end
+        # through GP.predict / GP.predict_grad with host buffers (few-query kernels)
+        x1 = np.array([[0.7, -1.3]])
+
+        def per_call_us(f, n=300):
+            for _ in range(20):
+                f()
+            torch.cuda.synchronize()
+            t0_ = time.perf_counter()
+            for _ in range(n):
+                f()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0_) / n * 1e6
+        kernels["one_point_calls_c2"] = {
+            "predict_mean_var_us": per_call_us(lambda: gp.predict(y, x1, return_var=True)),
+            "predict_mean_us": per_call_us(lambda: gp.predict(y, x1, return_cov=False)),
+            "predict_grad_us": per_call_us(lambda: gp.predict_grad(y, x1))}
 
     cpu = None
     if not args.no_cpu_baseline:
