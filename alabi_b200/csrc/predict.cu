@@ -409,6 +409,8 @@ argmin_final_kernel(const double* __restrict__ bval, const long long* __restrict
 //                      and the split sums of the mean in split order
 // ---------------------------------------------------------------------------
 constexpr int FEW_MQ = 8;
+constexpr int FEW_ST = 4;                           // cp.async ring depth of few_gemv_kernel (8 stages measured: no gain, the warp is issue / chain bound)
+constexpr int FEW_GEMV_SMEM = FEW_ST * (32 * 34 + 32 * FEW_MQ) * 8;
 int padded_dim(int d);
 
 template <int KIND, int D>
@@ -457,9 +459,10 @@ few_cross_kernel(const double* __restrict__ Xq, int m, const double* __restrict_
 template <int MQ>
 __global__ void __launch_bounds__(32)
 few_gemv_kernel(const double* __restrict__ Linv, int64_t ld, const double* __restrict__ P, double* __restrict__ Z) {
-    constexpr int ST = 4, LP = 34;                  // stages; row pitch (double2 reads of 8 lanes hit 32 distinct banks)
-    __shared__ __align__(16) double sL[ST][32 * LP];
-    __shared__ __align__(16) double sP[ST][32 * FEW_MQ];
+    constexpr int ST = FEW_ST, LP = 34;             // stages; row pitch (double2 reads of 8 lanes hit 32 distinct banks)
+    extern __shared__ __align__(16) double few_smem[];
+    double (*sL)[32 * LP] = reinterpret_cast<double (*)[32 * LP]>(few_smem);
+    double (*sP)[32 * FEW_MQ] = reinterpret_cast<double (*)[32 * FEW_MQ]>(few_smem + ST * 32 * LP);
     const int lane = threadIdx.x;
     const int64_t r0 = (int64_t)blockIdx.x * 32;
     const int nt = (int)blockIdx.x + 1;             // 32-wide k tiles up to and including the diagonal one
@@ -737,10 +740,16 @@ int launch_few(ab_gp* h, const double* Xq, int m, double* mu, double* var, doubl
     if (var) {
         ab_prof_begin(h, AB_PROF_PREDICT_VAR);
         const unsigned nb = (unsigned)(h->npad / 32);
-        if (m == 1) few_gemv_kernel<1><<<nb, 32, 0, s>>>(h->Linv, h->npad, P, Z);
-        else if (m == 2) few_gemv_kernel<2><<<nb, 32, 0, s>>>(h->Linv, h->npad, P, Z);
-        else if (m <= 4) few_gemv_kernel<4><<<nb, 32, 0, s>>>(h->Linv, h->npad, P, Z);
-        else few_gemv_kernel<8><<<nb, 32, 0, s>>>(h->Linv, h->npad, P, Z);
+#define AB_FGV(MQV)                                                                                                  \
+    do {                                                                                                             \
+        AB_CUDA(cudaFuncSetAttribute(few_gemv_kernel<MQV>, cudaFuncAttributeMaxDynamicSharedMemorySize, FEW_GEMV_SMEM)); \
+        few_gemv_kernel<MQV><<<nb, 32, FEW_GEMV_SMEM, s>>>(h->Linv, h->npad, P, Z);                                  \
+    } while (0)
+        if (m == 1) AB_FGV(1);
+        else if (m == 2) AB_FGV(2);
+        else if (m <= 4) AB_FGV(4);
+        else AB_FGV(8);
+#undef AB_FGV
         ab_prof_end(h, AB_PROF_PREDICT_VAR);
         AB_CHECK_LAUNCH();
     }
