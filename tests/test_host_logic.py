@@ -310,3 +310,62 @@ def test_report_writers_cpu(tmp_path):
     assert txt.count("=" * 66) == 6 and "Kernel: ExpSquaredKernel" in txt and "[mean:value] \t0.5" in txt
     assert "Final test error (MSE): 0.1" in txt and "Number of walkers: 40" in txt and "a = " in txt
     assert "Total weighted samples: 300" in txt
+
+
+def test_optimize_gp_driver_on_cpu_oracle():
+    """Host logic of gp_utils.optimize_gp (restart selection, fall-back to the initial vector)
+    exercised on the CPU oracle GP, which speaks the same protocol as the device GP."""
+    from oracle import gp as ogp
+    from alabi_b200 import gp_utils, utility as ut
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-1, 1, size=(120, 2))
+    y = np.sin(X.sum(axis=1)) + 0.3 * np.cos(2 * X[:, 0]) + 0.05 * rng.normal(size=120)
+    o = ogp.make_gp("Matern52Kernel", X, y, rng.uniform(-0.5, 0.8, size=2), amp=np.var(y), white_noise=-6.0, compute=True)
+    P = len(o.get_parameter_vector())
+    base = np.array(o.get_parameter_vector())
+    wide = lambda p: ut.lnprior_uniform(p, [(-20.0, 20.0)] * P)
+    nll0 = gp_utils._nll(base, o, y, wide)
+    p0 = np.vstack([base, base + rng.normal(0, 0.3, size=P), base + rng.normal(0, 0.3, size=P)])
+    gp_utils.optimize_gp(o, X, y, wide, p0, bounds=[(-10.0, 10.0)] * P, regularize=False)
+    best = np.array(o.get_parameter_vector())
+    assert gp_utils._nll(best, o, y, wide) < nll0 - 1.0 and o.computed
+    # gradient of the objective the optimiser saw is consistent with finite differences
+    from scipy.optimize import approx_fprime
+    g_fd = approx_fprime(best, lambda p: gp_utils._nll(p, o, y, wide), 1e-6)
+    np.testing.assert_allclose(gp_utils._grad_nll(best, o, y), g_fd, rtol=1e-3, atol=1e-3)
+    # a hyper-prior that rejects every solution: the initial vector is restored
+    o.set_parameter_vector(base)
+    o.recompute()
+    narrow = lambda p: ut.lnprior_uniform(p, [(b_ - 1e-9, b_ + 1e-9) for b_ in base + 5.0])
+    gp_utils.optimize_gp(o, X, y, narrow, p0, bounds=[(-10.0, 10.0)] * P, regularize=False)
+    np.testing.assert_array_equal(o.get_parameter_vector(), base)
+    gp_utils.optimize_gp(o, X, y, narrow, base, bounds=[(-10.0, 10.0)] * P, regularize=False)
+    np.testing.assert_array_equal(o.get_parameter_vector(), base)
+    assert gp_utils._nll(base, o, y, narrow) == np.inf
+
+
+def test_shared_point_cache_host_logic():
+    from alabi_b200.core import _SharedPoint
+
+    class FakeGP:
+        class kernel:
+            ndim = 3
+        calls = 0
+
+        def predict_grad(self, y, xs):
+            self.calls += 1
+            s = float(np.sum(xs))
+            return np.array([s]), np.array([s * s]), xs.copy(), 2 * xs
+
+        def predict(self, y, xs, return_var=True):
+            return np.zeros(len(xs)), np.ones(len(xs))
+    g = FakeGP()
+    sp = _SharedPoint(g, np.zeros(4))
+    x = np.array([0.1, 0.2, 0.3])
+    mu, var = sp.predict(x.reshape(1, -1))
+    r = sp.predict_grad(None, x)
+    assert g.calls == 1 and mu[0] == r[0][0] and var[0] == r[1][0]
+    sp.predict(x + 1.0)
+    assert g.calls == 2
+    mu, var = sp.predict(np.zeros((5, 3)))           # a batch goes to the plain predict
+    assert g.calls == 2 and mu.shape == (5,)
