@@ -14,6 +14,9 @@
 //             whose epilogue squares and column-reduces the product in
 //             registers; nothing but sigma^2 is written back.  White noise is
 //             not added (george semantics).
+//   few       m <= 8 queries (the reference's M = 1 calls inside optimisers and samplers):
+//             few_* kernels spread one query over the GPU and reproduce the batched
+//             kernels' summation order, so a query has the same bits in any batch.
 #include <float.h>
 #include "handle.h"
 #include "dmma_gemm.cuh"
