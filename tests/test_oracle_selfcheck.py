@@ -80,6 +80,25 @@ def test_replay_equals_explicit_draw_loop_and_targets_gaussian():
         np.testing.assert_allclose(r["lp"][ok], lp(r["q"][ok]))
 
 
+def test_box_times_normal_prior_posterior():
+    """Gaussian likelihood N(0, 0.6) x prior N(0.5, 0.3) on theta_0 (ut.lnprior_normal's oracle
+    restatement) in a box: the stretch move with the device draw layout samples the analytic
+    posterior N(0.4, 0.268) on theta_0 and the truncated likelihood on theta_1."""
+    from oracle import utility as ou
+    b = np.array([(-3.0, 3.0), (-3.0, 3.0)])
+    mu, sd = np.array([0.5, np.nan]), np.array([0.3, np.nan])
+    like = lambda q: -0.5 * (np.atleast_2d(q)[:, 0] / 0.6) ** 2 - 0.5 * (np.atleast_2d(q)[:, 1] / 0.9) ** 2
+    with np.errstate(invalid="ignore"):
+        lp = lambda q: like(q) + ou.lnprior_normal(q, b, mu, sd)
+        rng = np.random.default_rng(8)
+        p0 = rng.uniform(-1, 1, size=(48, 2))
+        chain, lps, nacc, rec = oem.replay_device_chain(p0, lp, 900, seed=77)
+    flat = chain[300:].reshape(-1, 2)
+    assert abs(flat[:, 0].mean() - 0.4) < 0.05 and abs(flat[:, 0].std() - 0.2683) < 0.04
+    assert abs(flat[:, 1].std() - 0.9) < 0.12 and np.all(np.abs(flat) < 3.0)
+    assert np.all(np.isfinite(lps[300:]))
+
+
 def test_emcee_order_sampler_targets_gaussian():
     lp = lambda q: -0.5 * np.sum(np.atleast_2d(q) ** 2, axis=1)
     s = oem.StretchEnsemble(40, 2, lp, seed=5, vectorize=True)
