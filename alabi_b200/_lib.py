@@ -74,6 +74,7 @@ SIGNATURES = {
     "ab_ensemble_run": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P]),
     "ab_ensemble_launch": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P]),
     "ab_ensemble_finish": (ctypes.c_int, [_P]),
+    "ab_ensemble_run_host": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P, ctypes.c_int]),
 }
 
 _lib = None

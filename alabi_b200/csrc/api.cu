@@ -96,6 +96,19 @@ static int ensure_kinv(ab_gp* h) {
     return 0;
 }
 
+static int create_resources(ab_gp* h) {
+    int lo = 0, hi = 0;
+    AB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    AB_CUDA(cudaStreamCreateWithPriority(&h->panel_stream, cudaStreamNonBlocking, hi));
+    AB_CUDA(cudaEventCreateWithFlags(&h->ev_panel, cudaEventDisableTiming));
+    AB_CUDA(cudaEventCreateWithFlags(&h->ev_col, cudaEventDisableTiming));
+    AB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    AB_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    AB_CUDA(cudaMalloc(&h->d_info, sizeof(int)));
+    AB_CUDA(cudaMallocHost(&h->h_pinned, 8192));   // [0, 512): scalars / flags / partial sums; [512, 1024): few-query staging
+    return ab_ensure_scratch(h, 1 << 20);
+}
+
 extern "C" {
 
 int ab_version(void) { return 100; }
@@ -121,17 +134,11 @@ int ab_gp_create(ab_gp** out, int device, void* cuda_stream) {
     h->device = device;
     h->nsm = prop.multiProcessorCount;
     h->stream = (cudaStream_t)cuda_stream;
-    int lo = 0, hi = 0;
-    AB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    AB_CUDA(cudaStreamCreateWithPriority(&h->panel_stream, cudaStreamNonBlocking, hi));
-    AB_CUDA(cudaEventCreateWithFlags(&h->ev_panel, cudaEventDisableTiming));
-    AB_CUDA(cudaEventCreateWithFlags(&h->ev_col, cudaEventDisableTiming));
-    AB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    AB_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-    AB_CUDA(cudaMalloc(&h->d_info, sizeof(int)));
-    AB_CUDA(cudaMallocHost(&h->h_pinned, 8192));   // [0, 512): scalars / flags / partial sums; [512, 1024): few-query staging
-    int rc = ab_ensure_scratch(h, 1 << 20);
-    if (rc) return rc;
+    int rc = create_resources(h);
+    if (rc) {                   // nothing half-built survives a failed create
+        ab_gp_destroy(h);
+        return rc;
+    }
     *out = h;
     return 0;
 }
@@ -152,6 +159,8 @@ int ab_gp_destroy(ab_gp* h) {
     cudaEvent_t evs[] = {h->ev_panel, h->ev_col, h->ev_fork, h->ev_join};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
+    for (auto& fam : h->prof_ev)
+        for (cudaEvent_t e : fam) cudaEventDestroy(e);
     delete h;
     return 0;
 }
@@ -184,16 +193,21 @@ int ab_gp_set_inputs(ab_gp* h, const double* d_X, int64_t n, int d) {
         AB_CUDA(cudaStreamSynchronize(h->stream));
         int64_t cap = npad > h->cap_pad ? npad : h->cap_pad;
         int cd = d > h->cap_d ? d : h->cap_d;
+        // the capacities describe what is allocated: zero them first, so a failure half-way
+        // (buffers freed and nulled) can never be mistaken for a usable allocation later
+        h->cap_pad = 0;
+        h->cap_d = 0;
+        h->have_inputs = h->scaled = h->factored = h->have_linv = h->have_kinv = h->have_alpha = false;
         int rc = 0;
-        rc |= re_alloc(&h->X, (size_t)cap * cd);
-        rc |= re_alloc(&h->Xs, (size_t)cap * cd);
-        rc |= re_alloc(&h->XsT, (size_t)cap * cd);
-        rc |= re_alloc(&h->L, (size_t)cap * cap);
-        rc |= re_alloc(&h->Dinv, (size_t)cap * AB_NB);
-        rc |= re_alloc(&h->alpha, (size_t)cap);
-        rc |= re_alloc(&h->z, (size_t)cap);
-        rc |= re_alloc(&h->work, (size_t)cap);
-        rc |= re_alloc(&h->logdet_parts, (size_t)cap / AB_NB);
+        if (!rc) rc = re_alloc(&h->X, (size_t)cap * cd);
+        if (!rc) rc = re_alloc(&h->Xs, (size_t)cap * cd);
+        if (!rc) rc = re_alloc(&h->XsT, (size_t)cap * cd);
+        if (!rc) rc = re_alloc(&h->L, (size_t)cap * cap);
+        if (!rc) rc = re_alloc(&h->Dinv, (size_t)cap * AB_NB);
+        if (!rc) rc = re_alloc(&h->alpha, (size_t)cap);
+        if (!rc) rc = re_alloc(&h->z, (size_t)cap);
+        if (!rc) rc = re_alloc(&h->work, (size_t)cap);
+        if (!rc) rc = re_alloc(&h->logdet_parts, (size_t)cap / AB_NB);
         if (rc) return rc;
         h->cap_pad = cap;
         h->cap_d = cd;
@@ -460,10 +474,12 @@ int ab_gp_utility_argmin(ab_gp* h, int utility_id, const double* d_Xq, int64_t m
 
 long long ab_launch_counter(void) { return g_launches.load(); }
 
+// returns the previous setting (0 / 1)
 int ab_gp_set_profiling(ab_gp* h, int enabled) {
     AB_REQUIRE(h, -1, "null handle");
+    const int prev = h->profiling ? 1 : 0;
     h->profiling = enabled != 0;
-    return 0;
+    return prev;
 }
 
 // Sum of the device time (ms) between the begin/end marks of one kernel family

@@ -107,8 +107,14 @@ template <typename T>
 int grow(T** p, size_t old_count, size_t new_count, cudaStream_t s) {
     T* q = nullptr;
     AB_CUDA(cudaMalloc(&q, new_count * sizeof(T)));
-    if (*p && old_count) AB_CUDA(cudaMemcpyAsync(q, *p, old_count * sizeof(T), cudaMemcpyDeviceToDevice, s));
-    AB_CUDA(cudaStreamSynchronize(s));
+    cudaError_t e = cudaSuccess;
+    if (*p && old_count) e = cudaMemcpyAsync(q, *p, old_count * sizeof(T), cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {          // the old buffer stays in place, the new one is released
+        cudaFree(q);
+        ab_set_error("grow: copy failed: %s", cudaGetErrorString(e));
+        return -100 - (int)e;
+    }
     if (*p) AB_CUDA(cudaFree(*p));
     *p = q;
     return 0;
@@ -123,8 +129,7 @@ int grow_padded(ab_gp* h) {
     int64_t cap = h->cap_pad;
     if (np1 > cap) {
         cap = np1 + (np1 / 4 + NB - 1) / NB * NB;
-        int rc = 0;
-        rc |= grow(&h->X, (size_t)h->n * d, (size_t)cap * h->cap_d, s);
+        int rc = grow(&h->X, (size_t)h->n * d, (size_t)cap * h->cap_d, s);
         if (rc) return rc;
         double* bufs_free[] = {h->Xs, h->XsT, h->alpha, h->z, h->work};
         for (double* b : bufs_free) if (b) AB_CUDA(cudaFree(b));
@@ -134,8 +139,8 @@ int grow_padded(ab_gp* h) {
         AB_CUDA(cudaMalloc(&h->alpha, (size_t)cap * sizeof(double)));
         AB_CUDA(cudaMalloc(&h->z, (size_t)cap * sizeof(double)));
         AB_CUDA(cudaMalloc(&h->work, (size_t)cap * sizeof(double)));
-        rc |= grow(&h->Dinv, (size_t)np0 * NB, (size_t)cap * NB, s);
-        rc |= grow(&h->logdet_parts, (size_t)np0 / NB, (size_t)cap / NB, s);
+        rc = grow(&h->Dinv, (size_t)np0 * NB, (size_t)cap * NB, s);
+        if (!rc) rc = grow(&h->logdet_parts, (size_t)np0 / NB, (size_t)cap / NB, s);
         if (rc) return rc;
     }
     // factor: new buffer (when the capacity grew) or a second buffer of the same capacity;

@@ -20,6 +20,7 @@
 // pair (2i, 2i+1): balanced, position independent, no compaction needed.
 #include <stdio.h>
 #include <cmath>
+#include <vector>
 #include "handle.h"
 #include "alabi_b200.h"
 
@@ -449,14 +450,13 @@ int launch_ens(ab_gp* h, EnsArgs& A, int n_half, int p) {
 
 }  // namespace
 
-extern "C" int ab_ensemble_launch(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords, double* d_logp,
-                                  long long* d_naccept, double* d_chain, double* d_logp_chain, double* d_rec_q,
-                                  double* d_rec_lp) {
-    if (!h || !cfg) { ab_set_error("null argument"); return -1; }
-    if (h->ens_pending) { ab_set_error("ab_ensemble_launch: the previous run was not finished (ab_ensemble_finish)"); return -1; }
+// Enqueue one sampler kernel on the handle's stream.  `first`: clear the barrier counter, the
+// NaN flag and the debug counters; later pieces of the same run clear the barrier counter only.
+static int ens_enqueue(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords, double* d_logp,
+                       long long* d_naccept, double* d_chain, double* d_logp_chain, double* d_rec_q,
+                       double* d_rec_lp, bool first) {
     if (!h->have_alpha) { ab_set_error("ab_ensemble_run: targets not set (call ab_gp_set_targets)"); return -2; }
     if (cfg->nwalkers < 2 || cfg->nsteps < 0 || cfg->thin_by < 1) { ab_set_error("bad ensemble configuration"); return -1; }
-    AB_CUDA(cudaSetDevice(h->device));
     int rc = ab_ensure_scratch(h, 64);
     if (rc) return rc;
     EnsArgs A{};
@@ -465,7 +465,7 @@ extern "C" int ab_ensemble_launch(ab_gp* h, const ab_ensemble_config* cfg, doubl
     A.barrier = reinterpret_cast<unsigned long long*>(h->scratch);
     A.nan_flag = reinterpret_cast<int*>(h->scratch + 1);
     A.dbg = cfg->reserved == 1 ? reinterpret_cast<long long*>(h->scratch + 16) : nullptr;
-    AB_CUDA(cudaMemsetAsync(h->scratch, 0, 256, h->stream));
+    AB_CUDA(cudaMemsetAsync(h->scratch, 0, first ? 256 : 8, h->stream));
     A.XsT = h->XsT; A.alpha = h->alpha; A.n = h->n; A.npad = h->npad; A.kp = h->kp; A.mean = h->mean;
     A.nwalkers = cfg->nwalkers; A.d = h->d; A.nsteps = cfg->nsteps; A.thin_by = cfg->thin_by;
     A.init_logp = cfg->init_logp; A.randomize_split = cfg->randomize_split; A.a = cfg->a;
@@ -518,8 +518,90 @@ extern "C" int ab_ensemble_launch(ab_gp* h, const ab_ensemble_config* cfg, doubl
     else AB_ENS(32);
 #undef AB_ENS
     if (rc) return rc;
+    h->ens_dbg = A.dbg != nullptr; h->ens_ws = A.ws;
+    return 0;
+}
+
+extern "C" int ab_ensemble_launch(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords, double* d_logp,
+                                  long long* d_naccept, double* d_chain, double* d_logp_chain, double* d_rec_q,
+                                  double* d_rec_lp) {
+    if (!h || !cfg) { ab_set_error("null argument"); return -1; }
+    if (h->ens_pending) { ab_set_error("ab_ensemble_launch: the previous run was not finished (ab_ensemble_finish)"); return -1; }
+    AB_CUDA(cudaSetDevice(h->device));
+    int rc = ens_enqueue(h, cfg, d_coords, d_logp, d_naccept, d_chain, d_logp_chain, d_rec_q, d_rec_lp, true);
+    if (rc) return rc;
     AB_CUDA(cudaMemcpyAsync(h->h_pinned, h->scratch, 256, cudaMemcpyDeviceToHost, h->stream));
-    h->ens_pending = true; h->ens_dbg = A.dbg != nullptr; h->ens_ws = A.ws;
+    h->ens_pending = true;
+    return 0;
+}
+
+// The same chain delivered to HOST buffers.  The run is cut into `nblocks` consecutive pieces
+// (the random streams are counter based, so the chain does not depend on the cut); every piece is
+// enqueued at once on the handle's stream, and the stored rows of piece b travel to the host on
+// the handle's second stream while piece b + 1 runs.  h_chain / h_logp_chain may be page-locked
+// (the copies are then asynchronous) or pageable.
+extern "C" int ab_ensemble_run_host(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords, double* d_logp,
+                                    long long* d_naccept, double* d_chain, double* d_logp_chain, double* h_chain,
+                                    double* h_logp_chain, int nblocks) {
+    if (!h || !cfg || !d_chain || !d_logp_chain || !h_chain || !h_logp_chain) { ab_set_error("null argument"); return -1; }
+    if (h->ens_pending) { ab_set_error("ab_ensemble_run_host: the previous run was not finished (ab_ensemble_finish)"); return -1; }
+    if (cfg->thin_by < 1 || cfg->nsteps < 0 || cfg->nsteps % cfg->thin_by != 0) {
+        ab_set_error("ab_ensemble_run_host: nsteps must be a multiple of thin_by"); return -1;
+    }
+    AB_CUDA(cudaSetDevice(h->device));
+    const long long rows = cfg->nsteps / cfg->thin_by, nw = cfg->nwalkers, d = h->d;
+    if (nblocks < 1) nblocks = 1;
+    if (nblocks > 64) nblocks = 64;
+    if ((long long)nblocks > rows) nblocks = rows > 0 ? (int)rows : 1;
+    const long long rpb = rows > 0 ? (rows + nblocks - 1) / nblocks : 0;
+    std::vector<cudaEvent_t> evs;
+    int rc = 0;
+    bool first = true;
+    long long done = 0;
+    struct Piece { long long row0, nrows; };
+    std::vector<Piece> pieces;
+    do {
+        const long long nr = (rows - done < rpb) ? (rows - done) : rpb;
+        ab_ensemble_config c = *cfg;
+        c.nsteps = (int)(nr * cfg->thin_by);
+        c.first_step = cfg->first_step + done * cfg->thin_by;
+        c.init_logp = first ? cfg->init_logp : 0;
+        c.reserved = 0;
+        rc = ens_enqueue(h, &c, d_coords, d_logp, d_naccept, d_chain + done * nw * d, d_logp_chain + done * nw, nullptr,
+                         nullptr, first);
+        if (rc) break;
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { ab_set_error("cudaEventCreate failed"); rc = -100; break; }
+        cudaEventRecord(e, h->stream);
+        evs.push_back(e);
+        pieces.push_back({done, nr});
+        done += nr;
+        first = false;
+    } while (done < rows);
+    if (!rc) {
+        cudaMemcpyAsync(h->h_pinned, h->scratch, 256, cudaMemcpyDeviceToHost, h->stream);
+        for (size_t b = 0; b < pieces.size() && !rc; b++) {
+            const Piece& p = pieces[b];
+            cudaError_t e = cudaStreamWaitEvent(h->panel_stream, evs[b], 0);
+            if (e == cudaSuccess && p.nrows > 0) {
+                e = cudaMemcpyAsync(h_chain + p.row0 * nw * d, d_chain + p.row0 * nw * d, (size_t)(p.nrows * nw * d) * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->panel_stream);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(h_logp_chain + p.row0 * nw, d_logp_chain + p.row0 * nw, (size_t)(p.nrows * nw) * sizeof(double),
+                                        cudaMemcpyDeviceToHost, h->panel_stream);
+            }
+            if (e != cudaSuccess) { ab_set_error("ab_ensemble_run_host: copy failed: %s", cudaGetErrorString(e)); rc = -100 - (int)e; }
+        }
+    }
+    cudaStreamSynchronize(h->panel_stream);
+    cudaError_t es = cudaStreamSynchronize(h->stream);
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    if (rc) return rc;
+    if (es != cudaSuccess) { ab_set_error("ab_ensemble_run_host: %s", cudaGetErrorString(es)); return -100 - (int)es; }
+    if (reinterpret_cast<int*>(h->h_pinned + 1)[0] != 0) {
+        ab_set_error("Probability function returned NaN");
+        return 1;
+    }
     return 0;
 }
 

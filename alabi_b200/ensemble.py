@@ -98,6 +98,7 @@ class EnsembleSampler:
         self.seed = int(np.random.SeedSequence().entropy % (2 ** 63)) if seed is None else int(seed)
         self.randomize_split = bool(randomize_split)
         self.warps_per_unit = int(warps_per_unit)
+        self.pinned_limit_bytes = 4 << 30      # larger stored chains land in pageable host memory
         self.reset()
 
     def reset(self):
@@ -159,34 +160,49 @@ class EnsembleSampler:
         rq = torch.full((total, self.nwalkers, self.ndim), float("nan"), dtype=torch.float64, device=dev) if record_proposals else None
         rl = torch.full((total, self.nwalkers), float("nan"), dtype=torch.float64, device=dev) if record_proposals else None
         cfg = self._config(total, thin_by, not have_lp, walker_offset)
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record(hd.stream)
-        _lib.check(hd.lib.ab_ensemble_launch(hd.h, ctypes.byref(cfg), _lib.ptr(coords), _lib.ptr(logp), _lib.ptr(nacc),
-                                             _lib.ptr(chain), _lib.ptr(lpc), _lib.ptr(rq), _lib.ptr(rl)),
-                   "ab_ensemble_launch")
-        t1.record(hd.stream)
-        # the whole chain is now enqueued; while it runs, allocate the host arrays it is copied
-        # into and touch their pages (a first-touch copy of the 120 MB of c2 takes 54 ms, a copy
-        # into touched pages 6 ms; page-locking the same bytes would cost 80 ms and keep them)
-        hbufs = None
-        try:
+        lib = hd.lib
+        prof_prev = lib.ab_gp_set_profiling(hd.h, 1)
+        if store and not record_proposals:
+            # chain delivered to host arrays by the library: the run is cut into pieces, piece b is
+            # copied out while piece b + 1 runs.  The host arrays are page-locked (torch's pinned
+            # allocator caches the block, so repeated runs reuse touched, locked pages); very large
+            # chains fall back to pageable memory.
+            nbytes = chain.numel() * 8
+            ch_t = lh_t = None
+            if nbytes <= self.pinned_limit_bytes:
+                try:
+                    ch_t = torch.empty(tuple(chain.shape), dtype=torch.float64, pin_memory=True)
+                    lh_t = torch.empty(tuple(lpc.shape), dtype=torch.float64, pin_memory=True)
+                except RuntimeError:
+                    ch_t = lh_t = None
+            if ch_t is None:
+                ch_t = torch.empty(tuple(chain.shape), dtype=torch.float64)
+                lh_t = torch.empty(tuple(lpc.shape), dtype=torch.float64)
+            nblocks = int(min(16, max(1, nbytes // (8 << 20)))) if int(nsteps) > 1 else 1
+            rc = _lib.check(lib.ab_ensemble_run_host(hd.h, ctypes.byref(cfg), _lib.ptr(coords), _lib.ptr(logp), _lib.ptr(nacc),
+                                                     _lib.ptr(chain), _lib.ptr(lpc), _lib.ptr(ch_t), _lib.ptr(lh_t), nblocks),
+                            "ab_ensemble_run_host")
+            hbufs = (ch_t.numpy(), lh_t.numpy())
+        else:
+            _lib.check(lib.ab_ensemble_launch(hd.h, ctypes.byref(cfg), _lib.ptr(coords), _lib.ptr(logp), _lib.ptr(nacc),
+                                              _lib.ptr(chain), _lib.ptr(lpc), _lib.ptr(rq), _lib.ptr(rl)),
+                       "ab_ensemble_launch")
+            rc = _lib.check(lib.ab_ensemble_finish(hd.h), "ab_ensemble_finish")
+            hbufs = None
             if store:
-                hbufs = (np.empty(tuple(chain.shape)), np.empty(tuple(lpc.shape)))
-                hbufs[0].fill(0.0)
-                hbufs[1].fill(0.0)
-        finally:
-            rc = _lib.check(hd.lib.ab_ensemble_finish(hd.h), "ab_ensemble_finish")
-        t1.synchronize()
-        self.last_run_device_seconds = t0.elapsed_time(t1) * 1e-3
+                hbufs = (chain.cpu().numpy(), lpc.cpu().numpy())
+        # device time of the sampler kernels alone (events around the launches, on the handle's stream)
+        kms, kcnt = ctypes.c_double(), ctypes.c_longlong()
+        lib.ab_gp_profile_read(hd.h, 4, ctypes.byref(kms), ctypes.byref(kcnt))
+        lib.ab_gp_set_profiling(hd.h, prof_prev)
+        self.last_run_device_seconds = kms.value * 1e-3
+        self.last_run_launches = int(kcnt.value)
         if rc == 1:
             raise ValueError("Probability function returned NaN")
         self._step_counter += total
         self._naccepted += nacc.cpu().numpy()
         if store:
-            # a first run adopts the host arrays instead of copying them again
             ch, lh = hbufs
-            torch.from_numpy(ch).copy_(chain)
-            torch.from_numpy(lh).copy_(lpc)
             self._chain = ch if len(self._chain) == 0 else np.concatenate([self._chain, ch])
             self._log_prob = lh if len(self._log_prob) == 0 else np.concatenate([self._log_prob, lh])
             self.iteration += int(nsteps)

@@ -8,6 +8,7 @@ attributes and ``solver.get_inverse()`` (alabi/utility.py:577-610).  All
 arithmetic runs in libalabi_b200.so through ``alabi_b200._lib`` (ctypes);
 torch only carries device buffers.  No CPU fallback exists.
 """
+import copy
 import ctypes
 
 import numpy as np
@@ -85,7 +86,9 @@ class GP:
                  fit_white_noise=None, solver=None, device=None, **kwargs):
         if kernel is None or not isinstance(kernel, Kernel):
             raise ValueError("alabi_b200.GP needs an alabi_b200.kernels kernel")
-        self.kernel = kernel
+        # own copy: `kernel * var(y)` keeps a reference to the caller's kernel object, and several
+        # GPs built from one SurrogateModel.kernel must not see each other's hyper-parameters
+        self.kernel = copy.deepcopy(kernel)
         self.mean_value = 0.0 if mean is None else float(mean)
         self.white_noise_value = np.log(TINY) if white_noise is None else float(white_noise)
         self.fit_mean = bool(fit_mean) if fit_mean is not None else False
@@ -102,6 +105,7 @@ class GP:
         self._inputs_pushed = False
         self._kernel_pushed = False
         self._targets_pushed = False
+        self._factor_key = None          # hyper-parameters the device factor was computed for
         self.solver = _Solver(self)
 
     # -- pickling / copying: drop device state, rebuild lazily -----------------------
@@ -109,7 +113,7 @@ class GP:
         st = self.__dict__.copy()
         for k in ("_hd", "_y_dev", "solver"):
             st[k] = None
-        st.update(computed=False, _inputs_pushed=False, _kernel_pushed=False, _targets_pushed=False)
+        st.update(computed=False, _inputs_pushed=False, _kernel_pushed=False, _targets_pushed=False, _factor_key=None)
         return st
 
     def __setstate__(self, st):
@@ -118,7 +122,9 @@ class GP:
 
     def __copy__(self):
         new = GP.__new__(GP)
-        new.__setstate__(self.__getstate__())
+        st = self.__getstate__()
+        st["kernel"] = copy.deepcopy(self.kernel)      # a copy never shares hyper-parameters
+        new.__setstate__(st)
         return new
 
     # -- george "mean" / "white_noise" views -----------------------------------------
@@ -159,8 +165,6 @@ class GP:
         cur = self.get_parameter_vector(include_frozen)
         if len(v) != len(cur):
             raise ValueError("dimension mismatch")
-        if np.array_equal(v, cur):
-            return                       # same hyper-parameters: keep the factorisation (results are identical)
         n = 0
         if self.fit_mean or include_frozen:
             self.mean_value = float(v[n]); n += 1
@@ -168,7 +172,16 @@ class GP:
             self.white_noise_value = float(v[n]); n += 1
         if self.fit_kernel or include_frozen:
             self.kernel.set_parameter_vector(v[n:])
-        self._mark_dirty()
+        # george marks the model dirty on every set; here the factor is kept only when the values
+        # now in force are exactly the ones it was computed for (compared against what was pushed
+        # to the device, never against a live object another GP could have modified)
+        if not (self.computed and self._factor_key is not None and self._spec_key() == self._factor_key):
+            self._mark_dirty()
+
+    def _spec_key(self):
+        kid, amp, log_M = self.kernel.spec()
+        return (int(kid), float(amp), np.asarray(log_M, dtype=np.float64).tobytes(), float(self.mean_value),
+                float(self.white_noise_value), float(self._yerr2))
 
     def get_parameter_dict(self, include_frozen=False):
         return dict(zip(self.get_parameter_names(include_frozen), self.get_parameter_vector(include_frozen)))
@@ -197,6 +210,7 @@ class GP:
         self._kernel_pushed = False
         self._targets_pushed = False
         self._alpha_np = None
+        self._factor_key = None
 
     @property
     def dirty(self):
@@ -256,6 +270,7 @@ class GP:
         if rc > 0:
             raise LinAlgError(f"{rc}-th leading minor of the covariance matrix is not positive definite")
         self.computed = True
+        self._factor_key = self._spec_key()
         return self
 
     def append_point(self, x_new):
@@ -492,11 +507,15 @@ class GP:
         hd.stream.synchronize()
         self._y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
         self.computed = True
+        self._factor_key = self._spec_key()
         self._targets_pushed = True
         return self
 
     def get_matrix(self, x1, x2=None):
         return self.kernel.get_value(x1, x2)
+
+
+_SCRATCH_HANDLES = {}
 
 
 def _kernel_value(kernel, x1, x2=None, diag=False):
@@ -509,7 +528,11 @@ def _kernel_value(kernel, x1, x2=None, diag=False):
     kid, amp, log_M = kernel.spec()
     if diag:
         return np.full(len(x1), amp)
-    hd = _Handle()
+    # one scratch handle per device, reused: numerical_kernel_gradient calls this 2 d times per point
+    cur = torch.cuda.current_device()
+    hd = _SCRATCH_HANDLES.get(cur)
+    if hd is None or hd.stream != torch.cuda.current_stream(cur):
+        hd = _SCRATCH_HANDLES[cur] = _Handle(cur)
     dev = f"cuda:{hd.device}"
     a = torch.from_numpy(np.ascontiguousarray(x1)).to(dev)
     b = torch.from_numpy(np.ascontiguousarray(x2)).to(dev)

@@ -20,7 +20,8 @@ from scipy.stats import norm, qmc
 from sklearn import preprocessing
 
 __all__ = ["agp_utility", "bape_utility", "jones_utility", "assign_utility", "minimize_objective",
-           "prior_sampler", "lnprior_uniform", "prior_transform_uniform", "logsubexp",
+           "prior_sampler", "prior_sampler_normal", "lnprior_uniform", "lnprior_normal",
+           "prior_transform_uniform", "prior_transform_normal", "logsubexp",
            "NewFunctionTransformer", "nlog_scaler", "log_scaler", "no_scaler", "scaler_affine"]
 
 
@@ -131,24 +132,25 @@ def lnprior_uniform(x, bounds):
     return 0
 
 
-def prior_sampler_normal(prior_data, bounds, nsample=1):
-    """Truncated-normal prior draws (alabi/utility.py:130-175): dimensions whose
-    ``prior_data[i]`` is ``(mean, std)`` are normal, ``(None, None)`` uniform; rejection
-    keeps every draw inside ``bounds``."""
+def prior_sampler_normal(prior_data, bounds, nsample=1, random_state=None):
+    """Truncated-normal prior draws (alabi/utility.py:202-215): dimensions whose
+    ``prior_data[i]`` is ``(mean, std)`` are drawn with ``scipy.stats.truncnorm`` inside
+    ``bounds``, ``(None, None)`` dimensions uniformly.  ``random_state`` (seed or Generator)
+    makes the draw reproducible; None uses NumPy's global state like the reference."""
+    from scipy.stats import truncnorm
     b = np.asarray(bounds, dtype=np.float64)
-    rng = np.random.default_rng()
-    out = np.empty((int(nsample), len(b)))
-    for i, (mu, sd) in enumerate(prior_data):
-        if mu is None or sd is None:
-            out[:, i] = rng.uniform(b[i, 0], b[i, 1], size=int(nsample))
-            continue
-        col = rng.normal(mu, sd, size=int(nsample))
-        bad = (col < b[i, 0]) | (col > b[i, 1])
-        while np.any(bad):
-            col[bad] = rng.normal(mu, sd, size=int(bad.sum()))
-            bad = (col < b[i, 0]) | (col > b[i, 1])
-        out[:, i] = col
-    return out
+    rng = np.random.default_rng(random_state) if random_state is not None else None
+    out = np.zeros((len(b), int(nsample)))
+    for i in range(len(b)):
+        mu, sd = prior_data[i]
+        if mu is not None:
+            lb, ub = (b[i, 0] - mu) / sd, (b[i, 1] - mu) / sd
+            out[i] = truncnorm.rvs(lb, ub, loc=mu, scale=sd, size=int(nsample), random_state=rng)
+        elif rng is not None:
+            out[i] = rng.uniform(b[i, 0], b[i, 1], size=int(nsample))
+        else:
+            out[i] = np.random.uniform(low=b[i, 0], high=b[i, 1], size=int(nsample))
+    return out.T
 
 
 def lnprior_normal(x, bounds, data):

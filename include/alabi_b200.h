@@ -64,7 +64,7 @@ int ab_device_sm_count(int device);
 long long ab_launch_counter(void);
 /* measured issue-rate peak of the FP64 tensor pipe (DMMA.8x8x4), TFLOP/s */
 int ab_fp64_tensor_peak(int device, double* h_tflops);
-int ab_gp_set_profiling(ab_gp* h, int enabled);
+int ab_gp_set_profiling(ab_gp* h, int enabled);   /* returns the previous setting (0 / 1) */
 int ab_gp_profile_read(ab_gp* h, int family, double* h_ms, long long* h_count);
 
 /* ---- lifecycle: george.GP(kernel, fit_mean, mean, white_noise, fit_white_noise)
@@ -199,6 +199,16 @@ int ab_ensemble_launch(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords
                        long long* d_naccept, double* d_chain, double* d_logp_chain, double* d_rec_q,
                        double* d_rec_lp);
 int ab_ensemble_finish(ab_gp* h);
+/* The same run with the stored chain delivered to HOST buffers (what emcee's backend holds after
+ * run_mcmc, alabi/core.py:2325 -> sampler.get_chain()): the run is cut into `nblocks` consecutive
+ * pieces (identical chain: the random streams are counter based) that are enqueued back to back;
+ * the stored rows of piece b travel to h_chain ((nsteps/thin_by) x nwalkers x d) and h_logp_chain
+ * on the handle's second stream while piece b + 1 runs.  d_chain / d_logp_chain are device staging
+ * of the same shapes.  Host buffers may be page-locked (asynchronous copies) or pageable.
+ * Returns 0, 1 (NaN log-probability) or < 0. */
+int ab_ensemble_run_host(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords, double* d_logp,
+                         long long* d_naccept, double* d_chain, double* d_logp_chain, double* h_chain,
+                         double* h_logp_chain, int nblocks);
 
 #ifdef __cplusplus
 }

@@ -76,8 +76,17 @@ def test_kernel_parameter_protocol():
     assert list(g.get_parameter_dict().values()) == list(v) and g.dirty
     g2 = ab.GP(kernel=k, mean=0.0)
     assert g2.get_parameter_names() == ("kernel:metric:log_M_0_0", "kernel:metric:log_M_1_1", "kernel:metric:log_M_2_2")
-    kid, amp, lm = kk.spec()
+    kid, amp, lm = g.kernel.spec()
     assert kid == 1 and lm.shape == (3,) and abs(amp - np.exp(v[2])) < 1e-15
+    # a GP owns its kernel: the caller's objects (and other GPs built from them) are untouched
+    np.testing.assert_allclose(kk.get_parameter_vector(), [np.log(6.0 / 3), 0.1, 0.2, 0.3])
+    np.testing.assert_allclose(k.get_parameter_vector(), [0.1, 0.2, 0.3])
+    g3 = ab.GP(kernel=kk, fit_mean=True, mean=1.5, white_noise=-12, fit_white_noise=True)
+    import copy
+    g4 = copy.copy(g3)
+    g4.set_parameter_vector(g3.get_parameter_vector() - 1.0)
+    np.testing.assert_allclose(g3.get_parameter_vector(), [1.5, -12, np.log(2.0), 0.1, 0.2, 0.3])
+    np.testing.assert_allclose(g.get_parameter_vector(), v)
 
 
 def test_host_utilities_match_reference_golden():
