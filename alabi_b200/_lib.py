@@ -39,6 +39,7 @@ SIGNATURES = {
     "ab_device_sm_count": (ctypes.c_int, [ctypes.c_int]),
     "ab_launch_counter": (ctypes.c_longlong, []),
     "ab_fp64_tensor_peak": (ctypes.c_int, [ctypes.c_int, c_double_p]),
+    "ab_fp64_fma_peak": (ctypes.c_int, [ctypes.c_int, c_double_p]),
     "ab_gp_set_profiling": (ctypes.c_int, [_P, ctypes.c_int]),
     "ab_gp_profile_read": (ctypes.c_int, [_P, ctypes.c_int, c_double_p, ctypes.POINTER(ctypes.c_longlong)]),
     "ab_gp_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_int, _P]),

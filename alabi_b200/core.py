@@ -275,8 +275,15 @@ class SurrogateModel(object):
     def set_hyperparameter_vector(self, tmp_gp, optimized_params):
         if optimized_params is None:
             raise ValueError("optimized_params cannot be None. Cannot set hyperparameters.")
-        tmp_gp.set_parameter_vector(self.expand_hyperparameter_vector(optimized_params)
-                                    if self.uniform_scales else optimized_params)
+        full = optimized_params
+        if self.uniform_scales:
+            # A vector that already has the full george length (what active_train hands to _fit_gp:
+            # gp.get_parameter_vector()) is used as it is.  The reference re-expands it through the
+            # positions of the OPTIMISED names (alabi/core.py:1780 -> 695-704), which swaps amplitude
+            # and white noise on every refit; that accident is not reproduced.
+            if not (self.ndim > 1 and len(np.atleast_1d(optimized_params)) == len(self.param_names_full)):
+                full = self.expand_hyperparameter_vector(optimized_params)
+        tmp_gp.set_parameter_vector(full)
         return tmp_gp
 
     def get_hyperparameter_dict(self, gp):
@@ -424,6 +431,40 @@ class SurrogateModel(object):
             return None
         return gp, time.time() - t0
 
+    def _ml_objective(self, cur, _y, regularize=True, amp_0=1.0, mu_0=1.0, sigma_0=2.0):
+        """(nll, grad_nll) of the maximum-likelihood search exactly as the reference composes them
+        (alabi/core.py:1242-1278): negative log marginal likelihood of ``cur`` at the (expanded)
+        hyper-vector plus the length-scale regulariser, non-finite -> 1e25; with
+        ``uniform_scales`` the tied length scale receives the MEAN of the per-dimension
+        gradients and the other entries are copied by their positions in the FULL vector
+        (kept as the reference has it).  Every evaluation is one device factorisation."""
+        kw = dict(amp_0=amp_0, mu_0=mu_0, sigma_0=sigma_0)
+
+        def nll(p_opt):
+            p = self.expand_hyperparameter_vector(p_opt) if self.uniform_scales else p_opt
+            ll = -self.set_hyperparameter_vector(cur, p).log_likelihood(_y, quiet=True)
+            if regularize:
+                ll += gp_utils.regularization_term(p, self.hp_length_indices, **kw)
+            return ll if np.isfinite(ll) else 1e25
+
+        def grad_nll(p_opt):
+            p = self.expand_hyperparameter_vector(p_opt) if self.uniform_scales else p_opt
+            g = -self.set_hyperparameter_vector(cur, p).grad_log_likelihood(_y, quiet=True)
+            if self.uniform_scales:
+                gll = np.zeros(len(p_opt))
+                gll[self.hp_length_index] = np.mean(g[self.hp_length_indices])
+                gll[self.hp_other_indices] = g[self.hp_other_indices]
+            else:
+                gll = g
+            if regularize:
+                rg = gp_utils.regularization_gradient(p, self.hp_length_indices, **kw)
+                if self.uniform_scales:
+                    gll[self.hp_length_index] += np.mean(rg[self.hp_length_indices])
+                else:
+                    gll = gll + rg
+            return gll
+        return nll, grad_nll
+
     def _opt_gp(self, hyperopt_method="ml", regularize=True, amp_0=1.0, mu_0=1.0, sigma_0=2.0,
                 optimizer_kwargs={"maxiter": 100, "xatol": 1e-4, "fatol": 1e-3, "adaptive": True}, cv_folds=5,
                 cv_scoring="mse", cv_n_candidates=20, multi_proc=True, cv_stage2_candidates=None,
@@ -446,31 +487,7 @@ class SurrogateModel(object):
         if hyperopt_method.lower() == "ml":
             cur = self.gp
             cur.compute(_theta)
-            kw = dict(amp_0=amp_0, mu_0=mu_0, sigma_0=sigma_0)
-
-            def nll(p_opt):
-                p = self.expand_hyperparameter_vector(p_opt) if self.uniform_scales else p_opt
-                ll = -self.set_hyperparameter_vector(cur, p).log_likelihood(_y, quiet=True)
-                if regularize:
-                    ll += gp_utils.regularization_term(p, self.hp_length_indices, **kw)
-                return ll if np.isfinite(ll) else 1e25
-
-            def grad_nll(p_opt):
-                p = self.expand_hyperparameter_vector(p_opt) if self.uniform_scales else p_opt
-                g = -self.set_hyperparameter_vector(cur, p).grad_log_likelihood(_y, quiet=True)
-                if self.uniform_scales:
-                    gll = np.zeros(len(p_opt))
-                    gll[self.hp_length_index] = np.mean(g[self.hp_length_indices])
-                    gll[self.hp_other_indices] = g[self.hp_other_indices]
-                else:
-                    gll = g
-                if regularize:
-                    rg = gp_utils.regularization_gradient(p, self.hp_length_indices, **kw)
-                    if self.uniform_scales:
-                        gll[self.hp_length_index] += np.mean(rg[self.hp_length_indices])
-                    else:
-                        gll = gll + rg
-                return gll
+            nll, grad_nll = self._ml_objective(cur, _y, regularize=regularize, amp_0=amp_0, mu_0=mu_0, sigma_0=sigma_0)
 
             def _optimize_fn(x0):
                 return op.minimize(fun=nll, x0=x0, jac=grad_nll if use_gradient else None,

@@ -109,6 +109,7 @@ class EnsembleSampler:
         self._last = None
         self._step_counter = 0
         self.last_run_device_seconds = None
+        self.device_chain = self.device_log_prob = None
 
     # ------------------------------------------------------------------------------------
     def _config(self, nsteps, thin_by, init_logp, walker_offset=0):
@@ -131,7 +132,10 @@ class EnsembleSampler:
     def run_mcmc(self, initial_state, nsteps, progress=False, thin_by=1, store=True, record_proposals=False,
                  walker_offset=0, **kwargs):
         """Run ``nsteps * thin_by`` ensemble steps on the device, storing every
-        ``thin_by``-th.  Returns the final :class:`State`."""
+        ``thin_by``-th.  Returns the final :class:`State`.  ``store``: True (chain and
+        log-probabilities end up in host arrays, emcee's backend), False (final state only) or
+        ``"device"`` (the stored chain stays in HBM as ``device_chain`` / ``device_log_prob``
+        torch tensors: what ``parallel.sharded_ensemble`` all_gathers over NVLink)."""
         import torch
         gp = self.log_prob_fn.gp
         gp.recompute()
@@ -150,6 +154,8 @@ class EnsembleSampler:
             raise ValueError("At least one parameter value was infinite or NaN")
         if self.nwalkers > 1 and np.linalg.matrix_rank(p0 - p0.mean(axis=0)) < min(self.ndim, self.nwalkers - 1):
             raise ValueError("Initial state has a large condition number. Make sure that your walkers are linearly independent for the best performance")
+        on_device = isinstance(store, str) and store == "device"
+        store = bool(store)
         total = int(nsteps) * int(thin_by)
         coords = torch.from_numpy(np.ascontiguousarray(p0)).to(dev)
         logp = torch.from_numpy(np.ascontiguousarray(initial_state.log_prob)).to(dev) if have_lp \
@@ -162,7 +168,7 @@ class EnsembleSampler:
         cfg = self._config(total, thin_by, not have_lp, walker_offset)
         lib = hd.lib
         prof_prev = lib.ab_gp_set_profiling(hd.h, 1)
-        if store and not record_proposals:
+        if store and not record_proposals and not on_device:
             # chain delivered to host arrays by the library: the run is cut into pieces, piece b is
             # copied out while piece b + 1 runs.  The host arrays are page-locked (torch's pinned
             # allocator caches the block, so repeated runs reuse touched, locked pages); very large
@@ -189,7 +195,7 @@ class EnsembleSampler:
                        "ab_ensemble_launch")
             rc = _lib.check(lib.ab_ensemble_finish(hd.h), "ab_ensemble_finish")
             hbufs = None
-            if store:
+            if store and not on_device:
                 hbufs = (chain.cpu().numpy(), lpc.cpu().numpy())
         # device time of the sampler kernels alone (events around the launches, on the handle's stream)
         kms, kcnt = ctypes.c_double(), ctypes.c_longlong()
@@ -201,7 +207,9 @@ class EnsembleSampler:
             raise ValueError("Probability function returned NaN")
         self._step_counter += total
         self._naccepted += nacc.cpu().numpy()
-        if store:
+        if on_device:
+            self.device_chain, self.device_log_prob = chain, lpc
+        elif store:
             ch, lh = hbufs
             self._chain = ch if len(self._chain) == 0 else np.concatenate([self._chain, ch])
             self._log_prob = lh if len(self._log_prob) == 0 else np.concatenate([self._log_prob, lh])

@@ -19,7 +19,7 @@ import os
 
 import numpy as np
 
-__all__ = ["init_distributed", "shard_range", "broadcast_gp", "argmin_allgather", "allgather_rows",
+__all__ = ["init_distributed", "shard_range", "broadcast_gp", "argmin_allgather", "allgather_rows", "allgather_walkers",
            "sharded_predict", "sharded_utility_argmin", "sharded_ensemble", "sharded_restarts",
            "broadcast_object", "world_size"]
 
@@ -57,10 +57,13 @@ def shard_range(m, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def broadcast_gp(gp, x=None, y=None, src=0):
+def broadcast_gp(gp, x=None, y=None, src=0, stats=None):
     """Make every rank hold the GP trained on ``src``: hyper-parameters, inputs
-    and targets travel as a pickled object, L (npad x npad) and alpha as device
-    tensors over NCCL.  Returns the (imported) GP on every rank."""
+    and targets travel as a pickled object, L (npad x npad), the diagonal-block inverses and
+    alpha as device tensors over NCCL.  Returns the (imported) GP on every rank.  ``stats``
+    (a dict) receives ``bytes`` and ``seconds`` of the three device broadcasts (CUDA events on
+    the current stream around them; the first NCCL call of a process also pays the communicator
+    set-up, so time a second broadcast for a bandwidth figure)."""
     import torch
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
@@ -74,14 +77,24 @@ def broadcast_gp(gp, x=None, y=None, src=0):
                      npad=int(L.shape[0]), n=int(alpha.shape[0]))]
     dist.broadcast_object_list(meta, src=src)
     m = meta[0]
-    dev = torch.device("cuda", torch.cuda.current_device())
+    on_gpu = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
     if rank != src:
         L = torch.empty((m["npad"], m["npad"]), dtype=torch.float64, device=dev)
         alpha = torch.empty(m["n"], dtype=torch.float64, device=dev)
         Dinv = torch.empty((m["npad"] // 128, 128, 128), dtype=torch.float64, device=dev)
+    if on_gpu:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     dist.broadcast(L, src=src)
     dist.broadcast(Dinv, src=src)          # same diagonal-block inverses => same L^-1 bits everywhere
     dist.broadcast(alpha, src=src)
+    if on_gpu:
+        e1.record()
+        e1.synchronize()
+        if stats is not None:
+            stats["bytes"] = int(8 * (L.numel() + Dinv.numel() + alpha.numel()))
+            stats["seconds"] = e0.elapsed_time(e1) * 1e-3
     if rank != src:
         gp.set_parameter_vector(m["vector"], include_frozen=True)
         gp.import_state(m["x"], m["y"], L, alpha, yerr=np.sqrt(m["yerr2"]), Dinv=Dinv)
@@ -99,12 +112,18 @@ def argmin_allgather(value, index, device=None):
     world = dist.get_world_size()
     dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
                                              if dist.get_backend() == "nccl" else torch.device("cpu"))
-    mine = torch.tensor([float(value), float(index)], dtype=torch.float64, device=dev)
-    out = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(out, mine)
+    # one 16-byte record per rank: the value's bit pattern and the index, both as int64 (an index
+    # carried as a float64 would be exact only below 2^53)
+    mine = torch.empty(2, dtype=torch.int64)
+    mine[0] = int(np.float64(value).view(np.int64))
+    mine[1] = int(index)
+    mine = mine.to(dev)
+    out = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, mine)
+    rec = out.cpu().numpy().reshape(world, 2)
     best_v, best_i = float("inf"), -1
-    for t in out:
-        v, i = float(t[0]), int(t[1])
+    for r in range(world):
+        v, i = float(rec[r, :1].view(np.float64)[0]), int(rec[r, 1])
         if i >= 0 and (best_i < 0 or v < best_v or (v == best_v and i < best_i)):
             best_v, best_i = v, i
     return best_v, best_i
@@ -156,23 +175,64 @@ def sharded_utility_argmin(gp, y, candidates, bounds, algorithm="bape", y_best=0
     return argmin_allgather(val, idx + lo if idx >= 0 else -1)
 
 
-def sharded_ensemble(sampler_factory, p0, nsteps, gather=True, **run_kwargs):
+def sharded_ensemble(sampler_factory, p0, nsteps, gather=True, to_host=True, **run_kwargs):
     """Independent sub-ensembles: rank r advances walkers [lo, hi) of ``p0`` with
     RNG counters offset by ``lo`` (statistically independent streams), then the
-    chain blocks are all_gather-ed along the walker axis.
+    chain blocks are all_gather-ed along the walker axis — on the device over NCCL when the
+    backend is nccl (the stored chain never leaves HBM before the collective).
 
-    ``sampler_factory(nwalkers_local)`` builds the rank-local EnsembleSampler."""
+    ``sampler_factory(nwalkers_local)`` builds the rank-local EnsembleSampler.  Returns
+    (sampler, chain): the gathered (nsteps, nwalkers, ndim) chain as a NumPy array
+    (``to_host=True``) or as a tensor on the collective's device."""
     import torch
     dist = _dist()
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     lo, hi = shard_range(len(p0), rank, world)
     s = sampler_factory(hi - lo)
-    s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, **run_kwargs)
     if not gather or world == 1:
+        s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, **run_kwargs)
         return s, s.get_chain()
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    chain = allgather_rows(torch.from_numpy(np.ascontiguousarray(s.get_chain())).to(dev), dim=1)
-    return s, chain.cpu().numpy()
+    if dist.get_backend() == "nccl":
+        s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, store="device", **run_kwargs)
+        local = s.device_chain
+    else:
+        s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, **run_kwargs)
+        local = torch.from_numpy(np.ascontiguousarray(s.get_chain()))
+    chain = allgather_walkers(local, len(p0))
+    return s, (_to_host(chain) if to_host else chain)
+
+
+def _to_host(t):
+    """NumPy copy of a tensor; CUDA tensors land in page-locked memory (torch caches the block, so
+    repeated gathers reuse locked, touched pages) unless that allocation fails."""
+    import torch
+    if t.device.type != "cuda":
+        return t.numpy()
+    try:
+        h = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+    except RuntimeError:
+        return t.cpu().numpy()
+    h.copy_(t)
+    return h.numpy()
+
+
+def allgather_walkers(local, nwalkers_total):
+    """all_gather of per-rank chain blocks (nsteps, nwalkers_local, ...) along the walker axis.
+    Equal shards take ONE ``all_gather_into_tensor`` (rank-major) followed by a local
+    re-interleave; ragged shards go through :func:`allgather_rows`."""
+    import torch
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    if nwalkers_total % world != 0:
+        return allgather_rows(local, dim=1)
+    local = local.contiguous()
+    out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local)                  # rank-major concatenation along dim 0
+    out = out.view((world,) + tuple(local.shape))
+    # (world, steps, nwl, ...) -> (steps, world * nwl, ...)
+    return out.movedim(0, 1).reshape((local.shape[0], world * local.shape[1]) + tuple(local.shape[2:]))
 
 
 def world_size():

@@ -64,6 +64,9 @@ int ab_device_sm_count(int device);
 long long ab_launch_counter(void);
 /* measured issue-rate peak of the FP64 tensor pipe (DMMA.8x8x4), TFLOP/s */
 int ab_fp64_tensor_peak(int device, double* h_tflops);
+/* measured issue-rate peak of plain FP64 FMA (DFMA), TFLOP/s: the roof of the kernel-evaluation
+ * loops (covariance build, predictive mean, sampler) */
+int ab_fp64_fma_peak(int device, double* h_tflops);
 int ab_gp_set_profiling(ab_gp* h, int enabled);   /* returns the previous setting (0 / 1) */
 int ab_gp_profile_read(ab_gp* h, int family, double* h_ms, long long* h_count);
 

@@ -250,6 +250,13 @@ def _worker(rank, world, port, q):
     ch = torch.full((4, hi - lo, 2), float(r))
     out["chain"] = par.allgather_rows(ch, dim=1).numpy()
     out["range"] = (lo, hi)
+    # the index travels as int64: values above 2^53 survive (a float64 carrier would round them)
+    big = (1 << 60) + 3 + r
+    out["big"] = par.argmin_allgather(1.0, big)
+    # chain blocks along the walker axis: equal shards take one all_gather_into_tensor
+    eq = torch.arange(3 * 4 * 2, dtype=torch.float64).reshape(3, 4, 2) + 100.0 * r
+    out["walkers_eq"] = par.allgather_walkers(eq, 8).numpy()
+    out["walkers_ragged"] = par.allgather_walkers(ch, 101).numpy()
     # optimiser restarts sharded over ranks: same winner everywhere, ties -> lowest restart index
     from scipy.optimize import minimize
     starts = par.broadcast_object(np.random.default_rng(100 + r).uniform(-3, 3, size=(5, 2)))
@@ -279,6 +286,11 @@ def test_world_size_2_gloo_host_logic():
         assert res[r]["none"][1] == 7 + 51
         np.testing.assert_array_equal(res[r]["rows"][:, 0], np.arange(101))
         assert res[r]["chain"].shape == (4, 101, 2) and res[r]["chain"][0, 50, 0] == 0 and res[r]["chain"][0, 51, 0] == 1
+        assert res[r]["big"] == (1.0, (1 << 60) + 3)
+        we = res[r]["walkers_eq"]
+        base = np.arange(24, dtype=np.float64).reshape(3, 4, 2)
+        assert we.shape == (3, 8, 2) and np.array_equal(we[:, :4], base) and np.array_equal(we[:, 4:], base + 100.0)
+        assert np.array_equal(res[r]["walkers_ragged"], res[r]["chain"])
     assert res[0]["restarts"] == res[1]["restarts"]                 # identical winner and seeds on both ranks
     fun_b, idx_b, x_b, order, starts = res[0]["restarts"]
     assert order == [0, 1, 2, 3, 4] and fun_b < 1e-8
@@ -286,6 +298,33 @@ def test_world_size_2_gloo_host_logic():
     serial = [minimize(lambda x: float(np.sum((x ** 2 - 1.0) ** 2)), np.array(s0), method="l-bfgs-b") for s0 in starts]
     want = min(range(5), key=lambda i: (serial[i].fun, i))
     assert idx_b == want and np.allclose(x_b, serial[want].x)
+
+
+def test_workloads_match_oracle_generator():
+    """alabi_b200.workloads (what bench.py and the GPU parity tests run on) rebuilds the oracle's
+    synthetic configurations bit for bit, and the committed extended-precision references were
+    made from exactly these inputs."""
+    import hashlib
+    from alabi_b200 import workloads as wl
+    from oracle import benchmarks as ob
+    for name in ("c1", "c2", "c3", "c4", "c5"):
+        n = 257 if name in ("c3", "c4", "c5") else None
+        a = wl.make_config(name, n=n)
+        b = ob.make_config(name, n_override=len(a["X"]))
+        assert a["kind"] == b["kind"] and np.array_equal(a["X"], b["X"]) and np.array_equal(a["y"], b["y"])
+        assert np.array_equal(a["bounds"], b["bounds"]) and a["utility"] == b["utility"]
+        assert a["hp"]["white_noise"] == -12.0 and a["hp"]["amp"] == float(np.var(a["y"]))
+    for name in ("c1", "c2", "c3", "c4"):
+        f = os.path.join(GOLDEN, f"extended_{name}.npz")
+        if not os.path.exists(f):
+            continue
+        g = np.load(f)
+        cfg = wl.make_config(name)
+        h = hashlib.sha256()
+        for arr in (cfg["X"], cfg["y"], g["xq"], cfg["hp"]["log_M"]):
+            h.update(np.ascontiguousarray(arr, dtype=np.float64).tobytes())
+        h.update(np.array([cfg["hp"]["amp"], cfg["hp"]["mean"], cfg["hp"]["white_noise"]]).tobytes())
+        assert h.hexdigest() == str(g["sha256"]), name
 
 
 def test_shard_range_covers_everything():
