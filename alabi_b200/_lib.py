@@ -30,6 +30,18 @@ class EnsembleConfig(ctypes.Structure):
                 ("prior_mu", ctypes.c_double * MAX_DIM), ("prior_sd", ctypes.c_double * MAX_DIM)]
 
 
+class NestedConfig(ctypes.Structure):
+    """Mirror of ``ab_nested_config``."""
+    _fields_ = [("nchains", ctypes.c_int), ("walks", ctypes.c_int), ("y_kind", ctypes.c_int),
+                ("use_normal_prior", ctypes.c_int), ("scale", ctypes.c_double), ("lmin", ctypes.c_double),
+                ("seed", ctypes.c_uint64), ("counter", ctypes.c_int64), ("chain_offset", ctypes.c_int64),
+                ("y_scale", ctypes.c_double), ("y_offset", ctypes.c_double),
+                ("lo", ctypes.c_double * MAX_DIM), ("hi", ctypes.c_double * MAX_DIM),
+                ("prior_mu", ctypes.c_double * MAX_DIM), ("prior_sd", ctypes.c_double * MAX_DIM),
+                ("theta_scale", ctypes.c_double * MAX_DIM), ("theta_offset", ctypes.c_double * MAX_DIM),
+                ("chol", ctypes.c_double * (MAX_DIM * MAX_DIM))]
+
+
 # name -> (restype, argtypes); every symbol include/alabi_b200.h declares
 _P = ctypes.c_void_p
 SIGNATURES = {
@@ -75,6 +87,8 @@ SIGNATURES = {
     "ab_ensemble_run": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P]),
     "ab_ensemble_launch": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P]),
     "ab_ensemble_finish": (ctypes.c_int, [_P]),
+    "ab_sizeof_nested_config": (ctypes.c_int, []),
+    "ab_nested_walk": (ctypes.c_int, [_P, ctypes.POINTER(NestedConfig), _P, _P, _P, _P]),
     "ab_ensemble_run_host": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P, ctypes.c_int]),
 }
 
@@ -102,6 +116,8 @@ def load():
     if lib.ab_sizeof_ensemble_config() != ctypes.sizeof(EnsembleConfig):
         raise AlabiB200Error(f"{LIB_PATH} is stale: ab_ensemble_config is {lib.ab_sizeof_ensemble_config()} bytes there, "
                              f"{ctypes.sizeof(EnsembleConfig)} here — rebuild with `python -m alabi_b200.build`")
+    if lib.ab_sizeof_nested_config() != ctypes.sizeof(NestedConfig):
+        raise AlabiB200Error(f"{LIB_PATH} is stale: ab_nested_config size mismatch — rebuild with `python -m alabi_b200.build`")
     _lib = lib
     return lib
 

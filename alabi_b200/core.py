@@ -855,16 +855,117 @@ class SurrogateModel(object):
         print(f"Saving final emcee samples to {fname} ...")
         np.savez(fname, samples=self.emcee_samples)
 
+    def _builtin_nested_runner(self, ns, batch_like, lp, mode, skw, rkw, save_iter):
+        """Closure running one built-in nested-sampling run (see run_dynesty)."""
+        allowed_s = {"nlive", "walks", "nbatch", "rstate", "seed", "bound", "sample", "pool", "queue_size", "use_pool"}
+        allowed_r = {"dlogz", "dlogz_init", "maxiter", "maxcall", "wt_kwargs", "stop_kwargs", "nlive_init", "nlive_batch",
+                     "maxbatch", "n_effective", "print_progress"}
+        bad = (set(skw) - allowed_s) | (set(rkw) - allowed_r)
+        if bad:
+            raise TypeError(f"run_dynesty (built-in sampler): unsupported keyword(s) {sorted(bad)}; sampler_kwargs "
+                            f"{sorted(allowed_s)}, run_kwargs {sorted(allowed_r)}")
+        if str(skw.get("sample", "auto")).lower() not in ("auto", "rwalk"):
+            raise NotImplementedError(f"sample={skw['sample']!r}: the built-in sampler proposes by constrained random "
+                                      "walks (dynesty's 'rwalk')")
+        if str(skw.get("bound", "multi")).lower() not in ("multi", "single", "none"):
+            raise NotImplementedError(f"bound={skw['bound']!r} is not available in the built-in sampler")
+        nlive = int(skw.get("nlive", 50 * self.ndim))
+        walks = int(skw.get("walks", 25))
+        seed = skw.get("seed", skw.get("rstate"))
+        if seed is not None and not isinstance(seed, (int, np.integer)):
+            seed = int(np.random.default_rng(seed).integers(2 ** 62))
+        pfrac = float(dict(rkw.get("wt_kwargs", {"pfrac": 1.0})).get("pfrac", 1.0))
+        maxiter = int(rkw.get("maxiter", int(5e4)))
+        builtin = ns._builtin_transform(self.prior_transform)
+
+        def run_one(run_number):
+            rseed = None if seed is None else int(seed) + 7919 * (run_number - 1)
+            if lp is not None and builtin is not None:
+                kind, pbounds, pdata = builtin
+                walker = ns.DeviceWalker(lp, pbounds, prior_data=pdata if kind == "normal" else None, seed=rseed)
+            else:
+                walker = ns.HostWalker(batch_like, self.prior_transform, self.ndim, rng=np.random.default_rng(rseed))
+            ds = ns.BatchedNestedSampler(walker, self.ndim, nlive=nlive, walks=walks, nbatch=skw.get("nbatch"),
+                                         rstate=None if rseed is None else rseed + 1)
+            if save_iter is not None:
+                path = os.path.join(self.savedir, f"dynesty_sampler_{self.like_fn_name}_run{run_number}.pkl")
+                ds.checkpoint, ds.checkpoint_every = ns.save_checkpoint(path), int(save_iter)
+            if mode == "dynamic":
+                res = ds.run_dynamic(dlogz_init=rkw.get("dlogz_init", 0.5), nlive_init=rkw.get("nlive_init"),
+                                     nlive_batch=rkw.get("nlive_batch"), maxiter=maxiter, maxcall=rkw.get("maxcall"),
+                                     maxbatch=rkw.get("maxbatch"), n_effective=rkw.get("n_effective"), pfrac=pfrac,
+                                     print_progress=bool(rkw.get("print_progress", False)))
+            else:
+                res = ds.run_nested(dlogz=rkw.get("dlogz", 0.01), maxiter=maxiter, maxcall=rkw.get("maxcall"),
+                                    print_progress=bool(rkw.get("print_progress", False)))
+            return ds, res
+        return run_one
+
+    def _dynesty_runner(self, ns, batch_like, mode, skw, rkw, save_iter):
+        """Closure running one real-dynesty run with the reference's defaults (alabi/core.py:2600-2700);
+        the likelihood is reached through a BatchPool, so a dynesty iteration of ``queue_size``
+        proposals is one batched predict."""
+        import dynesty
+        like = ns.BatchLikelihood(batch_like)
+        for key, val in {"bound": "multi", "nlive": 50 * self.ndim, "sample": "auto"}.items():
+            skw.setdefault(key, val)
+        qs = int(skw.pop("queue_size", 64))
+        skw.pop("pool", None)
+        skw.update(pool=ns.BatchPool(like, size=qs), queue_size=qs,
+                   use_pool={"prior_transform": False, "loglikelihood": True, "propose_point": False, "update_bound": False})
+        if mode == "dynamic":
+            for key, val in {"wt_kwargs": {"pfrac": 1.0}, "stop_kwargs": {"pfrac": 1.0}, "maxiter": int(5e4), "dlogz_init": 0.5}.items():
+                rkw.setdefault(key, val)
+        else:
+            rkw.setdefault("maxiter", int(5e4))
+            rkw.pop("dlogz_init", None)
+        cls = dynesty.DynamicNestedSampler if mode == "dynamic" else dynesty.NestedSampler
+
+        def run_one(run_number):
+            ds = cls(like, self.prior_transform, self.ndim, **skw)
+            if save_iter is not None:
+                last = 0
+                while True:
+                    ds.run_nested(maxiter=save_iter, **{k: v for k, v in rkw.items() if k != "maxiter"})
+                    with open(os.path.join(self.savedir, f"dynesty_sampler_{self.like_fn_name}_run{run_number}.pkl"), "wb") as f:
+                        pickle.dump(ds.results, f)
+                    if ds.results.niter <= last:
+                        break
+                    last = ds.results.niter
+            else:
+                ds.run_nested(**rkw)
+            return None, ds.results                      # the sampler holds the pool: keep the results only
+        return run_one
+
     def run_dynesty(self, like_fn=None, prior_transform=None, mode="dynamic", sampler_kwargs={}, run_kwargs={},
                     multi_proc=False, save_iter=None, prior_transform_comment=None, samples_file=None,
                     min_ess=int(1e4)):
-        """Nested sampling of the surrogate.  Uses dynesty when it is importable
-        (its likelihood callable is the cached GPU surrogate); otherwise the
-        built-in batched sampler of ``alabi_b200.nested`` with the same result
-        fields (samples, logwt, logz, logzerr, niter)."""
-        from .nested import BatchedNestedSampler, resample_equal
-        if like_fn is None or like_fn in ("surrogate", "gp", "surrogate_log_likelihood") or \
-                like_fn == self.surrogate_log_likelihood:
+        """Nested sampling of the surrogate (or of a Python likelihood), alabi/core.py:2417-2787.
+
+        * dynesty importable: exactly the reference's calls (``DynamicNestedSampler`` for
+          ``mode="dynamic"``, ``NestedSampler`` for ``"static"``, the reference's default sampler /
+          run kwargs), except that the surrogate likelihood is served through a ``pool``-shaped
+          :class:`alabi_b200.nested.BatchPool`: the ``queue_size`` points dynesty proposes per
+          iteration become ONE batched device predict (the reference re-factorises K for every
+          single point, core.py:1430).
+        * otherwise (this image: dynesty is not installable): the built-in
+          :class:`alabi_b200.nested.BatchedNestedSampler` with the same two modes and result fields
+          (``samples, logwt, logz, logzerr, niter``).  With the surrogate likelihood and one of the
+          reference's prior transforms (``ut.prior_transform_uniform`` / ``_normal``, or None) every
+          batch of constrained random walks is one kernel launch (``ab_nested_walk``); a custom
+          Python ``like_fn`` / ``prior_transform`` runs the same algorithm with host-side walks.
+          ``sampler_kwargs``: nlive (50 ndim), walks (25), nbatch, rstate / seed, bound, sample
+          ("auto" / "rwalk"); ``run_kwargs``: dlogz, dlogz_init (0.5), maxiter (5e4), maxcall,
+          wt_kwargs {"pfrac": 1.0}, nlive_init, nlive_batch, maxbatch, n_effective, print_progress;
+          anything else raises.  ``save_iter`` pickles the dead points every that many iterations;
+          ``multi_proc`` has no meaning here (the batch is the parallelism)."""
+        from . import nested as ns
+        if mode not in ("dynamic", "static"):
+            raise ValueError(f"mode {mode} is not a valid option. Choose 'dynamic' or 'static'.")
+        surrogate = like_fn is None or (isinstance(like_fn, str) and like_fn.lower() in ("surrogate", "gp", "surrogate_log_likelihood")) \
+            or like_fn == self.surrogate_log_likelihood
+        lp = None
+        if surrogate:
             self.like_fn_name = "surrogate"
             lp = self._device_log_prob(-1)
             gp, yc = lp.gp, lp.y
@@ -874,42 +975,58 @@ class SurrogateModel(object):
                 ys = gp.predict(yc, np.atleast_2d(theta) * ts + to, return_cov=False)
                 return self.y_scaler.inverse_transform(ys.reshape(-1, 1)).flatten()
             self.like_fn = self.surrogate_log_likelihood
+        elif isinstance(like_fn, str):
+            if like_fn.lower() not in ("true", "true_log_likelihood"):
+                raise ValueError(f"Unknown string identifier for like_fn: '{like_fn}'. Valid options: 'surrogate', 'true', "
+                                 "'gp', 'surrogate_log_likelihood', 'true_log_likelihood'")
+            self.like_fn_name, self.like_fn = "true", self.true_log_likelihood
+            batch_like = lambda theta: np.array([float(np.asarray(self.true_log_likelihood(t)).reshape(-1)[0])
+                                                 for t in np.atleast_2d(theta)])
         elif callable(like_fn):
             self.like_fn_name = "true" if like_fn == self.true_log_likelihood else "custom"
             self.like_fn = like_fn
             batch_like = lambda theta: np.array([float(np.asarray(like_fn(t)).reshape(-1)[0]) for t in np.atleast_2d(theta)])
-        elif isinstance(like_fn, str) and like_fn.lower() in ("true", "true_log_likelihood"):
-            self.like_fn_name, self.like_fn = "true", self.true_log_likelihood
-            batch_like = lambda theta: np.array([float(np.asarray(self.true_log_likelihood(t)).reshape(-1)[0])
-                                                 for t in np.atleast_2d(theta)])
         else:
-            raise ValueError(f"Unknown like_fn: {like_fn!r}")
-        self.prior_transform = partial(ut.prior_transform_uniform, bounds=self.bounds) \
-            if prior_transform is None else prior_transform
+            raise TypeError(f"like_fn must be None, a string, or a callable function. Received type: {type(like_fn)}")
+        if prior_transform is None:
+            self.prior_transform = partial(ut.prior_transform_uniform, bounds=self.bounds)
+            self.prior_transform_comment = ("Default uniform prior transform. \nPrior function: ut.prior_transform_uniform\n"
+                                            f"\twith bounds {self.bounds}")
+        else:
+            self.prior_transform = prior_transform
+            self.prior_transform_comment = prior_transform_comment if prior_transform_comment is not None else \
+                f"User defined prior transform.Prior function: {getattr(prior_transform, '__name__', 'unrecorded')}"
         t0 = time.time()
         skw = dict(sampler_kwargs)
-        skw.setdefault("nlive", 50 * self.ndim)
         rkw = dict(run_kwargs)
-        rkw.setdefault("maxiter", int(5e4))
-        dlogz = rkw.pop("dlogz_init", rkw.pop("dlogz", 0.5 if mode == "dynamic" else 0.01))
+        try:
+            import dynesty                                # noqa: F401
+            have_dynesty = not skw.pop("builtin", False)
+        except ImportError:
+            have_dynesty = False
+            skw.pop("builtin", None)
+
+        if have_dynesty:
+            run_one = self._dynesty_runner(ns, batch_like, mode, skw, rkw, save_iter)
+        else:
+            run_one = self._builtin_nested_runner(ns, batch_like, lp, mode, skw, rkw, save_iter)
         all_samples, all_logz, accumulated, run_number = [], [], 0, 1
         while True:
-            ds = BatchedNestedSampler(batch_like, self.prior_transform, self.ndim, nlive=skw["nlive"],
-                                      walks=skw.get("walks", 25), rstate=skw.get("rstate"))
-            res = ds.run_nested(dlogz=dlogz, maxiter=rkw["maxiter"])
+            ds, res = run_one(run_number)
             w = np.exp(res.logwt - res.logz[-1])
-            eq = resample_equal(res.samples, w)
+            eq = ns.resample_equal(res.samples, w)
             all_samples.append(eq)
             all_logz.append(res.logz[-1])
             accumulated += eq.shape[0]
             if self.verbose:
                 print(f"Run {run_number} complete: {eq.shape[0]} samples, logZ = {res.logz[-1]:.3f}")
             if accumulated >= min_ess or run_number >= 10:
+                if accumulated < min_ess:
+                    print(f"WARNING: Reached maximum of 10 runs, stopping with {accumulated} samples")
                 break
             run_number += 1
         self.dynesty_samples = np.vstack(all_samples) if len(all_samples) > 1 else all_samples[0]
         self.dynesty_logz = max(all_logz)
-        ds.loglike = None                  # keep the object picklable (results live in dynesty_results)
         self.dynesty_sampler, self.dynesty_results = ds, res
         self.dynesty_logz_err = res.logzerr[-1]
         if self.like_fn_name == "true":

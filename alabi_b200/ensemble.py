@@ -152,7 +152,7 @@ class EnsembleSampler:
             raise ValueError("incompatible input dimensions")
         if not np.all(np.isfinite(p0)):
             raise ValueError("At least one parameter value was infinite or NaN")
-        if self.nwalkers > 1 and np.linalg.matrix_rank(p0 - p0.mean(axis=0)) < min(self.ndim, self.nwalkers - 1):
+        if self.nwalkers > 1 and not self._independent(p0):
             raise ValueError("Initial state has a large condition number. Make sure that your walkers are linearly independent for the best performance")
         on_device = isinstance(store, str) and store == "device"
         store = bool(store)
@@ -218,6 +218,16 @@ class EnsembleSampler:
             self.proposal_record = (rq.cpu().numpy(), rl.cpu().numpy())
         self._last = State(coords.cpu().numpy(), logp.cpu().numpy())
         return self._last
+
+    def _independent(self, p0):
+        """emcee's start-up check: the walkers must span the space.  Rank of the centred positions
+        through their ndim x ndim triangular factor (O(nwalkers ndim^2)), not an SVD of the tall
+        matrix; skipped when the run continues from this sampler's own last state."""
+        if p0 is getattr(self._last, "coords", None):
+            return True
+        c = p0 - p0.mean(axis=0)
+        r = np.linalg.qr(c, mode="r") if c.shape[0] >= c.shape[1] else c
+        return np.linalg.matrix_rank(r) >= min(self.ndim, self.nwalkers - 1)
 
     def sample(self, initial_state, iterations=1, **kwargs):
         for _ in range(int(iterations)):

@@ -213,6 +213,37 @@ int ab_ensemble_run_host(ab_gp* h, const ab_ensemble_config* cfg, double* d_coor
                          long long* d_naccept, double* d_chain, double* d_logp_chain, double* h_chain,
                          double* h_logp_chain, int nblocks);
 
+/* Nested sampling on the surrogate: a batch of constrained random walks in the unit cube
+ * (dynesty's sample="rwalk" replacement step; the reference passes surrogate_log_likelihood and a
+ * prior transform to dynesty.(Dynamic)NestedSampler, alabi/core.py:2549-2706).  Chain c starts at
+ * d_u[c] (unit cube) with log-likelihood d_logl[c] and makes `walks` Metropolis steps
+ * u' = u + scale * chol z, z ~ N(0, I); u' is accepted iff it lies inside (0, 1)^d and the surrogate
+ * mean at prior_transform(u') exceeds lmin.  Prior transform: (hi - lo) u + lo per dimension
+ * (ut.prior_transform_uniform), or mu + sd * ndtri(u) where use_normal_prior != 0 and
+ * prior_sd[k] > 0 (ut.prior_transform_normal).  Random numbers: Philox4x32-10, key = seed,
+ * counter = (chain_offset + c, step, pair of dimensions, counter).  On return d_u / d_logl hold
+ * the end points, d_theta (nchains x d) their images under the prior transform (rows of chains
+ * that never moved are left untouched) and d_naccept the accepted steps per chain. */
+typedef struct ab_nested_config {
+    int nchains;
+    int walks;
+    int y_kind;            /* as in ab_ensemble_config */
+    int use_normal_prior;
+    double scale;
+    double lmin;
+    uint64_t seed;
+    int64_t counter;
+    int64_t chain_offset;
+    double y_scale, y_offset;
+    double lo[AB_MAX_DIM_PUBLIC], hi[AB_MAX_DIM_PUBLIC];
+    double prior_mu[AB_MAX_DIM_PUBLIC], prior_sd[AB_MAX_DIM_PUBLIC];
+    double theta_scale[AB_MAX_DIM_PUBLIC], theta_offset[AB_MAX_DIM_PUBLIC];
+    double chol[AB_MAX_DIM_PUBLIC * AB_MAX_DIM_PUBLIC];   /* d x d, row-major, lower triangular */
+} ab_nested_config;
+int ab_sizeof_nested_config(void);
+int ab_nested_walk(ab_gp* h, const ab_nested_config* cfg, double* d_u, double* d_logl, double* d_theta,
+                   int* d_naccept);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,7 +72,7 @@ def test_alabi_workflow(tmp_path, hyperopt):
     s = sm.emcee_samples
     assert s.shape[1] == 2 and len(s) >= 500 and 0.2 < sm.acc_frac < 0.9
     assert abs(s[:, 0].std() - 0.6) < 0.12 and abs(s[:, 1].std() - 0.9) < 0.15 and abs(s.mean()) < 0.15
-    sm.run_dynesty(sampler_kwargs={"nlive": 200}, min_ess=200, run_kwargs={"dlogz": 0.05})
+    sm.run_dynesty(sampler_kwargs={"nlive": 200}, min_ess=200, run_kwargs={"n_effective": 2000})      # default mode: dynamic
     dz = sm.dynesty_samples
     assert abs(dz[:, 0].std() - 0.6) < 0.12 and abs(dz[:, 1].std() - 0.9) < 0.15
     want_logz = np.log(2 * np.pi * 0.6 * 0.9 / 36.0)

@@ -209,16 +209,76 @@ def test_autocorr_and_samplers_host_side():
 
 
 def test_batched_nested_sampler_evidence():
-    from alabi_b200.nested import BatchedNestedSampler, resample_equal
+    """Built-in nested sampler on the host walker: static and dynamic runs recover the evidence and
+    the posterior of a Gaussian; a user prior transform is called ONE point at a time (dynesty's
+    contract); a likelihood plateau ends the run instead of looping for ever."""
+    import warnings
+    from alabi_b200.nested import BatchedNestedSampler, HostWalker, resample_equal, compute_weights
     sig = 0.1
     like = lambda t: -0.5 * np.sum(((np.atleast_2d(t) - 0.5) / sig) ** 2, axis=1)
-    s = BatchedNestedSampler(like, lambda u: u, 2, nlive=300, walks=20, rstate=1)
-    r = s.run_nested(dlogz=0.01)
     want = np.log(2 * np.pi * sig ** 2)
+    calls = {"n": 0}
+
+    def transform(u):                     # indexes DIMENSIONS: wrong if it were handed a batch
+        assert np.ndim(u) == 1 and len(u) == 2
+        calls["n"] += 1
+        return np.array([u[0], u[1]])
+    s = BatchedNestedSampler(HostWalker(like, transform, 2, rng=np.random.default_rng(1)), 2, nlive=300, walks=20, rstate=1)
+    r = s.run_nested(dlogz=0.01)
+    assert calls["n"] > 300
     assert abs(r.logz[-1] - want) < 5 * r.logzerr[-1] + 0.1, (r.logz[-1], want, r.logzerr[-1])
     eq = resample_equal(r.samples, np.exp(r.logwt - r.logz[-1]), np.random.default_rng(0))
     assert abs(eq[:, 0].mean() - 0.5) < 0.02 and abs(eq[:, 1].std() - sig) < 0.02
-    assert r.samples.shape[1] == 2 and len(r.logwt) == len(r.samples) == len(r.logz)
+    assert r.samples.shape[1] == 2 and len(r.logwt) == len(r.samples) == len(r.logz) == len(r.logzerr)
+    assert np.all(np.diff(r.logl) >= 0) and r.samples_n[0] == 300 and r.samples_n[-1] == 1
+    # dynamic: baseline + posterior-weighted batches until the requested effective sample size
+    from functools import partial
+    from alabi_b200 import utility as ut
+    pt = partial(ut.prior_transform_uniform, bounds=np.array([(0.0, 1.0), (0.0, 1.0)]))
+    s2 = BatchedNestedSampler(HostWalker(like, pt, 2, rng=np.random.default_rng(2)), 2, nlive=150, walks=20, rstate=3)
+    r2 = s2.run_dynamic(dlogz_init=0.5, n_effective=2500, pfrac=1.0)
+    assert r2.nbatch >= 1 and r2.n_effective >= 2500
+    assert abs(r2.logz[-1] - want) < 5 * r2.logzerr[-1] + 0.15, (r2.logz[-1], want, r2.logzerr[-1])
+    eq2 = resample_equal(r2.samples, np.exp(r2.logwt - r2.logz[-1]), np.random.default_rng(0))
+    assert abs(eq2[:, 0].mean() - 0.5) < 0.02 and abs(eq2[:, 1].std() - sig) < 0.02
+    assert r2.samples_n.max() > 150                      # batches add live points where the posterior mass is
+    # merged-run weights: a static run split into its births / deaths reproduces the textbook volumes
+    w = compute_weights(r.logl, r.birth_logl)
+    it = r.niter
+    np.testing.assert_allclose(w["logvol"][:it], np.arange(1, it + 1) * np.log(300.0 / 301.0), rtol=1e-12)
+    # plateau: nothing above the constraint can ever be found
+    flat = lambda t: np.minimum(-np.sum((np.atleast_2d(t) - 0.5) ** 2, axis=1), -0.01)
+    s3 = BatchedNestedSampler(HostWalker(flat, pt, 2, rng=np.random.default_rng(4)), 2, nlive=60, walks=5, rstate=5,
+                              max_failed_rounds=3)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        r3 = s3.run_nested(dlogz=1e-9)
+    assert any("plateau" in str(x.message) for x in rec) and np.isfinite(r3.logz[-1])
+
+
+def test_batch_pool_serves_dynesty_style_callers():
+    """The pool handed to real dynesty: mapping the likelihood wrapper over the queue is ONE batched
+    call; anything else is mapped serially."""
+    from alabi_b200.nested import BatchLikelihood, BatchPool
+    seen = []
+
+    def batch(pts):
+        seen.append(len(pts))
+        return -np.sum(np.asarray(pts) ** 2, axis=1)
+    like = BatchLikelihood(batch)
+
+    class Wrapper:                      # dynesty's _function_wrapper: .func, .args, .kwargs, __call__
+        def __init__(self, func):
+            self.func, self.args, self.kwargs = func, [], {}
+
+        def __call__(self, x):
+            return self.func(x, *self.args, **self.kwargs)
+    pool = BatchPool(like, size=8)
+    pts = [np.array([0.1 * i, -0.2 * i]) for i in range(8)]
+    out = pool.map(Wrapper(like), pts)
+    assert seen == [8] and out == [like(p) for p in pts] and all(isinstance(v, float) for v in out)
+    assert pool.map(like, pts[:3]) == out[:3]
+    assert pool.map(lambda x: float(x[0]), pts[:2]) == [0.0, 0.1] and pool.size == 8
 
 
 def _free_port():
