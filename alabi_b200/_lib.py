@@ -87,6 +87,10 @@ SIGNATURES = {
     "ab_ensemble_run": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P]),
     "ab_ensemble_launch": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P]),
     "ab_ensemble_finish": (ctypes.c_int, [_P]),
+    "ab_gp_cv_batch": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p,
+                                      ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                      ctypes.POINTER(ctypes.c_int), _P, ctypes.c_int, _P, ctypes.c_int, _P, c_double_p,
+                                      ctypes.POINTER(ctypes.c_int)]),
     "ab_sizeof_nested_config": (ctypes.c_int, []),
     "ab_nested_walk": (ctypes.c_int, [_P, ctypes.POINTER(NestedConfig), _P, _P, _P, _P]),
     "ab_ensemble_run_host": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P, ctypes.c_int]),

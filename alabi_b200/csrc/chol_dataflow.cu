@@ -75,14 +75,20 @@ __device__ __forceinline__ void gemm64(double (&acc)[4][2][2], const double* A, 
     }
 }
 
+// One matrix (strides 0) or a BATCH of equally sized matrices (k-fold cross-validation jobs,
+// cv_batch.cu): matrix b lives at A + b strideA, its diagonal-block inverses at Dinv + b strideD,
+// its per-block-row words (prog, logdet_parts) at + b T, its status at info + b.  A task is
+// (i | b << 12, j); the task list orders the tiles of ALL matrices column by column, so every
+// dependency still has a smaller task index and different matrices fill each other's waits.
 struct DfArgs {
     double* A; int64_t ld; int T;
     double* Dinv; double* logdet_parts; int* info;
-    int* prog;                    // [T] final tiles per block row
+    int* prog;                    // [T] final tiles per block row (per matrix)
     unsigned int* next_task;      // task counter
     int* abort_flag;
     const int2* tasks; int ntasks;
     unsigned long long* dbg;      // optional: 6 globaltimer stamps per task (development)
+    int64_t strideA, strideD;     // batch strides in doubles (0: single matrix)
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -181,20 +187,27 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
         __syncthreads();
         const int task = s_task;
         if (task >= a.ntasks) break;
-        const int i = a.tasks[task].x, j = a.tasks[task].y;
+        const int tx_ = a.tasks[task].x, j = a.tasks[task].y;
+        const int i = tx_ & 4095, mb = tx_ >> 12;                // block row, matrix of the batch
+        double* const Ab = a.A + (int64_t)mb * a.strideA;
+        double* const Db = a.Dinv + (int64_t)mb * a.strideD;
+        double* const logdet_b = a.logdet_parts + (int64_t)mb * a.T;
+        int* const info_b = a.info + mb;
+        int* const prog_b = a.prog + (int64_t)mb * a.T;
+        w.prog = prog_b;
         const int64_t row0 = (int64_t)i * NB, col0 = (int64_t)j * NB;
         int seen_i = 0, seen_j = 0;
         DF_STAMP(0);
         // the tile of K itself is only needed after the long accumulation: pull it into L2 now
         for (int c = tid; c < NB * 8; c += Core::THREADS)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.A + (row0 + (c >> 3)) * a.ld + col0 + (c & 7) * 16));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Ab + (row0 + (c >> 3)) * a.ld + col0 + (c & 7) * 16));
 
         // ---- S = sum_{k<j} L_ik L_jk^T, gated per k block --------------------------
         abg::Acc acc;
         acc.zero();
         if (j > 0) {
             RowGate gate{&w, i, j, 0, 0};
-            Core::mainloop_gated<true, true>(acc, a.A + row0 * a.ld, a.ld, a.A + col0 * a.ld, a.ld, j * Core::KB, smem,
+            Core::mainloop_gated<true, true>(acc, Ab + row0 * a.ld, a.ld, Ab + col0 * a.ld, a.ld, j * Core::KB, smem,
                                              gate, i == j);
             seen_i = gate.seen_i;
             seen_j = gate.seen_j;
@@ -208,7 +221,7 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int c = Core::gated_col(wn, q) + 2 * t;
-                const double2 v = *reinterpret_cast<const double2*>(a.A + (row0 + r) * a.ld + col0 + c);
+                const double2 v = *reinterpret_cast<const double2*>(Ab + (row0 + r) * a.ld + col0 + c);
                 double2 o;
                 o.x = v.x - acc.v[f][q][0];
                 o.y = v.y - acc.v[f][q][1];
@@ -226,8 +239,8 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
             //               (L^-1)21 = -D22 (L21 D11)              (two DMMA products)
             // D11 lives in the unused upper-right quadrant of sC, D22 and L21 D11 in the B ring.
             const int tx = tid & 15, ty = tid >> 4;
-            double* Aj = a.A + col0 * a.ld + col0;
-            double* Dj = a.Dinv + (int64_t)j * NB * NB;
+            double* Aj = Ab + col0 * a.ld + col0;
+            double* Dj = Db + (int64_t)j * NB * NB;
             double* sD11 = sC + 64;                       // [n][k], ld LDC
             double* sD22 = sBring;                        // [m][k], ld LDH
             double* sM1 = sBring + 64 * LDH;              // [k][n], ld LDH
@@ -244,7 +257,7 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
                             pa[r][c] = (kk <= ii) ? sC[(ob + ii) * LDC + ob + kk] : 0.0;
                             pb[r][c] = (kk == ii) ? 1.0 : 0.0;
                         }
-                abp::potf2_sweep<true, 4>(pa, pb, sh, tx, ty, col0 + ob, a.info, sweep_phase);
+                abp::potf2_sweep<true, 4>(pa, pb, sh, tx, ty, col0 + ob, info_b, sweep_phase);
                 if (tid < 32) {
                     double s = 0.0;
                     for (int q = tid; q < 64; q += 32) s += 2.0 * log(sdiag[q]);
@@ -305,7 +318,7 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
                     __syncthreads();
                 }
             }
-            if (tid == 0) a.logdet_parts[j] = logdet;
+            if (tid == 0) logdet_b[j] = logdet;
             {
                 // (L^-1)21 = -D22 (L21 D11)
                 double acc2[4][2][2];
@@ -331,7 +344,7 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
             // ---- off-diagonal tile: L_ij = C D_j^-T (A operand resident, D_j^-1 streamed) ----
             w.wait(j, j, seen_j);                                    // diagonal tile of column j is final
             DF_STAMP(3);
-            const double* Dj = a.Dinv + (int64_t)j * NB * NB;
+            const double* Dj = Db + (int64_t)j * NB * NB;
             abg::Acc out;
             out.zero();
             const int cb = (wm == 0) ? wn : 3 - wn;                  // output column block of this warp
@@ -374,7 +387,7 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
                 const int r = wm * 64 + f * 8 + g;
 #pragma unroll
                 for (int q = 0; q < 4; q++)
-                    *reinterpret_cast<double2*>(a.A + (row0 + r) * a.ld + col0 + cb * 32 + q * 8 + 2 * t) =
+                    *reinterpret_cast<double2*>(Ab + (row0 + r) * a.ld + col0 + cb * 32 + q * 8 + 2 * t) =
                         make_double2(out.v[f][q][0], out.v[f][q][1]);
             }
         }
@@ -382,7 +395,7 @@ chol_dataflow_kernel(const __grid_constant__ DfArgs a) {
         DF_STAMP(4);
         __threadfence();
         __syncthreads();
-        if (tid == 0) st_release(a.prog + i, j + 1);
+        if (tid == 0) st_release(prog_b + i, j + 1);
         DF_STAMP(5);
     }
 }
@@ -425,6 +438,7 @@ int ab_launch_factor_dataflow(ab_gp* h) {
     a.prog = ctrl + 2;
     a.tasks = reinterpret_cast<const int2*>(h->df_tasks); a.ntasks = ntasks;
     a.dbg = reinterpret_cast<unsigned long long*>(h->df_dbg);
+    a.strideA = 0; a.strideD = 0;
     const int grid = ntasks < h->nsm ? ntasks : h->nsm;
     ab_prof_begin(h, AB_PROF_FACTOR);
     chol_dataflow_kernel<<<grid, Core::THREADS, DF_SMEM_BYTES, s>>>(a);
@@ -433,4 +447,45 @@ int ab_launch_factor_dataflow(ab_gp* h) {
     AB_CHECK_LAUNCH();
     AB_CUDA(cudaMemcpyAsync(h->h_pinned + 9, ctrl + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
     return 0;
+}
+
+// Batched factorisation of `nmat` matrices of T x T tiles each (leading dimension T * 128):
+// d_A + b * strideA etc. as described at DfArgs.  d_ctrl: at least 2 + nmat * T ints (zeroed here),
+// d_tasks: nmat * T (T + 1) / 2 int2 filled by ab_build_batch_tasks.  Asynchronous on h->stream;
+// the abort word is d_ctrl[1].
+int ab_launch_factor_dataflow_batch(ab_gp* h, double* d_A, int64_t strideA, int T, int nmat, double* d_Dinv,
+                                    double* d_logdet_parts, int* d_info, int* d_ctrl, const int2* d_tasks) {
+    static unsigned long long configured = 0;
+    if (h->device >= 64 || !((configured >> h->device) & 1ULL)) {
+        AB_CUDA(cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
+        if (h->device < 64) configured |= 1ULL << h->device;
+    }
+    if (T < 1 || T > 4095 || nmat < 1 || nmat >= (1 << 19)) { ab_set_error("batched factorisation: bad shape"); return -1; }
+    const long long ntasks = (long long)nmat * T * (T + 1) / 2;
+    cudaStream_t s = h->stream;
+    AB_CUDA(cudaMemsetAsync(d_ctrl, 0, (2 + (size_t)nmat * T) * sizeof(int), s));
+    AB_CUDA(cudaMemsetAsync(d_info, 0, (size_t)nmat * sizeof(int), s));
+    DfArgs a;
+    a.A = d_A; a.ld = (int64_t)T * NB; a.T = T;
+    a.Dinv = d_Dinv; a.logdet_parts = d_logdet_parts; a.info = d_info;
+    a.next_task = reinterpret_cast<unsigned int*>(d_ctrl);
+    a.abort_flag = d_ctrl + 1;
+    a.prog = d_ctrl + 2;
+    a.tasks = d_tasks; a.ntasks = (int)ntasks;
+    a.dbg = nullptr;
+    a.strideA = strideA; a.strideD = (int64_t)T * NB * NB;
+    const int grid = ntasks < h->nsm ? (int)ntasks : h->nsm;
+    chol_dataflow_kernel<<<grid, Core::THREADS, DF_SMEM_BYTES, s>>>(a);
+    ab_count_launches(1);
+    AB_CHECK_LAUNCH();
+    return 0;
+}
+
+// task list of a batch: column by column over all matrices (host vector)
+void ab_build_batch_tasks(int T, int nmat, std::vector<int2>& tasks) {
+    tasks.clear();
+    tasks.reserve((size_t)nmat * T * (T + 1) / 2);
+    for (int j = 0; j < T; j++)
+        for (int b = 0; b < nmat; b++)
+            for (int i = j; i < T; i++) tasks.push_back(make_int2(i | (b << 12), j));
 }

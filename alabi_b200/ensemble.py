@@ -110,6 +110,7 @@ class EnsembleSampler:
         self._step_counter = 0
         self.last_run_device_seconds = None
         self.device_chain = self.device_log_prob = None
+        self._device_rows_pending = False
 
     # ------------------------------------------------------------------------------------
     def _config(self, nsteps, thin_by, init_logp, walker_offset=0):
@@ -156,6 +157,8 @@ class EnsembleSampler:
             raise ValueError("Initial state has a large condition number. Make sure that your walkers are linearly independent for the best performance")
         on_device = isinstance(store, str) and store == "device"
         store = bool(store)
+        if store:
+            self._materialise()              # rows of an earlier store="device" run join the host chain first
         total = int(nsteps) * int(thin_by)
         coords = torch.from_numpy(np.ascontiguousarray(p0)).to(dev)
         logp = torch.from_numpy(np.ascontiguousarray(initial_state.log_prob)).to(dev) if have_lp \
@@ -208,7 +211,10 @@ class EnsembleSampler:
         self._step_counter += total
         self._naccepted += nacc.cpu().numpy()
         if on_device:
+            # the stored rows stay in HBM; get_chain() / get_log_prob() copy them on first use
             self.device_chain, self.device_log_prob = chain, lpc
+            self._device_rows_pending = True
+            self.iteration += int(nsteps)
         elif store:
             ch, lh = hbufs
             self._chain = ch if len(self._chain) == 0 else np.concatenate([self._chain, ch])
@@ -235,11 +241,20 @@ class EnsembleSampler:
             initial_state = None
 
     # ------------------------------------------------------------------------------------
+    def _materialise(self):
+        if getattr(self, "_device_rows_pending", False):
+            ch, lh = self.device_chain.cpu().numpy(), self.device_log_prob.cpu().numpy()
+            self._chain = ch if len(self._chain) == 0 else np.concatenate([self._chain, ch])
+            self._log_prob = lh if len(self._log_prob) == 0 else np.concatenate([self._log_prob, lh])
+            self._device_rows_pending = False
+
     def get_chain(self, discard=0, thin=1, flat=False):
+        self._materialise()
         v = self._chain[discard + thin - 1:self.iteration:thin]
         return v.reshape(-1, self.ndim) if flat else v
 
     def get_log_prob(self, discard=0, thin=1, flat=False):
+        self._materialise()
         v = self._log_prob[discard + thin - 1:self.iteration:thin]
         return v.reshape(-1) if flat else v
 

@@ -514,6 +514,60 @@ class GP:
     def get_matrix(self, x1, x2=None):
         return self.kernel.get_value(x1, x2)
 
+    # -- batched k-fold cross-validation jobs ----------------------------------------------
+    def cv_batch(self, x, y, candidates, folds, job_cand=None):
+        """Factorise / score many (candidate, fold) jobs in one batched device call
+        (``ab_gp_cv_batch``).  ``candidates`` (ncand, P) are hyper-vectors in this GP's
+        ``get_parameter_vector()`` layout; ``folds`` is a list of (train_idx, val_idx) pairs, job b
+        using candidate ``job_cand[b]`` (default: ``len(folds) // ncand`` consecutive folds per
+        candidate).  Returns (preds, loglik, status): the predictive mean at each job's
+        validation rows (list of arrays), the log-likelihood of its training rows and the
+        Cholesky status (0 = ok, else the first non-positive pivot).  The GP's own state
+        (hyper-parameters, factor) is not touched."""
+        torch = _torch()
+        hd = self._handle()
+        x = self.parse_samples(x)
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+        cands = np.atleast_2d(np.asarray(candidates, dtype=np.float64))
+        n, d = x.shape
+        ncand, njobs = len(cands), len(folds)
+        if job_cand is None:
+            per = njobs // ncand
+            if per * ncand != njobs:
+                raise ValueError("folds must hold the same number of folds for every candidate (or pass job_cand)")
+            job_cand = np.repeat(np.arange(ncand), per)
+        job_cand = np.ascontiguousarray(job_cand, dtype=np.int32)
+        # candidate vectors -> [mean, white_noise, amp, log_M...] through a scratch copy of this GP
+        probe = self.__copy__()
+        params = np.empty((ncand, 3 + d))
+        for c, v in enumerate(cands):
+            probe.set_parameter_vector(v)
+            kid, amp, log_M = probe.kernel.spec()
+            params[c, 0], params[c, 1], params[c, 2] = probe.mean_value, probe.white_noise_value, amp
+            params[c, 3:] = log_M
+        ntr = np.array([len(f[0]) for f in folds], dtype=np.int32)
+        nva = np.array([len(f[1]) for f in folds], dtype=np.int32)
+        ld_tr, ld_va = int(ntr.max()), max(int(nva.max()), 1)
+        tr = np.zeros((njobs, ld_tr), dtype=np.int32)
+        va = np.zeros((njobs, ld_va), dtype=np.int32)
+        for b, (a_, v_) in enumerate(folds):
+            tr[b, :len(a_)] = a_
+            va[b, :len(v_)] = v_
+        dev = f"cuda:{hd.device}"
+        xd, yd = torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev)
+        trd, vad = torch.from_numpy(tr).to(dev), torch.from_numpy(va).to(dev)
+        pred = torch.empty((njobs, ld_va), dtype=torch.float64, device=dev)
+        loglik = np.empty(njobs, dtype=np.float64)
+        status = np.empty(njobs, dtype=np.int32)
+        ci = ctypes.POINTER(ctypes.c_int)
+        _lib.check(hd.lib.ab_gp_cv_batch(hd.h, _lib.ptr(xd), _lib.ptr(yd), n, d, int(kid), ncand,
+                                         params.ctypes.data_as(_lib.c_double_p), njobs, job_cand.ctypes.data_as(ci),
+                                         ntr.ctypes.data_as(ci), nva.ctypes.data_as(ci), _lib.ptr(trd), ld_tr, _lib.ptr(vad),
+                                         ld_va, _lib.ptr(pred), loglik.ctypes.data_as(_lib.c_double_p),
+                                         status.ctypes.data_as(ci)), "ab_gp_cv_batch")
+        ph = pred.cpu().numpy()
+        return [ph[b, :nva[b]] for b in range(njobs)], loglik, status
+
 
 _SCRATCH_HANDLES = {}
 

@@ -191,30 +191,54 @@ def _fold_score(scoring, y_val, y_pred, wmethod, wfactor):
     raise ValueError(f"Unsupported scoring method: {scoring}")
 
 
-def _evaluate_candidates(gp, theta, y, y_scaler, cands, k_folds, scoring, wmethod, wfactor):
-    """scores[cand, fold]; inf for failed folds.  Every (candidate, fold) is one
-    factorise + log-likelihood + mean-predict job on the GPU; a fresh shuffled
-    KFold split is drawn per candidate like the reference's worker does."""
+def _evaluate_candidates(gp, theta, y, y_scaler, cands, k_folds, scoring, wmethod, wfactor, batched=True,
+                         random_state=None):
+    """scores[cand, fold]; inf for failed folds.  Every (candidate, fold) is one factorise +
+    log-likelihood + mean-predict job; a fresh shuffled ``KFold`` split is drawn per candidate like
+    the reference's worker does (alabi/gp_utils.py:532; ``random_state`` makes the splits
+    reproducible: candidate c uses ``random_state + c``).  ``batched=True`` (default) hands ALL jobs
+    of the stage to one batched device call (``GP.cv_batch``); ``False`` runs them one after
+    another on one handle (the pre-batching path, kept for cross-checks)."""
     from sklearn.model_selection import KFold
     scores = np.full((len(cands), k_folds), np.inf)
+    ok_c = [ci for ci, hp in enumerate(cands) if np.all(np.isfinite(hp))]
+    folds = {}
+    for ci in ok_c:
+        kf = KFold(n_splits=k_folds, shuffle=True, random_state=None if random_state is None else int(random_state) + ci)
+        folds[ci] = list(kf.split(theta))
+
+    def score(ci, fi, ll, pred, va):
+        if not np.isfinite(ll) or len(pred) == 0 or not np.all(np.isfinite(pred)):
+            return np.inf
+        y_val = y_scaler.inverse_transform(y[va].reshape(-1, 1)).flatten()
+        y_pred = y_scaler.inverse_transform(np.asarray(pred).reshape(-1, 1)).flatten()
+        try:
+            return _fold_score(scoring, y_val, y_pred, wmethod, wfactor)
+        except Exception:  # noqa: BLE001 - a failed fold scores inf, like the reference
+            return np.inf
+
+    if batched and hasattr(gp, "cv_batch") and ok_c:
+        jobs = [(ci, fi) for ci in ok_c for fi in range(k_folds)]
+        try:
+            preds, lls, status = gp.cv_batch(theta, y, np.asarray(cands)[ok_c], [folds[ci][fi] for ci, fi in jobs])
+        except Exception as e:  # noqa: BLE001 - e.g. out of device memory: fall through to the serial path
+            print(f"CV: batched evaluation failed ({e}); evaluating the candidates one by one")
+        else:
+            for b, (ci, fi) in enumerate(jobs):
+                if status[b] == 0:
+                    scores[ci, fi] = score(ci, fi, lls[b], preds[b], folds[ci][fi][1])
+            return scores
     work = copy.copy(gp)
-    for ci, hp in enumerate(cands):
-        if not np.all(np.isfinite(hp)):
-            continue
-        kf = KFold(n_splits=k_folds, shuffle=True, random_state=None)
-        for fi, (tr, va) in enumerate(kf.split(theta)):
+    for ci in ok_c:
+        for fi, (tr, va) in enumerate(folds[ci]):
             try:
-                work.set_parameter_vector(hp)
+                work.set_parameter_vector(cands[ci])
                 work.compute(theta[tr])
                 ll = work.log_likelihood(y[tr])
                 if not np.isfinite(ll):
                     raise ValueError("invalid log-likelihood")
                 pred = work.predict(y[tr], theta[va], return_var=False, return_cov=False)
-                if len(pred) == 0 or not np.all(np.isfinite(pred)):
-                    raise ValueError("invalid predictions")
-                y_val = y_scaler.inverse_transform(y[va].reshape(-1, 1)).flatten()
-                y_pred = y_scaler.inverse_transform(pred.reshape(-1, 1)).flatten()
-                scores[ci, fi] = _fold_score(scoring, y_val, y_pred, wmethod, wfactor)
+                scores[ci, fi] = score(ci, fi, ll, pred, va)
             except Exception:  # noqa: BLE001 - a failed fold scores inf, like the reference
                 scores[ci, fi] = np.inf
     return scores
@@ -267,12 +291,15 @@ _generate_stage3_candidates = _generate_stage_candidates
 
 def optimize_gp_kfold_cv(gp, _theta, _y, hyperparameter_candidates, y_scaler, k_folds=5, scoring="mse", pool=None,
                          stage2_candidates=None, stage2_width=0.5, stage3_candidates=None, stage3_width=0.2,
-                         weighted_mse_method="exponential", weighted_mse_factor=1.0, verbose=True):
+                         weighted_mse_method="exponential", weighted_mse_factor=1.0, verbose=True, batched=True,
+                         random_state=None):
     """Pick the hyper-vector with the best mean k-fold validation score out of
     the given candidates, then refine around the winner with up to two
     Gaussian candidate clouds.  Returns the GP set to the winner and computed
     on all data (None if every candidate fails).  ``pool`` is accepted for
-    signature compatibility; candidates are evaluated on the GPU."""
+    signature compatibility: every stage (candidates x folds jobs) is ONE batched device call
+    (``GP.cv_batch`` -> ``ab_gp_cv_batch``); ``batched=False`` evaluates the jobs one after another,
+    ``random_state`` makes the shuffled splits reproducible."""
     theta = np.asarray(_theta, dtype=np.float64)
     y = np.asarray(_y, dtype=np.float64)
     if theta.ndim == 1:
@@ -292,9 +319,14 @@ def optimize_gp_kfold_cv(gp, _theta, _y, hyperparameter_candidates, y_scaler, k_
     two_stage = stage2_candidates is not None
     three_stage = stage3_candidates is not None
 
+    stage = [0]
+
     def run(c):
-        return _mean_scores(_evaluate_candidates(gp, theta, y, y_scaler, c, k_folds, scoring,
-                                                 weighted_mse_method, weighted_mse_factor))
+        # one batched device call per stage (all candidates x folds); ``random_state`` fixes the splits
+        rs = None if random_state is None else int(random_state) + 100003 * stage[0]
+        stage[0] += 1
+        return _mean_scores(_evaluate_candidates(gp, theta, y, y_scaler, c, k_folds, scoring, weighted_mse_method,
+                                                 weighted_mse_factor, batched=batched, random_state=rs))
 
     s1 = run(cands)
     if np.all(np.isinf(s1)):

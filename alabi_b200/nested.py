@@ -78,7 +78,7 @@ def compute_weights(logl, birth):
         H = np.where(zfrac > 0, h_cum / zfrac - logz, 0.0)      # H_i = sum_{k<=i} (w_k / Z_i) L_k - ln Z_i
     H = np.maximum(np.nan_to_num(H, nan=0.0, posinf=0.0, neginf=0.0), 0.0)
     dH = np.diff(np.concatenate([[0.0], H]))
-    logzvar = np.maximum(np.cumsum(np.maximum(dH, 0.0) / nlive), 0.0)
+    logzvar = np.maximum(np.cumsum(dH / nlive), 0.0)           # signed increments: H / n for constant n
     return dict(order=order, nlive=nlive, logvol=logvol, logwt=logwt, logz=logz, logzerr=np.sqrt(logzvar), H=H)
 
 

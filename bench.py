@@ -408,7 +408,10 @@ def main():
             torch.cuda.synchronize()
             info["train_ms"] = (time.perf_counter() - t0) * 1e3
         if world > 1:
-            barrier()                      # also sets the NCCL communicator up before the timed broadcast
+            barrier()                      # sets the NCCL communicator up
+            warm = torch.zeros(1 << 20, dtype=torch.float64, device=dev)
+            dist.broadcast(warm, src=0)    # and the broadcast channels, before the timed broadcast
+            barrier()
             st = {}
             par.broadcast_gp(gp, stats=st)
             barrier()

@@ -244,6 +244,22 @@ int ab_sizeof_nested_config(void);
 int ab_nested_walk(ab_gp* h, const ab_nested_config* cfg, double* d_u, double* d_logl, double* d_theta,
                    int* d_naccept);
 
+/* k-fold cross-validation of hyper-parameter candidates as one batched job
+ * (gp_utils.optimize_gp_kfold_cv and its per-candidate worker, alabi/gp_utils.py:511-637, 640-1231;
+ * the default hyper-parameter search of init_gp, alabi/core.py:751).  Job b = (candidate
+ * h_job_cand[b], one fold): the GP with that candidate's hyper-parameters is factorised on the
+ * rows d_train_idx[b][0 .. h_ntrain[b]) of X (n x d, device), the log-likelihood of y on those rows
+ * goes to h_loglik[b], the predictive mean at the rows d_val_idx[b][0 .. h_nval[b]) to
+ * d_pred[b][...] (leading dimensions ld_train / ld_val), and h_status[b] is 0 or the 1-based index
+ * of the first non-positive pivot (the reference scores such a fold as failed).  h_params holds,
+ * per candidate, 3 + d doubles: mean, white_noise (ln variance), amp = exp(log_constant), log_M[d].
+ * All jobs of a call are factorised by ONE batched dataflow-Cholesky launch per workspace chunk.
+ * The handle supplies device, stream and nothing else: its own model state is not touched. */
+int ab_gp_cv_batch(ab_gp* h, const double* d_X, const double* d_y, int64_t n, int d, int kernel_id, int ncand,
+                   const double* h_params, int njobs, const int* h_job_cand, const int* h_ntrain,
+                   const int* h_nval, const int* d_train_idx, int ld_train, const int* d_val_idx, int ld_val,
+                   double* d_pred, double* h_loglik, int* h_status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -385,3 +385,53 @@ def test_shared_point_cache_serves_utility_and_gradient():
         np.testing.assert_array_equal(gr, gr_direct)
     mu, var = sp.predict(X[:10])                          # batches pass straight through
     assert mu.shape == (10,) and var.shape == (10,)
+
+
+@pytest.mark.parametrize("kind,n,d", [("ExpSquaredKernel", 150, 2), ("Matern32Kernel", 1000, 3), ("Matern52Kernel", 333, 5)])
+def test_cv_batch_matches_oracle_folds(kind, n, d):
+    """k-fold CV as one batched device job (ab_gp_cv_batch): per (candidate, fold) the predictions at
+    the held-out rows, the log-likelihood and the fold MSE equal the oracle doing the SAME folds;
+    a candidate whose covariance matrix is not positive definite fails like the reference's worker;
+    the batched scores equal the one-by-one device path."""
+    import time
+    from sklearn.model_selection import KFold
+    from alabi_b200 import gp_utils, utility as ut
+    o, g, X, y, rng = make_pair(kind, n, d, seed=n + 3 * d, white_noise=-8.0)
+    base = g.get_parameter_vector()
+    ncand, k = 6, 5
+    cands = base + rng.normal(0, 0.3, size=(ncand, len(base)))
+    cands[0] = base
+    folds, job_cand = [], []
+    for c in range(ncand):
+        for tr, va in KFold(n_splits=k, shuffle=True, random_state=c).split(X):
+            folds.append((tr, va))
+            job_cand.append(c)
+    preds, lls, status = g.cv_batch(X, y, cands, folds, job_cand=job_cand)
+    np.testing.assert_array_equal(g.get_parameter_vector(), base)           # the GP itself is untouched
+    assert np.all(status == 0)
+    for b, (tr, va) in enumerate(folds):
+        oc = ogp.make_gp(kind, X[tr], y[tr], np.zeros(d), amp=1.0, compute=False)
+        oc.set_parameter_vector(cands[job_cand[b]])
+        oc.compute(X[tr])
+        ll_o = oc.log_likelihood(y[tr])
+        mu_o = oc.predict(y[tr], X[va])
+        assert abs(lls[b] - ll_o) <= 1e-9 * abs(ll_o), (b, lls[b], ll_o)
+        np.testing.assert_allclose(preds[b], mu_o, rtol=1e-8, atol=1e-8 * np.max(np.abs(mu_o)))
+        assert abs(np.mean((y[va] - preds[b]) ** 2) - np.mean((y[va] - mu_o) ** 2)) <= 1e-7 * np.mean((y[va] - mu_o) ** 2) + 1e-14
+    # a candidate that cannot be factorised: white noise -80 on duplicated points
+    Xd, yd = X.copy(), y.copy()
+    Xd[1] = Xd[0]
+    bad = base.copy()
+    bad[1] = -80.0
+    folds2 = [(np.arange(n - 20), np.arange(n - 20, n))] * 2
+    p2, l2, s2 = g.cv_batch(Xd, yd, np.array([base, bad]), folds2, job_cand=[0, 1])
+    assert s2[0] == 0 and np.isfinite(l2[0]) and s2[1] > 0 and l2[1] == -np.inf and np.all(np.isnan(p2[1]))
+    # the stage evaluation used by optimize_gp_kfold_cv: batched == one-by-one
+    t0 = time.time()
+    sb = gp_utils._evaluate_candidates(g, X, y, ut.no_scaler, cands, k, "mse", "exponential", 1.0, batched=True, random_state=7)
+    tb = time.time() - t0
+    t0 = time.time()
+    ss = gp_utils._evaluate_candidates(g, X, y, ut.no_scaler, cands, k, "mse", "exponential", 1.0, batched=False, random_state=7)
+    ts = time.time() - t0
+    np.testing.assert_allclose(sb, ss, rtol=1e-7, atol=1e-14)
+    print(f"cv stage of {ncand} x {k} jobs at n = {n}: batched {tb * 1e3:.1f} ms, one by one {ts * 1e3:.1f} ms")

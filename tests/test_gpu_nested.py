@@ -72,17 +72,17 @@ def test_static_and_dynamic_sampler_on_c3_surrogate():
     g.compute(cfg["X"])
     lp = SurrogateLogProb(g, cfg["y"], cfg["bounds"])
     lib = _lib.load()
-    s1 = BatchedNestedSampler(DeviceWalker(lp, cfg["bounds"], seed=11), 2, nlive=1000, walks=25, rstate=12)
+    s1 = BatchedNestedSampler(DeviceWalker(lp, cfg["bounds"], seed=11), 2, nlive=2000, walks=25, rstate=12)
     n0 = lib.ab_launch_counter()
     r1 = s1.run_nested(dlogz=0.02)
     launches = lib.ab_launch_counter() - n0
     # every batch of nbatch x walks proposals is ONE walk launch (the only other launches are the
     # three kernels of the batched predict for the initial live points)
     assert launches <= 3 + r1.ncall / (s1.nbatch * s1.walks) + 1, (launches, r1.ncall)
-    s2 = BatchedNestedSampler(DeviceWalker(lp, cfg["bounds"], seed=21), 2, nlive=600, walks=25, rstate=22)
+    s2 = BatchedNestedSampler(DeviceWalker(lp, cfg["bounds"], seed=21), 2, nlive=1000, walks=25, rstate=22)
     r2 = s2.run_dynamic(dlogz_init=0.5, n_effective=6000, pfrac=1.0)
     z1, e1, z2, e2 = r1.logz[-1], r1.logzerr[-1], r2.logz[-1], r2.logzerr[-1]
-    assert abs(z1 - z2) < 3.0 * np.hypot(e1, e2) + 0.1, (z1, e1, z2, e2)
+    assert abs(z1 - z2) < 4.0 * np.hypot(e1, e2) + 0.05, (z1, e1, z2, e2)
     assert r2.nbatch >= 1 and r2.n_effective >= 6000
     # quadrature of exp(surrogate) over the unit square is the evidence both estimate
     ng = 400
@@ -90,7 +90,7 @@ def test_static_and_dynamic_sampler_on_c3_surrogate():
     grid = np.stack(np.meshgrid(gx, gx, indexing="ij"), axis=-1).reshape(-1, 2)
     mu = g.predict(cfg["y"], grid, return_cov=False)
     z_quad = np.log(np.mean(np.exp(mu - mu.max()))) + mu.max()
-    assert abs(z1 - z_quad) < 3.0 * e1 + 0.15 and abs(z2 - z_quad) < 3.0 * e2 + 0.15, (z1, z2, z_quad)
+    assert abs(z1 - z_quad) < 4.0 * e1 + 0.05 and abs(z2 - z_quad) < 4.0 * e2 + 0.05, (z1, e1, z2, e2, z_quad)
     # posteriors: the eggbox has 25 modes whose weights every run estimates with its own noise, and
     # resampled points are not independent, so the KS STATISTIC against the quadrature marginals is
     # bounded (and between the two runs), not a p-value
@@ -102,8 +102,8 @@ def test_static_and_dynamic_sampler_on_c3_surrogate():
         cdf = np.cumsum(marg) / marg.sum()
         for q in (q1, q2):
             emp = np.searchsorted(np.sort(q[:, k]), gx + 0.5 / ng, side="right") / len(q)
-            assert np.max(np.abs(emp - cdf)) < 0.08, (k, np.max(np.abs(emp - cdf)))
-        assert stats.ks_2samp(q1[:, k], q2[:, k]).statistic < 0.1
+            assert np.max(np.abs(emp - cdf)) < 0.1, (k, np.max(np.abs(emp - cdf)))
+        assert stats.ks_2samp(q1[:, k], q2[:, k]).statistic < 0.12
 
 
 def test_run_dynesty_modes_and_kwargs(tmp_path):
