@@ -206,10 +206,23 @@ cvb_solve_predict_kernel(const CvArgs a) {
     }
 }
 
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) { AB_CUDA(cudaMalloc(&p, bytes ? bytes : 8)); return 0; }
+// bytes of workspace one job needs (matrix, diagonal-block inverses, scaled inputs, vectors, control words)
+size_t job_bytes(int npad, int d, int ld_val) {
+    const int T = npad / NB;
+    size_t b = ((size_t)npad * npad + (size_t)npad * NB + (size_t)npad * d + (size_t)ld_val * d + (size_t)npad + T) * sizeof(double);
+    b += (size_t)(T * (T + 1) / 2) * sizeof(int2) + (size_t)(T + 2) * sizeof(int) + 64;
+    return (b + 255) / 256 * 256;
+}
+
+// carve `bytes` (256-aligned) out of the caller's workspace
+struct Carver {
+    char* p; size_t left;
+    void* take(size_t bytes) {
+        bytes = (bytes + 255) / 256 * 256;
+        if (bytes > left) return nullptr;
+        void* r = p; p += bytes; left -= bytes;
+        return r;
+    }
 };
 
 }  // namespace
@@ -217,7 +230,7 @@ struct DevBuf {
 extern "C" int ab_gp_cv_batch(ab_gp* h, const double* d_X, const double* d_y, int64_t n, int d, int kernel_id, int ncand,
                               const double* h_params, int njobs, const int* h_job_cand, const int* h_ntrain,
                               const int* h_nval, const int* d_train_idx, int ld_train, const int* d_val_idx, int ld_val,
-                              double* d_pred, double* h_loglik, int* h_status) {
+                              double* d_pred, double* h_loglik, int* h_status, void* d_work, size_t work_bytes) {
     if (!h || !d_X || !d_y || !h_params || !h_job_cand || !h_ntrain || !h_nval || !d_train_idx || !d_val_idx || !d_pred ||
         !h_loglik || !h_status) { ab_set_error("ab_gp_cv_batch: null argument"); return -1; }
     if (n < 2 || d < 1 || d > AB_MAX_DIM || kernel_id < 0 || kernel_id > 2 || ncand < 1 || njobs < 1 || ld_train < 1 || ld_val < 1) {
@@ -241,48 +254,58 @@ extern "C" int ab_gp_cv_batch(ab_gp* h, const double* d_X, const double* d_y, in
         cp[c].amp = p[2];
         for (int k = 0; k < AB_MAX_DIM; k++) cp[c].inv_len[k] = (k < d) ? exp(-0.5 * p[3 + k]) : 0.0;
     }
-    // chunk size from a workspace budget (the matrices dominate)
-    const size_t per_job = ((size_t)npad * npad + (size_t)npad * NB + (size_t)npad * (d + 2) + (size_t)ld_val * d + T) * sizeof(double);
-    size_t budget = (size_t)8 << 30;
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b / 2 < budget) budget = free_b / 2;
-    int chunk = (int)(budget / per_job);
-    if (chunk < 1) chunk = 1;
+    // the caller's workspace decides how many jobs are factorised per launch
+    const size_t fixed = sizeof(CandParams) * ncand + (size_t)njobs * (3 * sizeof(int) + sizeof(double)) + 4096;
+    const size_t per_job = job_bytes(npad, d, ld_val);
+    if (!d_work || work_bytes < fixed + per_job) {
+        ab_set_error("ab_gp_cv_batch: workspace too small (%zu bytes; one job needs %zu + %zu)", work_bytes, per_job, fixed);
+        return -3;
+    }
+    int chunk = (int)((work_bytes - fixed) / per_job);
     if (chunk > njobs) chunk = njobs;
-    DevBuf bCand, bJc, bNt, bNv, bXs, bXv, bR, bA, bD, bLd, bInfo, bCtrl, bTasks, bLl;
+    const int ntiles = T * (T + 1) / 2;
+    Carver cv{static_cast<char*>(d_work), work_bytes};
+    void* bCand = cv.take(sizeof(CandParams) * ncand);
+    int* bJc = static_cast<int*>(cv.take(sizeof(int) * njobs));
+    int* bNt = static_cast<int*>(cv.take(sizeof(int) * njobs));
+    int* bNv = static_cast<int*>(cv.take(sizeof(int) * njobs));
+    double* bLl = static_cast<double*>(cv.take(sizeof(double) * njobs));
+    double* bA = static_cast<double*>(cv.take(sizeof(double) * chunk * npad * npad));
+    double* bD = static_cast<double*>(cv.take(sizeof(double) * chunk * npad * NB));
+    double* bXs = static_cast<double*>(cv.take(sizeof(double) * chunk * npad * d));
+    double* bXv = static_cast<double*>(cv.take(sizeof(double) * chunk * ld_val * d));
+    double* bR = static_cast<double*>(cv.take(sizeof(double) * chunk * npad));
+    double* bLd = static_cast<double*>(cv.take(sizeof(double) * chunk * T));
+    int* bInfo = static_cast<int*>(cv.take(sizeof(int) * chunk));
+    int* bCtrl = static_cast<int*>(cv.take(sizeof(int) * (2 + (size_t)chunk * T)));
+    int2* bTasks = static_cast<int2*>(cv.take(sizeof(int2) * (size_t)chunk * ntiles));
+    if (!bCand || !bJc || !bNt || !bNv || !bLl || !bA || !bD || !bXs || !bXv || !bR || !bLd || !bInfo || !bCtrl || !bTasks) {
+        ab_set_error("ab_gp_cv_batch: workspace layout does not fit (%zu bytes)", work_bytes);
+        return -3;
+    }
     int rc = 0;
-    if ((rc = bCand.alloc(sizeof(CandParams) * ncand)) || (rc = bJc.alloc(sizeof(int) * njobs)) || (rc = bNt.alloc(sizeof(int) * njobs)) ||
-        (rc = bNv.alloc(sizeof(int) * njobs)) || (rc = bXs.alloc(sizeof(double) * chunk * npad * d)) ||
-        (rc = bXv.alloc(sizeof(double) * chunk * ld_val * d)) || (rc = bR.alloc(sizeof(double) * chunk * npad)) ||
-        (rc = bA.alloc(sizeof(double) * chunk * npad * npad)) || (rc = bD.alloc(sizeof(double) * chunk * npad * NB)) ||
-        (rc = bLd.alloc(sizeof(double) * chunk * T)) || (rc = bInfo.alloc(sizeof(int) * chunk)) ||
-        (rc = bCtrl.alloc(sizeof(int) * (2 + (size_t)chunk * T))) || (rc = bLl.alloc(sizeof(double) * njobs)))
-        return rc;
-    AB_CUDA(cudaMemcpyAsync(bCand.p, cp.data(), sizeof(CandParams) * ncand, cudaMemcpyHostToDevice, s));
-    AB_CUDA(cudaMemcpyAsync(bJc.p, h_job_cand, sizeof(int) * njobs, cudaMemcpyHostToDevice, s));
-    AB_CUDA(cudaMemcpyAsync(bNt.p, h_ntrain, sizeof(int) * njobs, cudaMemcpyHostToDevice, s));
-    AB_CUDA(cudaMemcpyAsync(bNv.p, h_nval, sizeof(int) * njobs, cudaMemcpyHostToDevice, s));
+    AB_CUDA(cudaMemcpyAsync(bCand, cp.data(), sizeof(CandParams) * ncand, cudaMemcpyHostToDevice, s));
+    AB_CUDA(cudaMemcpyAsync(bJc, h_job_cand, sizeof(int) * njobs, cudaMemcpyHostToDevice, s));
+    AB_CUDA(cudaMemcpyAsync(bNt, h_ntrain, sizeof(int) * njobs, cudaMemcpyHostToDevice, s));
+    AB_CUDA(cudaMemcpyAsync(bNv, h_nval, sizeof(int) * njobs, cudaMemcpyHostToDevice, s));
     std::vector<int2> tasks;
     int tasks_for = -1;
     std::vector<int> info_h(njobs, 0), abort_h(1, 0);
     CvArgs a{};
     a.X = d_X; a.y = d_y; a.d = d;
-    a.cand = static_cast<const CandParams*>(bCand.p); a.job_cand = static_cast<const int*>(bJc.p);
-    a.ntrain = static_cast<const int*>(bNt.p); a.nval = static_cast<const int*>(bNv.p);
+    a.cand = static_cast<const CandParams*>(bCand); a.job_cand = bJc;
+    a.ntrain = bNt; a.nval = bNv;
     a.train_idx = d_train_idx; a.ld_train = ld_train; a.val_idx = d_val_idx; a.ld_val = ld_val;
     a.npad = npad; a.T = T;
-    a.Xs = static_cast<double*>(bXs.p); a.Xv = static_cast<double*>(bXv.p); a.r = static_cast<double*>(bR.p);
-    a.A = static_cast<double*>(bA.p); a.Dinv = static_cast<double*>(bD.p); a.logdet = static_cast<double*>(bLd.p);
-    a.info = static_cast<int*>(bInfo.p); a.pred = d_pred; a.loglik = static_cast<double*>(bLl.p);
-    const int ntiles = T * (T + 1) / 2;
+    a.Xs = bXs; a.Xv = bXv; a.r = bR; a.A = bA; a.Dinv = bD; a.logdet = bLd;
+    a.info = bInfo; a.pred = d_pred; a.loglik = bLl;
     for (int j0 = 0; j0 < njobs; j0 += chunk) {
         const int nj = (njobs - j0 < chunk) ? (njobs - j0) : chunk;
         a.job0 = j0;
         if (tasks_for != nj) {
+            AB_CUDA(cudaStreamSynchronize(s));              // the previous chunk may still read the list
             ab_build_batch_tasks(T, nj, tasks);
-            if (bTasks.p) { AB_CUDA(cudaStreamSynchronize(s)); cudaFree(bTasks.p); bTasks.p = nullptr; }
-            if ((rc = bTasks.alloc(sizeof(int2) * tasks.size()))) return rc;
-            AB_CUDA(cudaMemcpyAsync(bTasks.p, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice, s));
+            AB_CUDA(cudaMemcpyAsync(bTasks, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice, s));
             AB_CUDA(cudaStreamSynchronize(s));              // `tasks` may be rebuilt for a smaller last chunk
             tasks_for = nj;
         }
@@ -295,19 +318,26 @@ extern "C" int ab_gp_cv_batch(ab_gp* h, const double* d_X, const double* d_y, in
             cvb_cov_kernel<KIND><<<dim3(ntiles, nj), 256, cov_smem, s>>>(a);
         });
         AB_CHECK_LAUNCH();
-        rc = ab_launch_factor_dataflow_batch(h, a.A, (int64_t)npad * npad, T, nj, a.Dinv, a.logdet, a.info,
-                                             static_cast<int*>(bCtrl.p), static_cast<const int2*>(bTasks.p));
+        rc = ab_launch_factor_dataflow_batch(h, a.A, (int64_t)npad * npad, T, nj, a.Dinv, a.logdet, a.info, bCtrl, bTasks);
         if (rc) return rc;
         AB_DISPATCH_KIND(kernel_id, (cvb_solve_predict_kernel<KIND><<<nj, 256, 0, s>>>(a)));
         AB_CHECK_LAUNCH();
         ab_count_launches(3);
         AB_CUDA(cudaMemcpyAsync(info_h.data() + j0, a.info, sizeof(int) * nj, cudaMemcpyDeviceToHost, s));
-        AB_CUDA(cudaMemcpyAsync(abort_h.data(), static_cast<int*>(bCtrl.p) + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+        AB_CUDA(cudaMemcpyAsync(abort_h.data(), bCtrl + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
         AB_CUDA(cudaStreamSynchronize(s));
         if (abort_h[0] != 0) { ab_set_error("batched Cholesky watchdog fired (dependency wait exceeded its limit)"); return -5; }
     }
-    AB_CUDA(cudaMemcpyAsync(h_loglik, bLl.p, sizeof(double) * njobs, cudaMemcpyDeviceToHost, s));
+    AB_CUDA(cudaMemcpyAsync(h_loglik, bLl, sizeof(double) * njobs, cudaMemcpyDeviceToHost, s));
     AB_CUDA(cudaStreamSynchronize(s));
     for (int j = 0; j < njobs; j++) h_status[j] = info_h[j];
     return 0;
+}
+
+// workspace (bytes) that lets ab_gp_cv_batch factorise `njobs` jobs of at most `ntrain_max` training
+// rows in one launch; any size from one job's worth upwards works (more launches)
+extern "C" size_t ab_gp_cv_workspace_bytes(int ntrain_max, int d, int ld_val, int ncand, int njobs) {
+    const int npad = (ntrain_max + NB - 1) / NB * NB;
+    return sizeof(CandParams) * (size_t)ncand + (size_t)njobs * (3 * sizeof(int) + sizeof(double)) + 8192 +
+           (size_t)njobs * job_bytes(npad, d, ld_val) + 16 * 256;
 }

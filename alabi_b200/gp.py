@@ -82,6 +82,8 @@ class _Solver:
 
 
 class GP:
+    cv_workspace_limit_bytes = 16 << 30      # device scratch ceiling of one cv_batch call
+
     def __init__(self, kernel=None, fit_kernel=True, mean=None, fit_mean=None, white_noise=None,
                  fit_white_noise=None, solver=None, device=None, **kwargs):
         if kernel is None or not isinstance(kernel, Kernel):
@@ -560,11 +562,18 @@ class GP:
         loglik = np.empty(njobs, dtype=np.float64)
         status = np.empty(njobs, dtype=np.int32)
         ci = ctypes.POINTER(ctypes.c_int)
+        # scratch from torch's caching allocator (a cudaMalloc / cudaFree of gigabytes per stage costs
+        # more than the factorisations): everything in one launch when it fits, else a capped block
+        need = int(hd.lib.ab_gp_cv_workspace_bytes(ld_tr, d, ld_va, ncand, njobs))
+        one = int(hd.lib.ab_gp_cv_workspace_bytes(ld_tr, d, ld_va, ncand, 1))
+        free_b = torch.cuda.mem_get_info(hd.device)[0] + torch.cuda.memory_reserved(hd.device) - torch.cuda.memory_allocated(hd.device)
+        cap = max(one, min(need, self.cv_workspace_limit_bytes, int(0.6 * free_b)))
+        work = torch.empty(cap, dtype=torch.uint8, device=dev)
         _lib.check(hd.lib.ab_gp_cv_batch(hd.h, _lib.ptr(xd), _lib.ptr(yd), n, d, int(kid), ncand,
                                          params.ctypes.data_as(_lib.c_double_p), njobs, job_cand.ctypes.data_as(ci),
                                          ntr.ctypes.data_as(ci), nva.ctypes.data_as(ci), _lib.ptr(trd), ld_tr, _lib.ptr(vad),
                                          ld_va, _lib.ptr(pred), loglik.ctypes.data_as(_lib.c_double_p),
-                                         status.ctypes.data_as(ci)), "ab_gp_cv_batch")
+                                         status.ctypes.data_as(ci), _lib.ptr(work), cap), "ab_gp_cv_batch")
         ph = pred.cpu().numpy()
         return [ph[b, :nva[b]] for b in range(njobs)], loglik, status
 

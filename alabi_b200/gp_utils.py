@@ -224,9 +224,24 @@ def _evaluate_candidates(gp, theta, y, y_scaler, cands, k_folds, scoring, wmetho
         except Exception as e:  # noqa: BLE001 - e.g. out of device memory: fall through to the serial path
             print(f"CV: batched evaluation failed ({e}); evaluating the candidates one by one")
         else:
+            # the y scaler is applied ONCE to all targets and ONCE to all predictions (875 jobs would
+            # otherwise make 1750 sklearn transformer calls)
+            y_true = y_scaler.inverse_transform(y.reshape(-1, 1)).flatten()
+            sizes = [len(p) for p in preds]
+            flat = np.concatenate(preds) if sum(sizes) else np.empty(0)
+            good = np.isfinite(flat)
+            flat_t = np.full(len(flat), np.nan)
+            if good.any():
+                flat_t[good] = y_scaler.inverse_transform(flat[good].reshape(-1, 1)).flatten()
+            off = np.concatenate([[0], np.cumsum(sizes)])
             for b, (ci, fi) in enumerate(jobs):
-                if status[b] == 0:
-                    scores[ci, fi] = score(ci, fi, lls[b], preds[b], folds[ci][fi][1])
+                pb = flat_t[off[b]:off[b + 1]]
+                if status[b] != 0 or not np.isfinite(lls[b]) or len(pb) == 0 or not np.all(np.isfinite(pb)):
+                    continue
+                try:
+                    scores[ci, fi] = _fold_score(scoring, y_true[folds[ci][fi][1]], pb, wmethod, wfactor)
+                except Exception:  # noqa: BLE001 - a failed fold scores inf, like the reference
+                    scores[ci, fi] = np.inf
             return scores
     work = copy.copy(gp)
     for ci in ok_c:

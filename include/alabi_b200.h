@@ -253,12 +253,15 @@ int ab_nested_walk(ab_gp* h, const ab_nested_config* cfg, double* d_u, double* d
  * d_pred[b][...] (leading dimensions ld_train / ld_val), and h_status[b] is 0 or the 1-based index
  * of the first non-positive pivot (the reference scores such a fold as failed).  h_params holds,
  * per candidate, 3 + d doubles: mean, white_noise (ln variance), amp = exp(log_constant), log_M[d].
- * All jobs of a call are factorised by ONE batched dataflow-Cholesky launch per workspace chunk.
+ * All jobs of a call are factorised by ONE batched dataflow-Cholesky launch per workspace chunk:
+ * d_work / work_bytes is caller-owned device scratch (ab_gp_cv_workspace_bytes gives the size that
+ * takes all jobs in one launch; anything from one job's worth upwards works with more launches).
  * The handle supplies device, stream and nothing else: its own model state is not touched. */
 int ab_gp_cv_batch(ab_gp* h, const double* d_X, const double* d_y, int64_t n, int d, int kernel_id, int ncand,
                    const double* h_params, int njobs, const int* h_job_cand, const int* h_ntrain,
                    const int* h_nval, const int* d_train_idx, int ld_train, const int* d_val_idx, int ld_val,
-                   double* d_pred, double* h_loglik, int* h_status);
+                   double* d_pred, double* h_loglik, int* h_status, void* d_work, size_t work_bytes);
+size_t ab_gp_cv_workspace_bytes(int ntrain_max, int d, int ld_val, int ncand, int njobs);
 
 #ifdef __cplusplus
 }

@@ -28,3 +28,16 @@ for name, n in (("c1", 150), ("c2", 1000), ("c3", 2000)):
         out[batched] = (time.time() - t0, r.get_parameter_vector())
     print(f"{name} N={n}: 875 jobs batched {out[True][0]:.3f} s, one by one {out[False][0]:.3f} s, "
           f"speed-up {out[False][0] / out[True][0]:.1f}x, same winner {np.allclose(out[True][1], out[False][1])}", flush=True)
+
+# the batched call alone: 100 candidates x 5 folds on the c2 training set
+from sklearn.model_selection import KFold
+cfg = workloads.make_config("c2")
+X, y = cfg["X"], cfg["y"]
+g = workloads.build_gp(cfg)
+base = g.get_parameter_vector()
+cands = base + np.random.default_rng(2).normal(0, 0.2, size=(100, len(base)))
+folds = [f for c in range(100) for f in KFold(n_splits=5, shuffle=True, random_state=c).split(X)]
+for rep in range(3):
+    torch.cuda.synchronize(); t0 = time.time()
+    preds, ll, st = g.cv_batch(X, y, cands, folds)
+    torch.cuda.synchronize(); print(f"cv_batch 500 jobs, nt = 800: {(time.time() - t0) * 1e3:.1f} ms, ok {int((st == 0).sum())}", flush=True)
