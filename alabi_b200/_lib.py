@@ -58,6 +58,7 @@ SIGNATURES = {
     "ab_gp_destroy": (ctypes.c_int, [_P]),
     "ab_gp_set_lookahead": (ctypes.c_int, [_P, ctypes.c_int]),
     "ab_gp_set_few_query_path": (ctypes.c_int, [_P, ctypes.c_int]),
+    "ab_gp_set_variance_schedule": (ctypes.c_int, [_P, ctypes.c_int]),
     "ab_gp_append_point": (ctypes.c_int, [_P, _P]),
     "ab_gp_debug_stamps": (ctypes.c_int, [_P, _P]),
     "ab_gp_predict_grad": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, _P, _P, _P]),

@@ -131,6 +131,21 @@ __device__ __forceinline__ double ab_radial_grad(double r2) {
     return -5.0 * (1.0 + r) * ab_exp_sel<TAB>(-r) * 0.16666666666666666;
 }
 
+// k(r^2) and dk/d(r^2) from ONE exponential (the gradient kernels need both)
+template <int KIND, bool TAB = true>
+__device__ __forceinline__ void ab_radial_both(double r2, double& kv, double& gv) {
+    if (KIND == 0) {
+        const double e = ab_exp_sel<TAB>(-0.5 * r2);
+        kv = e; gv = -0.5 * e;
+    } else if (KIND == 1) {
+        const double r = ab_sqrt_pos(3.0 * r2), e = ab_exp_sel<TAB>(-r);
+        kv = (1.0 + r) * e; gv = -1.5 * e;
+    } else {
+        const double r = ab_sqrt_pos(5.0 * r2), e = ab_exp_sel<TAB>(-r);
+        kv = (1.0 + r + r * r * 0.3333333333333333) * e; gv = -5.0 * (1.0 + r) * e * 0.16666666666666666;
+    }
+}
+
 #define AB_DISPATCH_KIND(kind, ...)                                   \
     do {                                                              \
         if ((kind) == 0) { constexpr int KIND = 0; __VA_ARGS__; }     \

@@ -95,7 +95,7 @@ __device__ __forceinline__ void grid_wait(unsigned long long* counter, unsigned 
 }
 
 template <int KIND, int D, int EW, int P>
-__global__ void __launch_bounds__(EW * 32, (P == 32) ? 2 : 1)
+__global__ void __launch_bounds__(EW * 32, (P == 32 && EW == 8) ? 2 : 1)
 ensemble_kernel(const __grid_constant__ EnsArgs A) {
     constexpr int ETHREADS = EW * 32;
     extern __shared__ __align__(16) double sm[];
@@ -258,17 +258,23 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                         const int j0 = warp * per, j1 = j0 + per;
 #pragma unroll 2
                         for (int j = j0; j < j1; j += 2) {
-                            double r0 = 0.0, r1 = 0.0;
+                            // two partial sums per point (even / odd dimensions): with the two points of
+                            // a load and the unroll that is 8 independent FMA chains per lane
+                            double r0 = 0.0, r1 = 0.0, s0 = 0.0, s1 = 0.0;
 #pragma unroll
-                            for (int k = 0; k < D; k++) {
-                                const double2 xx = *reinterpret_cast<const double2*>(&bX[k * CH + j]);
-                                const double d0 = qv[k] - xx.x, d1 = qv[k] - xx.y;
+                            for (int k = 0; k < D; k += 2) {
+                                const double2 xa = *reinterpret_cast<const double2*>(&bX[k * CH + j]);
+                                const double2 xb = *reinterpret_cast<const double2*>(&bX[(k + 1) * CH + j]);
+                                const double d0 = qv[k] - xa.x, d1 = qv[k] - xa.y;
+                                const double e0 = qv[k + 1] - xb.x, e1 = qv[k + 1] - xb.y;
                                 r0 = fma(d0, d0, r0);
                                 r1 = fma(d1, d1, r1);
+                                s0 = fma(e0, e0, s0);
+                                s1 = fma(e1, e1, s1);
                             }
                             const double2 al = *reinterpret_cast<const double2*>(&bAl[j]);
-                            accw = fma(ab_radial<KIND>(r0), al.x, accw);
-                            accw = fma(ab_radial<KIND>(r1), al.y, accw);
+                            accw = fma(ab_radial<KIND>(r0 + s0), al.x, accw);
+                            accw = fma(ab_radial<KIND>(r1 + s1), al.y, accw);
                         }
                     };
                     if (resident) {
@@ -403,9 +409,8 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
     }
 }
 
-template <int KIND, int D, int P>
+template <int KIND, int D, int P, int EW = 8>
 int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
-    constexpr int EW = 8;
     constexpr int ETHREADS = EW * 32;
     auto kern = ensemble_kernel<KIND, D, EW, P>;
     // shared memory: resident when the whole training set fits, else two chunk buffers
@@ -418,8 +423,11 @@ int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
         if (ch < 32) ch = 32;
         smem = (size_t)ch * (D + 1) * 8;
     } else {
-        ch = 128;                                   // divides npad; two buffers of at most ~48 KB each
-        while (ch * 2 <= 512 && A.npad % (ch * 2) == 0 && (size_t)(ch * 2) * (D + 1) * 8 <= 48 * 1024) ch *= 2;
+        // divides npad; two buffers of at most ~48 KB each (two CTAs per SM) or ~100 KB each (the
+        // 16-warp wide unit has the SM to itself: longer chunks, fewer CTA barriers per point)
+        const size_t per_buf = (EW == 16) ? 100 * 1024 : 48 * 1024;
+        ch = 128;
+        while (ch * 2 <= 1024 && A.npad % (ch * 2) == 0 && (size_t)(ch * 2) * (D + 1) * 8 <= per_buf) ch *= 2;
         smem = 2 * (size_t)ch * (D + 1) * 8;
     }
     A.ch = ch;
@@ -443,7 +451,9 @@ int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
 // n_half: proposals of the larger half-step (or all walkers for a log-prob-only call)
 template <int KIND, int D>
 int launch_ens(ab_gp* h, EnsArgs& A, int n_half, int p) {
-    if (p == 32) return launch_ens_p<KIND, D, 32>(h, A, n_half);
+    // wide unit: 16 warps split the training points (4 warps per scheduler hide the FP64 dependency
+    // latency that 2 leave exposed: ncu, c5 share, FP64 pipe 56 % with 8 warps); one CTA per SM
+    if (p == 32) return launch_ens_p<KIND, D, 32, 16>(h, A, n_half);
     if (D <= 24 && p == 4) return launch_ens_p<KIND, (D <= 24 ? D : 2), 4>(h, A, n_half);
     return launch_ens_p<KIND, D, 2>(h, A, n_half);
 }
@@ -501,10 +511,10 @@ static int ens_enqueue(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords
     // warps per unit: all 8 warps on one unit while that still fills the GPU
     const int units_half = (n_half + p - 1) / p;
     int ws = 1;
-    if (p == 32) ws = 8;                       // wide unit = the whole CTA
+    if (p == 32) ws = 16;                      // wide unit = the whole CTA (16 warps)
     else if (cfg->warps_per_unit > 0) ws = cfg->warps_per_unit;
     else while (ws < 8 && units_half * ws <= nsm * 8) ws *= 2;
-    if (ws != 1 && ws != 2 && ws != 4 && ws != 8) { ab_set_error("warps_per_unit must be 1, 2, 4 or 8"); return -1; }
+    if (ws != 1 && ws != 2 && ws != 4 && ws != 8 && !(p == 32 && ws == 16)) { ab_set_error("warps_per_unit must be 1, 2, 4 or 8"); return -1; }
     A.ws = ws;
     const int d = h->d;
 #define AB_ENS(DD) AB_DISPATCH_KIND(h->kp.kind, rc = (launch_ens<KIND, DD>(h, A, n_half, p)))

@@ -16,7 +16,7 @@ namespace {
 constexpr int NB = AB_NB;
 
 template <int KIND, int DMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (DMAX <= 8) ? 3 : ((DMAX <= 20) ? 2 : 1))
 grad_tiles_kernel(const double* __restrict__ Kinv, int64_t ld, const double* __restrict__ XsT, int64_t npad,
                   int64_t n, const double* __restrict__ alpha, KernParams kp, double* __restrict__ partials) {
     extern __shared__ __align__(16) double sm[];
@@ -57,8 +57,10 @@ grad_tiles_kernel(const double* __restrict__ Kinv, int64_t ld, const double* __r
             } else d2[k] = 0.0;
         }
         const double a = wt * (sAi[r] * aj - Kinv[gi * ld + j0 + c]);
-        s_c = fma(a, kp.amp * ab_radial<KIND, false>(r2), s_c);
-        const double gk = -a * kp.amp * ab_radial_grad<KIND, false>(r2);
+        double kv, gv;
+        ab_radial_both<KIND, true>(r2, kv, gv);          // one exponential for k and dk/d(r^2)
+        s_c = fma(a, kp.amp * kv, s_c);
+        const double gk = -a * kp.amp * gv;
 #pragma unroll
         for (int k = 0; k < DMAX; k++)
             if (k < d) s_m[k] = fma(gk, d2[k], s_m[k]);
@@ -97,10 +99,13 @@ grad_final_kernel(const double* __restrict__ partials, int ntiles, const double*
         for (int w = 0; w < 8; w++) t += sh[w];
         out[0] = t;
     }
-    if (tid < d + 2) {
+    // tile partials: output w, w + 8, ... by warp w; lanes stride over the tiles, fixed-order tree
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int o = warp; o < d + 2; o += 8) {
         double t = 0.0;
-        for (int p = 0; p < ntiles; p++) t += partials[(int64_t)p * (AB_MAX_DIM + 2) + tid];
-        out[1 + tid] = 0.5 * t * (tid == 0 ? wn_scale : 1.0);
+        for (int p = lane; p < ntiles; p += 32) t += partials[(int64_t)p * (AB_MAX_DIM + 2) + o];
+        t = ab_warp_sum(t);
+        if (lane == 0) out[1 + o] = 0.5 * t * (o == 0 ? wn_scale : 1.0);
     }
 }
 
@@ -115,20 +120,26 @@ int ab_launch_grad(ab_gp* h, double* /*unused*/) {
     if (rc) return rc;
     double* partials = h->scratch + 64;
     cudaStream_t s = h->stream;
-    if (h->d <= 8) {
-        constexpr int DM = 8;
-        int smem = (2 * DM * NB + 2 * NB + 8 * (DM + 2)) * 8;
-        AB_DISPATCH_KIND(h->kp.kind, (grad_tiles_kernel<KIND, DM><<<ntiles, 256, smem, s>>>(
-                                         h->Kinv, h->npad, h->XsT, h->npad, h->n, h->alpha, h->kp, partials)));
-    } else {
-        constexpr int DM = AB_MAX_DIM;
-        int smem = (2 * DM * NB + 2 * NB + 8 * (DM + 2)) * 8;
-        AB_DISPATCH_KIND(h->kp.kind, {
-            AB_CUDA(cudaFuncSetAttribute(grad_tiles_kernel<KIND, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            grad_tiles_kernel<KIND, DM><<<ntiles, 256, smem, s>>>(h->Kinv, h->npad, h->XsT, h->npad, h->n, h->alpha,
-                                                                  h->kp, partials);
-        });
-    }
+    // the per-dimension loops are unrolled over the template dimension: instantiate the padded
+    // dimension of the problem, not AB_MAX_DIM (d = 10 ran 32-long predicated loops with 230 registers)
+#define AB_GT(DM)                                                                                                    \
+    do {                                                                                                             \
+        const int smem = (2 * DM * NB + 2 * NB + 8 * (DM + 2)) * 8;                                                  \
+        AB_DISPATCH_KIND(h->kp.kind, {                                                                               \
+            AB_CUDA(cudaFuncSetAttribute(grad_tiles_kernel<KIND, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            grad_tiles_kernel<KIND, DM><<<ntiles, 256, smem, s>>>(h->Kinv, h->npad, h->XsT, h->npad, h->n, h->alpha,  \
+                                                                  h->kp, partials);                                  \
+        });                                                                                                          \
+    } while (0)
+    if (h->d <= 2) AB_GT(2);
+    else if (h->d <= 4) AB_GT(4);
+    else if (h->d <= 8) AB_GT(8);
+    else if (h->d <= 12) AB_GT(12);
+    else if (h->d <= 16) AB_GT(16);
+    else if (h->d <= 20) AB_GT(20);
+    else if (h->d <= 24) AB_GT(24);
+    else AB_GT(32);
+#undef AB_GT
     AB_CHECK_LAUNCH();
     grad_final_kernel<<<1, 256, 0, s>>>(partials, ntiles, h->alpha, h->n, h->d, exp(h->white_noise), h->scratch);
     AB_CHECK_LAUNCH();

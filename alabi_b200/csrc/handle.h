@@ -47,6 +47,7 @@ struct ab_gp {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev[AB_PROF_FAMILIES];
 
+    int var_schedule = 0;                 // variance GEMM over full panels: 0 auto, 1 one CTA per query tile, 2 row-block pairs per CTA
     bool few_path = true;                 // m <= 8 queries: the spread-one-query kernels of predict.cu (false: batched kernels)
     int lookahead = 2;                    // factor schedule: 0 plain sweep, 1 look-ahead streams, 2 dataflow kernel
     void* df_tasks = nullptr;             // dataflow task list (device) for df_tasks_T block rows

@@ -193,6 +193,46 @@ predict_var_split_kernel(const double* __restrict__ Linv, int64_t ld, const doub
     for (int j = 0; j < 4; j++) *reinterpret_cast<double2*>(dst + 2 * j) = make_double2(blk[j][0], blk[j][1]);
 }
 
+// Full panels with many row blocks: predict_var_kernel gives one CTA the whole row-block loop of its
+// 128 queries, so the CTA streams its own 128-column slice of the panel (N x 128 x 8 B = 8 MB at
+// N = 8192) once per row block, and 148 such slices do not fit the L2: ncu shows 40 GB of DRAM
+// reads per 18 944-query wave against 1.5 GB of algorithmic bytes.  Here the work of ONE query tile
+// is spread over ceil(T / 2) CTAs that are ADJACENT in launch order (blockIdx.x = row-block pair
+// (p, T - 1 - p): T + 1 k blocks each, so all CTAs carry equal work), so the few tiles in flight
+// share their panel slices through the L2 and L^-1 is streamed once per group of tiles.  Per-thread
+// block values go to `part` exactly like predict_var_split_kernel; var_combine_kernel finishes in
+// the canonical order, so the bits equal predict_var_kernel's.
+template <int NL>
+__global__ void __launch_bounds__(abg::THREADS, 1)
+predict_var_pair_kernel(const double* __restrict__ Linv, int64_t ld, int T, int ntq, const double* __restrict__ P,
+                        int64_t ldp, double* __restrict__ part) {
+    extern __shared__ __align__(16) double smem[];
+    // persistent: one CTA per SM walks the (tile, pair) items round-robin, pair index fastest, so the
+    // CTAs that run at the same time work on neighbouring items = the same few query tiles
+    const int npairs = (T + 1) / 2;
+    const long long nitems = (long long)npairs * ntq;
+    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int p = (int)(item % npairs), q = (int)(item / npairs);
+        const double* Bp = P + (int64_t)q * abg::BN;
+        for (int h = 0; h < 2; h++) {
+            const int i = (h == 0) ? p : T - 1 - p;
+            if (h == 1 && i == p) break;                         // middle row block of an odd T
+            abg::Acc acc;
+            acc.zero();
+            if (NL < 16 && i == T - 1)      // last row block: only the 8-row groups that hold training points
+                abg::Main::mainloop<true, false, true, abg::NoGate, NL>(acc, Linv + (int64_t)i * NB * ld, ld, Bp, ldp,
+                                                                       (i + 1) * (NB / abg::BK), smem);
+            else
+                abg::mainloop<true, false, true>(acc, Linv + (int64_t)i * NB * ld, ld, Bp, ldp, (i + 1) * (NB / abg::BK), smem);
+            double blk[4][2];
+            tile_thread_sq(acc, blk);
+            double* dst = part + (((int64_t)i * ntq + q) * abg::THREADS + threadIdx.x) * 8;
+#pragma unroll
+            for (int j = 0; j < 4; j++) *reinterpret_cast<double2*>(dst + 2 * j) = make_double2(blk[j][0], blk[j][1]);
+        }
+    }
+}
+
 // one CTA (256 threads) per query tile
 __global__ void __launch_bounds__(abg::THREADS)
 var_combine_kernel(const double* __restrict__ part, int T, int64_t m, int64_t q_off, double amp,
@@ -804,7 +844,25 @@ static int launch_variance(ab_gp* h, int T, const double* P, int64_t ldp, int64_
                            double* var, double* part) {
     cudaStream_t s = h->stream;
     const unsigned ntq = (unsigned)((cnt + abg::BN - 1) / abg::BN);
-    if (T > 1 && (int)ntq * 2 <= h->nsm && part) {
+    const bool pair = part && T >= 2 && (h->var_schedule == 2 || (h->var_schedule == 0 && T >= 16 && (int)ntq * 2 > h->nsm));
+    if (pair) {
+        const long long nitems = (long long)((T + 1) / 2) * ntq;
+        const unsigned grid = (unsigned)(nitems < h->nsm ? nitems : h->nsm);
+        const int nlp = (int)((h->n - (int64_t)(T - 1) * NB + 7) / 8);       // 1..16 row groups in the last block
+#define AB_PP(NLV)                                                                                                 \
+    case NLV:                                                                                                      \
+        AB_CUDA(cudaFuncSetAttribute(predict_var_pair_kernel<NLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES)); \
+        predict_var_pair_kernel<NLV><<<grid, abg::THREADS, abg::SMEM_BYTES, s>>>(h->Linv, h->npad, T, (int)ntq, P, ldp, part); \
+        break
+        switch (nlp) {
+            AB_PP(1); AB_PP(2); AB_PP(3); AB_PP(4); AB_PP(5); AB_PP(6); AB_PP(7); AB_PP(8);
+            AB_PP(9); AB_PP(10); AB_PP(11); AB_PP(12); AB_PP(13); AB_PP(14); AB_PP(15);
+            default: AB_PP(16);
+        }
+#undef AB_PP
+        var_combine_kernel<<<ntq, abg::THREADS, 0, s>>>(part, T, m, q0, h->kp.amp, var);
+        ab_count_launches(1);
+    } else if (T > 1 && (int)ntq * 2 <= h->nsm && part) {
         predict_var_split_kernel<<<dim3(ntq, T), abg::THREADS, abg::SMEM_BYTES, s>>>(h->Linv, h->npad, P, ldp, part);
         var_combine_kernel<<<ntq, abg::THREADS, 0, s>>>(part, T, m, q0, h->kp.amp, var);
         ab_count_launches(1);
@@ -880,7 +938,7 @@ int ab_launch_predict(ab_gp* h, const double* Xq, int64_t m, double* mu, double*
     const int nsplit = (int)((h->npad + JCHUNK - 1) / JCHUNK);
     (void)nblk;
     const size_t panel_elems = (size_t)h->npad * ldp;
-    const bool few = (int64_t)2 * ((mq + abg::BN - 1) / abg::BN) <= h->nsm;      // split-T variance path possible
+    const bool few = true;            // per-thread block values: split-T (few tiles) and paired (full panels) schedules
     int rc = ab_ensure_scratch(h, (panel_elems + (size_t)nsplit * ldp + (few ? (size_t)T * ldp * 16 : 0)) * sizeof(double));
     if (rc) return rc;
     AB_CUDA(cudaFuncSetAttribute(predict_var_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, abg::SMEM_BYTES));

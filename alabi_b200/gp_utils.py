@@ -307,7 +307,7 @@ _generate_stage3_candidates = _generate_stage_candidates
 def optimize_gp_kfold_cv(gp, _theta, _y, hyperparameter_candidates, y_scaler, k_folds=5, scoring="mse", pool=None,
                          stage2_candidates=None, stage2_width=0.5, stage3_candidates=None, stage3_width=0.2,
                          weighted_mse_method="exponential", weighted_mse_factor=1.0, verbose=True, batched=True,
-                         random_state=None):
+                         random_state=None, shard_candidates=False):
     """Pick the hyper-vector with the best mean k-fold validation score out of
     the given candidates, then refine around the winner with up to two
     Gaussian candidate clouds.  Returns the GP set to the winner and computed
@@ -340,6 +340,20 @@ def optimize_gp_kfold_cv(gp, _theta, _y, hyperparameter_candidates, y_scaler, k_
         # one batched device call per stage (all candidates x folds); ``random_state`` fixes the splits
         rs = None if random_state is None else int(random_state) + 100003 * stage[0]
         stage[0] += 1
+        from . import parallel as par
+        if shard_candidates and par.world_size() > 1:
+            # candidates sharded over the ranks, one all_gather of the per-fold scores;
+            # the splits are seeded by the GLOBAL candidate index, so the scores equal a one-rank run
+            c = np.asarray(par.broadcast_object(np.asarray(c)))
+            seed0 = par.broadcast_object(int(np.random.randint(2 ** 31)) if rs is None else rs)
+
+            def part(idx):
+                sc = np.full((len(idx), k_folds), np.inf)
+                for row, ci in enumerate(idx):
+                    sc[row] = _evaluate_candidates(gp, theta, y, y_scaler, c[ci:ci + 1], k_folds, scoring, weighted_mse_method,
+                                                   weighted_mse_factor, batched=batched, random_state=seed0 + int(ci))[0]
+                return sc
+            return _mean_scores(par.sharded_rows(part, len(c)))
         return _mean_scores(_evaluate_candidates(gp, theta, y, y_scaler, c, k_folds, scoring, weighted_mse_method,
                                                  weighted_mse_factor, batched=batched, random_state=rs))
 

@@ -21,7 +21,7 @@ import numpy as np
 
 __all__ = ["init_distributed", "shard_range", "broadcast_gp", "argmin_allgather", "allgather_rows", "allgather_walkers",
            "sharded_predict", "sharded_utility_argmin", "sharded_ensemble", "sharded_restarts",
-           "broadcast_object", "world_size"]
+           "broadcast_object", "world_size", "sharded_rows"]
 
 
 def init_distributed(backend=None):
@@ -277,3 +277,32 @@ def sharded_restarts(optimize_fn, starts):
     allr.sort(key=lambda t: t[1])
     best = min(allr, key=lambda t: (t[0] if np.isfinite(t[0]) else np.inf, t[1]))
     return OptimizeResult(x=best[2], fun=best[0], nit=best[3], success=best[4], restart=best[1]), allr
+
+
+def sharded_rows(eval_fn, nrows):
+    """Row-sharded evaluation with one all_gather (k-fold CV candidates): rank r calls
+    ``eval_fn(indices)`` for the rows r, r + world, ... and gets a (len(indices), ...) float array;
+    every rank returns the full (nrows, ...) array in row order.  ``eval_fn`` must depend on the
+    global row index only (e.g. fold splits seeded by candidate index), so the result equals a
+    single-rank evaluation."""
+    import torch
+    dist = _dist()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    mine = np.arange(rank, nrows, world)
+    local = np.asarray(eval_fn(mine), dtype=np.float64)
+    if world == 1:
+        return local
+    tail = tuple(local.shape[1:])
+    per = (nrows + world - 1) // world
+    pad = np.full((per,) + tail, np.nan)
+    pad[:len(mine)] = local
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(pad).to(dev)
+    out = torch.empty((world * per,) + tail, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, t)
+    out = out.cpu().numpy().reshape((world, per) + tail)
+    full = np.empty((nrows,) + tail)
+    for r in range(world):
+        idx = np.arange(r, nrows, world)
+        full[idx] = out[r, :len(idx)]
+    return full

@@ -317,6 +317,8 @@ def _worker(rank, world, port, q):
     eq = torch.arange(3 * 4 * 2, dtype=torch.float64).reshape(3, 4, 2) + 100.0 * r
     out["walkers_eq"] = par.allgather_walkers(eq, 8).numpy()
     out["walkers_ragged"] = par.allgather_walkers(ch, 101).numpy()
+    # row-sharded evaluation (CV candidates): equals the one-rank result, in row order
+    out["rows_eval"] = par.sharded_rows(lambda idx: np.stack([np.asarray(idx, dtype=float) ** 2, -np.asarray(idx, dtype=float)], axis=1), 7)
     # optimiser restarts sharded over ranks: same winner everywhere, ties -> lowest restart index
     from scipy.optimize import minimize
     starts = par.broadcast_object(np.random.default_rng(100 + r).uniform(-3, 3, size=(5, 2)))
@@ -347,6 +349,7 @@ def test_world_size_2_gloo_host_logic():
         np.testing.assert_array_equal(res[r]["rows"][:, 0], np.arange(101))
         assert res[r]["chain"].shape == (4, 101, 2) and res[r]["chain"][0, 50, 0] == 0 and res[r]["chain"][0, 51, 0] == 1
         assert res[r]["big"] == (1.0, (1 << 60) + 3)
+        np.testing.assert_array_equal(res[r]["rows_eval"], np.stack([np.arange(7.0) ** 2, -np.arange(7.0)], axis=1))
         we = res[r]["walkers_eq"]
         base = np.arange(24, dtype=np.float64).reshape(3, 4, 2)
         assert we.shape == (3, 8, 2) and np.array_equal(we[:, :4], base) and np.array_equal(we[:, 4:], base + 100.0)
