@@ -10,7 +10,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libalabi_b200.so")
+# ALABI_B200_LIB: development override (kernel variants built by tools/ens_variants.sh)
+LIB_PATH = os.environ.get("ALABI_B200_LIB") or os.path.join(HERE, "libalabi_b200.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)

@@ -24,7 +24,13 @@
 #include "handle.h"
 #include "alabi_b200.h"
 
+#ifndef AB_ENS_WIDE_UNROLL
+#define AB_ENS_WIDE_UNROLL 2      // point pairs per iteration of the wide unit's inner loop (1 and 4 measured: tools/ens_variants.sh)
+#endif
+
 namespace {
+
+constexpr int kWideUnroll = AB_ENS_WIDE_UNROLL;
 
 // warps per CTA (EW): 8; 16 was measured slower on the c2 workload (longer proposal and compute phases)
 
@@ -38,6 +44,11 @@ struct EnsArgs {
     KernParams kp; double mean;
     // sampler configuration
     int nwalkers, d, nsteps, thin_by, init_logp, randomize_split, ws, ch;
+    // wide unit: the training points of one 32-proposal unit are split over `nslice` CTAs (work
+    // items) so that the items of a half-step fill the SMs evenly; slice sums meet in slice_part
+    // and the CTA that completes a unit (slice_cnt) finishes it
+    int nslice, max_units;
+    double* slice_part; unsigned* slice_cnt;
     double a;
     unsigned seed_lo, seed_hi;
     long long first_step, walker_offset;
@@ -114,6 +125,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
     __shared__ double sPart[EW][P], sLogZ[NU][P], sLogU[NU][P], sLps[NU][P], sZZ[NU][P];
     __shared__ int sW[NU][P], sInside[NU][P], sPartner[NU][P];
     __shared__ double sPrior[NU][P];             // ln of the normal part of the prior at the proposal
+    __shared__ int sSliceLast;                   // split units: this CTA delivered the last slice of its unit
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int WS = A.ws, G = EW / WS;
@@ -186,7 +198,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
     };
 
     const int first = A.init_logp ? -1 : 0;
-    if (first < A.nsteps) prep(first, 0, blockIdx.x);
+    if (first < A.nsteps) prep(first, 0, (int)blockIdx.x / (WIDE ? A.nslice : 1));
     for (int step = first; step < A.nsteps; step++) {
         const int nsplit = (step < 0) ? 1 : 2;
         // row of the stored chain this step writes (-1: not stored)
@@ -195,10 +207,13 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
         for (int split = 0; split < nsplit; split++) {
             const int n_items = (step < 0) ? nw : (split == 0 ? (nw + 1) / 2 : nw / 2);
             const int nbatch = (n_items + P * G - 1) / (P * G);
-            for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
+            const int S = WIDE ? A.nslice : 1;                   // slices of the training set per unit
+            const int slot = (step < 0) ? 2 : split;             // completion counters / slice sums of this kind of half-step
+            for (int it = blockIdx.x; it < nbatch * S; it += gridDim.x) {
+                const int b = it / S, sl = it - b * S;
                 long long t0 = 0, t1 = 0, t2 = 0;
                 if (A.dbg) t0 = clock64();
-                if (b != (int)blockIdx.x) prep(step, split, b);      // extra batches of this CTA: inline
+                if (it != (int)blockIdx.x) prep(step, split, b);     // extra items of this CTA: inline
                 // ---- gather (proposal lanes): own state and partner position, proposal ----
                 if (prop_lane) {
                     const int e = lane, w = sW[unit][e], partner = sPartner[unit][e];
@@ -256,7 +271,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                     auto eval_wide = [&](const double* bX, const double* bAl, int cn) {
                         const int per = cn / EW;
                         const int j0 = warp * per, j1 = j0 + per;
-#pragma unroll 2
+#pragma unroll kWideUnroll
                         for (int j = j0; j < j1; j += 2) {
                             // two partial sums per point (even / odd dimensions): with the two points of
                             // a load and the unroll that is 8 independent FMA chains per lane
@@ -281,13 +296,14 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                         eval_wide(sX, sAl, CH);
                     } else {
                         const int nch = (int)(A.npad / CH);
-                        issue_chunk(0, 0);
-                        for (int c = 0; c < nch; c++) {
-                            if (c + 1 < nch) issue_chunk((long long)(c + 1) * CH, (c + 1) & 1);
+                        const int c_lo = (int)((long long)sl * nch / S), c_hi = (int)((long long)(sl + 1) * nch / S);
+                        if (c_lo < c_hi) issue_chunk((long long)c_lo * CH, 0);
+                        for (int c = c_lo; c < c_hi; c++) {
+                            if (c + 1 < c_hi) issue_chunk((long long)(c + 1) * CH, (c + 1 - c_lo) & 1);
                             else asm volatile("cp.async.commit_group;" ::: "memory");
                             asm volatile("cp.async.wait_group 1;" ::: "memory");
                             __syncthreads();
-                            const double* bX = sm + (c & 1) * BUF;
+                            const double* bX = sm + ((c - c_lo) & 1) * BUF;
                             eval_wide(bX, bX + D * CH, CH);
                             __syncthreads();
                         }
@@ -344,16 +360,41 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 }
                 __syncthreads();
                 if (A.dbg) t2 = clock64();
+                // ---- split units: publish this slice's sums; the CTA that completes the unit goes on ----
+                bool finisher = true;
+                if (WIDE && S > 1) {
+                    double* part = A.slice_part + (((long long)slot * A.max_units + b) * S) * 32;
+                    if (prop_lane) {
+                        double sp = 0.0;
+#pragma unroll
+                        for (int x = 0; x < EW; x++) sp += sPart[x][lane];          // warps in order
+                        __stcg(&part[sl * 32 + lane], sp);
+                    }
+                    __threadfence();
+                    __syncthreads();
+                    if (tid == 0) {
+                        const unsigned old = atomicAdd(&A.slice_cnt[(long long)slot * A.max_units + b], 1u);
+                        sSliceLast = ((old + 1u) % (unsigned)S == 0u) ? 1 : 0;
+                        __threadfence();
+                    }
+                    __syncthreads();
+                    finisher = sSliceLast != 0;
+                }
                 // ---- accept / reject ------------------------------------------------
-                if (prop_lane) {
+                if (prop_lane && finisher) {
                     const int e = lane, w = sW[unit][e];
                     if (w >= 0) {
+                        double s = 0.0;
+                        if (WIDE && S > 1) {
+                            const double* part = A.slice_part + (((long long)slot * A.max_units + b) * S) * 32;
+                            for (int x = 0; x < S; x++) s += __ldcg(&part[x * 32 + e]);   // slices in order
+                        } else {
                         double pv[EW];                       // independent loads, then the fixed-order sum
 #pragma unroll
                         for (int x = 0; x < EW; x++) pv[x] = (x < WS) ? sPart[unit * WS + x][e] : 0.0;
-                        double s = 0.0;
 #pragma unroll
                         for (int x = 0; x < EW; x++) s += pv[x];
+                        }
                         double ys = fma(A.kp.amp, s, A.mean);
                         double y = (A.y_kind == 0) ? fma(ys, A.y_scale, A.y_off)
                                  : (A.y_kind == 1) ? -pow(10.0, ys) : pow(10.0, ys);
@@ -393,7 +434,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 // the proposal lanes own sW.. of their unit: the next prep / gather by the same
                 // lanes follows in program order; sQs / sPart readers are fenced by the two
                 // __syncthreads above and the one that opens grid_arrive / the next gather
-                if (b + (int)gridDim.x < nbatch) __syncthreads();
+                if (it + (int)gridDim.x < nbatch * S) __syncthreads();
             }
             long long tb = 0;
             if (A.dbg) { __syncthreads(); tb = clock64(); }
@@ -401,7 +442,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
             {   // random-stream part of the next half-step, overlapped with the barrier
                 int nstep = step, nsp = split + 1;
                 if (nsp >= nsplit) { nstep = step + 1; nsp = 0; }
-                if (nstep < A.nsteps) prep(nstep, nsp, blockIdx.x);
+                if (nstep < A.nsteps) prep(nstep, nsp, (int)blockIdx.x / (WIDE ? A.nslice : 1));
             }
             grid_wait(A.barrier, bar_target);
             if (A.dbg && blockIdx.x == 0 && tid == 0) { A.dbg[3] += clock64() - tb; A.dbg[4] += 1; }
@@ -437,8 +478,22 @@ int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
     if (per_sm < 1) { ab_set_error("ensemble kernel does not fit on an SM (smem %zu)", smem); return -3; }
     int G = EW / A.ws;
     int nbatch = (n_half + P * G - 1) / (P * G);
-    int grid = per_sm * h->nsm;
-    if (grid > nbatch) grid = nbatch;
+    const int grid_max = per_sm * h->nsm;
+    A.nslice = 1;
+    if (P == 32 && (size_t)need > budget) {
+        // streamed wide unit: split the training points of a unit over S work items when that fills
+        // the SMs more evenly (128 units on 148 SMs leave 14 % idle; 8 x 128 items fill 98.8 %)
+        const int nch = (int)(A.npad / ch);
+        double best = 0.0;
+        for (int sN = 1; sN <= 16 && sN <= nch; sN *= 2) {
+            const long long items = (long long)nbatch * sN;
+            const double eff = (double)items / (double)(((items + grid_max - 1) / grid_max) * grid_max);
+            if (eff > best + 0.02) { best = eff; A.nslice = sN; }
+        }
+    }
+    long long items = (long long)nbatch * A.nslice;
+    int grid = grid_max;
+    if (grid > items) grid = (int)items;
     if (grid < 1) grid = 1;
     void* args[] = {(void*)&A};
     ab_prof_begin(h, AB_PROF_ENSEMBLE);
@@ -467,9 +522,18 @@ static int ens_enqueue(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords
                        double* d_rec_lp, bool first) {
     if (!h->have_alpha) { ab_set_error("ab_ensemble_run: targets not set (call ab_gp_set_targets)"); return -2; }
     if (cfg->nwalkers < 2 || cfg->nsteps < 0 || cfg->thin_by < 1) { ab_set_error("bad ensemble configuration"); return -1; }
-    int rc = ab_ensure_scratch(h, 64);
+    // scratch: [0, 4096) barrier word, NaN flag, debug counters; then the completion counters and the
+    // slice sums of split wide units (3 kinds of half-step x units x up to 16 slices x 32 proposals)
+    const int max_units = (cfg->nwalkers + 31) / 32;
+    const size_t cnt_bytes = ((size_t)3 * max_units * sizeof(unsigned) + 255) / 256 * 256;
+    const size_t part_bytes = (size_t)3 * max_units * 16 * 32 * sizeof(double);
+    int rc = ab_ensure_scratch(h, 4096 + cnt_bytes + part_bytes);
     if (rc) return rc;
     EnsArgs A{};
+    A.max_units = max_units;
+    A.slice_cnt = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(h->scratch) + 4096);
+    A.slice_part = reinterpret_cast<double*>(reinterpret_cast<char*>(h->scratch) + 4096 + cnt_bytes);
+    if (first) AB_CUDA(cudaMemsetAsync(A.slice_cnt, 0, cnt_bytes, h->stream));
     A.coords = d_coords; A.logp = d_logp; A.naccept = d_naccept;
     A.chain = d_chain; A.logp_chain = d_logp_chain; A.rec_q = d_rec_q; A.rec_lp = d_rec_lp;
     A.barrier = reinterpret_cast<unsigned long long*>(h->scratch);

@@ -82,7 +82,7 @@ int ab_gp_set_few_query_path(ab_gp* h, int enabled);
 /* schedule of the variance GEMM over full query panels: 1 = one CTA per 128-query tile loops over
  * all row blocks (its panel slice is re-streamed from HBM once per row block when N is large),
  * 2 = the row blocks of a tile are spread over adjacent CTAs in pairs (p, T - 1 - p) that share
- * the slice through the L2, 0 (default) = 2 for N >= 2048 on full panels, else 1.  Same bits. */
+ * the slice through the L2, 0 (default) = 2 for N >= 6144 on full panels, else 1.  Same bits. */
 int ab_gp_set_variance_schedule(ab_gp* h, int mode);
 /* development aid: device buffer (6 x uint64 per tile task, column-major task order) that the
  * dataflow Cholesky fills with %globaltimer stamps; NULL (default) disables it */

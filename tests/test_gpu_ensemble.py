@@ -143,3 +143,24 @@ def test_large_nonresident_training_set():
     s.run_mcmc(p0, 12)
     chain, lps, nacc, _ = oem.replay_device_chain(p0, lp_oracle, 12, 5)
     np.testing.assert_allclose(s.get_chain(), chain, rtol=1e-9, atol=1e-12)
+
+
+def test_wide_streamed_split_units_replay():
+    """Large ensemble on a training set that does not fit shared memory: the wide unit streams the
+    points, and the points of one 32-proposal unit are split over several CTAs whose slice sums
+    are combined in slice order by the CTA that completes the unit.  The chain must still replay on
+    the CPU, and must not depend on how a run is cut into pieces."""
+    from alabi_b200.ensemble import EnsembleSampler
+    d, nw = 12, 4800
+    g, lp, lp_oracle, rng, b = surrogate("ExpSquaredKernel", 6000, d, 31, [(-2.0, 2.0)] * d)
+    p0 = rng.uniform(-1, 1, size=(nw, d))
+    s = EnsembleSampler(nw, d, lp, seed=77)
+    s.run_mcmc(p0, 5)
+    chain, lps, nacc, _ = oem.replay_device_chain(p0, lp_oracle, 5, 77)
+    np.testing.assert_allclose(s.get_chain(), chain, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(s.get_log_prob(), lps, rtol=1e-9, atol=1e-9)
+    assert np.array_equal(s._naccepted, nacc)
+    s2 = EnsembleSampler(nw, d, lp, seed=77)
+    s2.run_mcmc(p0, 2)
+    s2.run_mcmc(None, 3)
+    np.testing.assert_array_equal(s2.get_chain(), s.get_chain())
