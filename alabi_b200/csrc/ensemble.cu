@@ -24,6 +24,7 @@
 #include "handle.h"
 #include "alabi_b200.h"
 
+#define AB_ENS_MAXSEG 64           // segments a streamed wide unit may be cut into (ranged schedule)
 #ifndef AB_ENS_WIDE_UNROLL
 #define AB_ENS_WIDE_UNROLL 2      // point pairs per iteration of the wide unit's inner loop (1 and 4 measured: tools/ens_variants.sh)
 #endif
@@ -44,10 +45,12 @@ struct EnsArgs {
     KernParams kp; double mean;
     // sampler configuration
     int nwalkers, d, nsteps, thin_by, init_logp, randomize_split, ws, ch;
-    // wide unit: the training points of one 32-proposal unit are split over `nslice` CTAs (work
-    // items) so that the items of a half-step fill the SMs evenly; slice sums meet in slice_part
-    // and the CTA that completes a unit (slice_cnt) finishes it
-    int nslice, max_units;
+    // streamed wide unit, `ranged` != 0: the work of a half-step is the list of (unit, chunk of
+    // training points) pairs, cut into equal CONTIGUOUS ranges, one per CTA, so every SM carries the
+    // same load whatever the number of units (128 units on 148 SMs would leave 14 % idle).  A unit
+    // whose chunks fall into several ranges is finished by the CTA that delivers its last segment:
+    // segment sums meet in slice_part (fixed segment order), completions are counted in slice_cnt.
+    int ranged, max_units;
     double* slice_part; unsigned* slice_cnt;
     double a;
     unsigned seed_lo, seed_hi;
@@ -198,7 +201,23 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
     };
 
     const int first = A.init_logp ? -1 : 0;
-    if (first < A.nsteps) prep(first, 0, (int)blockIdx.x / (WIDE ? A.nslice : 1));
+    // contiguous ranges of (unit, chunk) pairs: CTA c owns [c W / G, (c + 1) W / G)
+    auto range_begin = [&](long long W, long long c) -> long long { return c * W / (long long)gridDim.x; };
+    auto range_owner = [&](long long W, long long w) -> int {
+        long long c = w * (long long)gridDim.x / W;
+        while (c + 1 < (long long)gridDim.x && range_begin(W, c + 1) <= w) c++;
+        while (c > 0 && range_begin(W, c) > w) c--;
+        return (int)c;
+    };
+    // unit this CTA starts the given half-step with (its random-stream part is prepared early)
+    auto first_unit = [&](int step, int split) -> int {
+        if (!(WIDE && !resident && A.ranged != 0)) return (int)blockIdx.x;
+        const int n_items = (step < 0) ? nw : (split == 0 ? (nw + 1) / 2 : nw / 2);
+        const int nbatch = (n_items + P * G - 1) / (P * G);
+        const int nchunks = (int)(A.npad / CH);
+        return (int)(range_begin((long long)nbatch * nchunks, blockIdx.x) / nchunks);
+    };
+    if (first < A.nsteps) prep(first, 0, first_unit(first, 0));
     for (int step = first; step < A.nsteps; step++) {
         const int nsplit = (step < 0) ? 1 : 2;
         // row of the stored chain this step writes (-1: not stored)
@@ -207,13 +226,35 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
         for (int split = 0; split < nsplit; split++) {
             const int n_items = (step < 0) ? nw : (split == 0 ? (nw + 1) / 2 : nw / 2);
             const int nbatch = (n_items + P * G - 1) / (P * G);
-            const int S = WIDE ? A.nslice : 1;                   // slices of the training set per unit
-            const int slot = (step < 0) ? 2 : split;             // completion counters / slice sums of this kind of half-step
-            for (int it = blockIdx.x; it < nbatch * S; it += gridDim.x) {
-                const int b = it / S, sl = it - b * S;
+            const int slot = (step < 0) ? 2 : split;             // completion counters / segment sums of this kind of half-step
+            const bool ranged = WIDE && !resident && A.ranged != 0;
+            const int nchunks = resident ? 1 : (int)(A.npad / CH);
+            const long long Wtot = (long long)nbatch * nchunks;  // (unit, chunk) pairs of this half-step
+            const long long w_begin = ranged ? range_begin(Wtot, blockIdx.x) : 0, w_end = ranged ? range_begin(Wtot, blockIdx.x + 1) : 0;
+            long long wcur = w_begin;
+            int it = blockIdx.x;
+            bool first_seg = true;
+            for (;;) {
+                int b, c_lo = 0, c_hi = nchunks, seg = 0, nseg = 1;
+                if (ranged) {
+                    if (wcur >= w_end) break;
+                    b = (int)(wcur / nchunks);
+                    const long long u0 = (long long)b * nchunks, u1 = u0 + nchunks;
+                    c_lo = (int)(wcur - u0);
+                    c_hi = (int)((w_end < u1 ? w_end : u1) - u0);
+                    const int cta0 = range_owner(Wtot, u0), cta1 = range_owner(Wtot, u1 - 1);
+                    seg = (int)blockIdx.x - cta0;
+                    nseg = cta1 - cta0 + 1;
+                    wcur = u0 + c_hi;
+                } else {
+                    if (it >= nbatch) break;
+                    b = it;
+                    it += gridDim.x;
+                }
                 long long t0 = 0, t1 = 0, t2 = 0;
                 if (A.dbg) t0 = clock64();
-                if (it != (int)blockIdx.x) prep(step, split, b);     // extra items of this CTA: inline
+                if (!first_seg) prep(step, split, b);                // further units of this CTA: inline
+                first_seg = false;
                 // ---- gather (proposal lanes): own state and partner position, proposal ----
                 if (prop_lane) {
                     const int e = lane, w = sW[unit][e], partner = sPartner[unit][e];
@@ -295,8 +336,6 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                     if (resident) {
                         eval_wide(sX, sAl, CH);
                     } else {
-                        const int nch = (int)(A.npad / CH);
-                        const int c_lo = (int)((long long)sl * nch / S), c_hi = (int)((long long)(sl + 1) * nch / S);
                         if (c_lo < c_hi) issue_chunk((long long)c_lo * CH, 0);
                         for (int c = c_lo; c < c_hi; c++) {
                             if (c + 1 < c_hi) issue_chunk((long long)(c + 1) * CH, (c + 1 - c_lo) & 1);
@@ -362,19 +401,19 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 if (A.dbg) t2 = clock64();
                 // ---- split units: publish this slice's sums; the CTA that completes the unit goes on ----
                 bool finisher = true;
-                if (WIDE && S > 1) {
-                    double* part = A.slice_part + (((long long)slot * A.max_units + b) * S) * 32;
+                if (WIDE && nseg > 1) {
+                    double* part = A.slice_part + (((long long)slot * A.max_units + b) * AB_ENS_MAXSEG) * 32;
                     if (prop_lane) {
                         double sp = 0.0;
 #pragma unroll
                         for (int x = 0; x < EW; x++) sp += sPart[x][lane];          // warps in order
-                        __stcg(&part[sl * 32 + lane], sp);
+                        __stcg(&part[seg * 32 + lane], sp);
                     }
                     __threadfence();
                     __syncthreads();
                     if (tid == 0) {
                         const unsigned old = atomicAdd(&A.slice_cnt[(long long)slot * A.max_units + b], 1u);
-                        sSliceLast = ((old + 1u) % (unsigned)S == 0u) ? 1 : 0;
+                        sSliceLast = ((old + 1u) % (unsigned)nseg == 0u) ? 1 : 0;   // nseg is the same in every half-step of this kind
                         __threadfence();
                     }
                     __syncthreads();
@@ -385,9 +424,9 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                     const int e = lane, w = sW[unit][e];
                     if (w >= 0) {
                         double s = 0.0;
-                        if (WIDE && S > 1) {
-                            const double* part = A.slice_part + (((long long)slot * A.max_units + b) * S) * 32;
-                            for (int x = 0; x < S; x++) s += __ldcg(&part[x * 32 + e]);   // slices in order
+                        if (WIDE && nseg > 1) {
+                            const double* part = A.slice_part + (((long long)slot * A.max_units + b) * AB_ENS_MAXSEG) * 32;
+                            for (int x = 0; x < nseg; x++) s += __ldcg(&part[x * 32 + e]);   // segments in order
                         } else {
                         double pv[EW];                       // independent loads, then the fixed-order sum
 #pragma unroll
@@ -434,7 +473,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 // the proposal lanes own sW.. of their unit: the next prep / gather by the same
                 // lanes follows in program order; sQs / sPart readers are fenced by the two
                 // __syncthreads above and the one that opens grid_arrive / the next gather
-                if (it + (int)gridDim.x < nbatch * S) __syncthreads();
+                __syncthreads();
             }
             long long tb = 0;
             if (A.dbg) { __syncthreads(); tb = clock64(); }
@@ -442,7 +481,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
             {   // random-stream part of the next half-step, overlapped with the barrier
                 int nstep = step, nsp = split + 1;
                 if (nsp >= nsplit) { nstep = step + 1; nsp = 0; }
-                if (nstep < A.nsteps) prep(nstep, nsp, (int)blockIdx.x / (WIDE ? A.nslice : 1));
+                if (nstep < A.nsteps) prep(nstep, nsp, first_unit(nstep, nsp));
             }
             grid_wait(A.barrier, bar_target);
             if (A.dbg && blockIdx.x == 0 && tid == 0) { A.dbg[3] += clock64() - tb; A.dbg[4] += 1; }
@@ -479,21 +518,16 @@ int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
     int G = EW / A.ws;
     int nbatch = (n_half + P * G - 1) / (P * G);
     const int grid_max = per_sm * h->nsm;
-    A.nslice = 1;
-    if (P == 32 && (size_t)need > budget) {
-        // streamed wide unit: split the training points of a unit over S work items when that fills
-        // the SMs more evenly (128 units on 148 SMs leave 14 % idle; 8 x 128 items fill 98.8 %)
-        const int nch = (int)(A.npad / ch);
-        double best = 0.0;
-        for (int sN = 1; sN <= 16 && sN <= nch; sN *= 2) {
-            const long long items = (long long)nbatch * sN;
-            const double eff = (double)items / (double)(((items + grid_max - 1) / grid_max) * grid_max);
-            if (eff > best + 0.02) { best = eff; A.nslice = sN; }
-        }
-    }
-    long long items = (long long)nbatch * A.nslice;
     int grid = grid_max;
-    if (grid > items) grid = (int)items;
+    A.ranged = 0;
+    if (P == 32 && (size_t)need > budget) {
+        // streamed wide unit: equal contiguous ranges of (unit, chunk) pairs per CTA when every CTA
+        // gets at least 4 chunks and no unit is cut into more than AB_ENS_MAXSEG segments
+        const long long nch = A.npad / ch;
+        const long long share = (long long)nbatch * nch / grid_max;
+        if (share >= 4 && nch / share + 2 <= AB_ENS_MAXSEG) A.ranged = 1;
+    }
+    if (!A.ranged && grid > nbatch) grid = nbatch;
     if (grid < 1) grid = 1;
     void* args[] = {(void*)&A};
     ab_prof_begin(h, AB_PROF_ENSEMBLE);
@@ -523,10 +557,10 @@ static int ens_enqueue(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords
     if (!h->have_alpha) { ab_set_error("ab_ensemble_run: targets not set (call ab_gp_set_targets)"); return -2; }
     if (cfg->nwalkers < 2 || cfg->nsteps < 0 || cfg->thin_by < 1) { ab_set_error("bad ensemble configuration"); return -1; }
     // scratch: [0, 4096) barrier word, NaN flag, debug counters; then the completion counters and the
-    // slice sums of split wide units (3 kinds of half-step x units x up to 16 slices x 32 proposals)
+    // segment sums of split wide units (3 kinds of half-step x units x AB_ENS_MAXSEG segments x 32 proposals)
     const int max_units = (cfg->nwalkers + 31) / 32;
     const size_t cnt_bytes = ((size_t)3 * max_units * sizeof(unsigned) + 255) / 256 * 256;
-    const size_t part_bytes = (size_t)3 * max_units * 16 * 32 * sizeof(double);
+    const size_t part_bytes = (size_t)3 * max_units * AB_ENS_MAXSEG * 32 * sizeof(double);
     int rc = ab_ensure_scratch(h, 4096 + cnt_bytes + part_bytes);
     if (rc) return rc;
     EnsArgs A{};
