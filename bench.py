@@ -554,7 +554,7 @@ def main():
                 if traffic is not None else None
         except Exception:  # noqa: BLE001
             traffic = None
-    roofline = {"bound": "tensor", "kernel": "predict_var_kernel (DMMA.8x8x4 GEMM L^-1 x K*), c4: N=8192",
+    roofline = {"bound": "tensor", "kernel": "predict_var_pair_kernel (DMMA.8x8x4 GEMM L^-1 x K*, row-block pairs of a query tile on adjacent CTAs), c4: N=8192",
                 "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
                 "frac_of_nominal_40": achieved / NOMINAL_FP64_TFLOPS, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": q_per_launch * n4 * 8.0 + 4.0 * n4 * n4,
