@@ -94,6 +94,14 @@ SIGNATURES = {
                                       ctypes.POINTER(ctypes.c_int), _P, ctypes.c_int, _P, ctypes.c_int, _P, c_double_p,
                                       ctypes.POINTER(ctypes.c_int), _P, ctypes.c_size_t]),
     "ab_gp_cv_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "ab_nccl_unique_id": (ctypes.c_int, [ctypes.POINTER(ctypes.c_ubyte)]),
+    "ab_nccl_init": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_ubyte),
+                                    ctypes.c_int, _P]),
+    "ab_nccl_destroy": (ctypes.c_int, [_P]),
+    "ab_nccl_sync": (ctypes.c_int, [_P]),
+    "ab_nccl_broadcast": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int]),
+    "ab_nccl_allgather": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64]),
+    "ab_nccl_broadcast_gp": (ctypes.c_int, [_P, _P, ctypes.c_int]),
     "ab_sizeof_nested_config": (ctypes.c_int, []),
     "ab_nested_walk": (ctypes.c_int, [_P, ctypes.POINTER(NestedConfig), _P, _P, _P, _P]),
     "ab_ensemble_run_host": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P, ctypes.c_int]),

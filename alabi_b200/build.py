@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(HERE, "libalabi_b200.so")
-SOURCES = ["api.cu", "cov.cu", "chol.cu", "chol_dataflow.cu", "trsv_dataflow.cu", "append.cu", "grad.cu", "predict.cu", "ensemble.cu", "nested.cu", "cv_batch.cu", "peak.cu"]
+SOURCES = ["api.cu", "cov.cu", "chol.cu", "chol_dataflow.cu", "trsv_dataflow.cu", "append.cu", "grad.cu", "predict.cu", "ensemble.cu", "nested.cu", "cv_batch.cu", "nccl_helpers.cu", "peak.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
            for ln in log.splitlines() if "spill" in ln):
         print("warning: register spills reported by ptxas", file=sys.stderr)
     if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError(f"link failed:\n{p.stdout}\n{p.stderr}")

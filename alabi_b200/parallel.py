@@ -21,7 +21,7 @@ import numpy as np
 
 __all__ = ["init_distributed", "shard_range", "broadcast_gp", "argmin_allgather", "allgather_rows", "allgather_walkers",
            "sharded_predict", "sharded_utility_argmin", "sharded_ensemble", "sharded_restarts",
-           "broadcast_object", "world_size", "sharded_rows"]
+           "broadcast_object", "world_size", "sharded_rows", "NativeComm"]
 
 
 def init_distributed(backend=None):
@@ -57,6 +57,82 @@ def shard_range(m, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class NativeComm:
+    """NCCL communicator owned by libalabi_b200 (``ab_nccl_*``, include/alabi_b200.h): the factor state
+    moves between the handles' own buffers without staging copies and without torch tensors.  The
+    128-byte NCCL id is made on rank 0 and handed to the other ranks through whatever channel the
+    application has — here ``torch.distributed``'s object broadcast, which is only used for that."""
+
+    def __init__(self, device=None):
+        import ctypes
+        import torch
+        from . import _lib
+        dist = _dist()
+        self._lib, self.lib = _lib, _lib.load()
+        self.rank = dist.get_rank() if dist else 0
+        self.world = dist.get_world_size() if dist else 1
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.stream = torch.cuda.current_stream(self.device)
+        idb = (ctypes.c_ubyte * 128)()
+        if self.rank == 0:
+            _lib.check(self.lib.ab_nccl_unique_id(idb), "ab_nccl_unique_id")
+        raw = broadcast_object(bytes(idb), src=0)
+        idb = (ctypes.c_ubyte * 128).from_buffer_copy(raw)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.ab_nccl_init(ctypes.byref(h), self.world, self.rank, idb, self.device,
+                                         ctypes.c_void_p(self.stream.cuda_stream)), "ab_nccl_init")
+        self.h = h
+
+    def broadcast(self, t, root=0):
+        self._lib.check(self.lib.ab_nccl_broadcast(self.h, self._lib.ptr(t), t.numel() * t.element_size(), root), "ab_nccl_broadcast")
+        return t
+
+    def allgather(self, t):
+        import torch
+        t = t.contiguous()
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self._lib.check(self.lib.ab_nccl_allgather(self.h, self._lib.ptr(t), self._lib.ptr(out), t.numel() * t.element_size()),
+                        "ab_nccl_allgather")
+        return out
+
+    def sync(self):
+        self._lib.check(self.lib.ab_nccl_sync(self.h), "ab_nccl_sync")
+
+    def broadcast_gp(self, gp, root=0):
+        """``broadcast_gp`` through the library's own communicator: hyper-parameters, inputs and
+        targets as a pickled object, then L / D^-1 / alpha handle to handle (``ab_nccl_broadcast_gp``)."""
+        meta = None
+        if self.rank == root:
+            meta = dict(vector=gp.get_parameter_vector(include_frozen=True), x=gp._x, y=gp._y, yerr2=gp._yerr2)
+        m = broadcast_object(meta, src=root)
+        if self.rank != root:
+            gp.set_parameter_vector(m["vector"], include_frozen=True)
+            gp._x = gp.parse_samples(m["x"])
+            gp._yerr2 = float(m["yerr2"])
+            gp._inputs_pushed = False
+            gp._mark_dirty()
+            gp._push()
+        self._lib.check(self.lib.ab_nccl_broadcast_gp(self.h, gp._hd.h, root), "ab_nccl_broadcast_gp")
+        if self.rank != root:
+            gp._y = np.ascontiguousarray(np.asarray(m["y"], dtype=np.float64).reshape(-1))
+            gp.computed = True
+            gp._factor_key = gp._spec_key()
+            gp._targets_pushed = True
+            gp._alpha_np = None
+        return gp
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ab_nccl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 def broadcast_gp(gp, x=None, y=None, src=0, stats=None):
     """Make every rank hold the GP trained on ``src``: hyper-parameters, inputs
     and targets travel as a pickled object, L (npad x npad), the diagonal-block inverses and
@@ -84,6 +160,9 @@ def broadcast_gp(gp, x=None, y=None, src=0, stats=None):
         alpha = torch.empty(m["n"], dtype=torch.float64, device=dev)
         Dinv = torch.empty((m["npad"] // 128, 128, 128), dtype=torch.float64, device=dev)
     if on_gpu:
+        if stats is not None:
+            torch.cuda.synchronize()       # timing requested: buffers allocated and exported on every rank first
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     dist.broadcast(L, src=src)

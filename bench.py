@@ -409,8 +409,9 @@ def main():
             info["train_ms"] = (time.perf_counter() - t0) * 1e3
         if world > 1:
             barrier()                      # sets the NCCL communicator up
-            warm = torch.zeros(1 << 20, dtype=torch.float64, device=dev)
-            dist.broadcast(warm, src=0)    # and the broadcast channels, before the timed broadcast
+            warm = torch.zeros(1 << 24, dtype=torch.float64, device=dev)
+            dist.broadcast(warm, src=0)    # and the large-message broadcast channels (128 MB), before the timed broadcast
+            del warm
             barrier()
             st = {}
             par.broadcast_gp(gp, stats=st)
@@ -499,7 +500,14 @@ def main():
     wlo, whi = par.shard_range(WALKERS_TOTAL, rank, world)
     p0 = np.random.default_rng(55).uniform(-1.0, 1.0, size=(WALKERS_TOTAL, d5))
     es = EnsembleSampler(whi - wlo, d5, lp5, seed=99)
-    es.run_mcmc(p0[wlo:whi], 2, store=False, walker_offset=wlo)              # warm-up (module load, L2)
+    # warm-up: the same run and gather once (kernel module, NCCL channels of these sizes, the chain
+    # blocks in torch's caching allocator), results discarded
+    es.run_mcmc(p0[wlo:whi], MCMC_STEPS, store="device", walker_offset=wlo)
+    _w1 = par.allgather_walkers(es.device_chain, WALKERS_TOTAL)
+    _w2 = par.allgather_walkers(es.device_log_prob, WALKERS_TOTAL)
+    del _w1, _w2
+    es.device_chain = es.device_log_prob = None
+    es._device_rows_pending = False
     barrier()
     mc_launch0 = lib.ab_launch_counter()
     m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

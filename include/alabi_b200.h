@@ -249,6 +249,26 @@ int ab_sizeof_nested_config(void);
 int ab_nested_walk(ab_gp* h, const ab_nested_config* cfg, double* d_u, double* d_logl, double* d_theta,
                    int* d_naccept);
 
+/* ---- NCCL helpers: one process per GPU; the factor is trained once and
+ *      broadcast over NVLink, argmin records and chain blocks are all_gathered.  The reference has
+ *      no counterpart (its parallelism is multiprocessing pools, alabi/core.py:309-314).  NCCL is
+ *      resolved at run time (dlopen of libnccl.so.2, e.g. the copy PyTorch already loaded); without
+ *      it the calls return -6.  A communicator is bound to one device and one stream; calls are
+ *      asynchronous on that stream except where stated. ---- */
+#define AB_NCCL_ID_BYTES 128
+typedef struct ab_comm ab_comm;
+int ab_nccl_unique_id(unsigned char* h_id /* AB_NCCL_ID_BYTES, made on one rank and handed to all */);
+int ab_nccl_init(ab_comm** out, int world, int rank, const unsigned char* h_id, int device, void* cuda_stream);
+int ab_nccl_destroy(ab_comm* c);
+int ab_nccl_sync(ab_comm* c);                                         /* waits for the communicator's stream */
+int ab_nccl_broadcast(ab_comm* c, void* d_buf, int64_t nbytes, int root);
+int ab_nccl_allgather(ab_comm* c, const void* d_send, void* d_recv /* world x nbytes_per_rank */, int64_t nbytes_per_rank);
+/* factor state (L, diagonal-block inverses, log-determinant parts, alpha) of the trained handle of
+ * rank `root` into the handles of all ranks, in place, no staging copies; every rank must have set
+ * the same inputs and hyper-parameters (ab_gp_set_inputs / ab_gp_set_kernel).  Returns after the
+ * transfer has completed. */
+int ab_nccl_broadcast_gp(ab_comm* c, ab_gp* h, int root);
+
 /* k-fold cross-validation of hyper-parameter candidates as one batched job
  * (gp_utils.optimize_gp_kfold_cv and its per-candidate worker, alabi/gp_utils.py:511-637, 640-1231;
  * the default hyper-parameter search of init_gp, alabi/core.py:751).  Job b = (candidate

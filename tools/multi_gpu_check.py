@@ -62,6 +62,23 @@ ref = EnsembleSampler(hi - lo, d, lp, seed=5)
 ref.run_mcmc(p0[lo:hi], steps, walker_offset=lo)
 out["ensemble_reproducible"] = bool(np.array_equal(ref.get_chain(), s.get_chain()))
 
+# the library's own NCCL communicator (ab_nccl_*): factor state handle to handle, all_gather of records
+if world > 1:
+    comm = par.NativeComm()
+    gp2 = mk()
+    if rank == 0:
+        gp2.compute(X)
+        gp2._set_targets(y)
+    comm.broadcast_gp(gp2)
+    mu_n, var_n = gp2.predict(y, xq[:5000], return_var=True)
+    out["native_broadcast_identical"] = bool(torch.equal(mu_n, mu_1[:5000]) and torch.equal(var_n, var_1[:5000]))
+    rec = torch.tensor([float(rank), 10.0 * rank + 1.0], dtype=torch.float64, device=dev)
+    got = comm.allgather(rec)
+    comm.sync()
+    want = torch.tensor([[float(r), 10.0 * r + 1.0] for r in range(world)], dtype=torch.float64, device=dev)
+    out["native_allgather"] = bool(torch.equal(got, want))
+    comm.close()
+
 flags = torch.tensor([float(all(v for k, v in out.items() if k != "world"))], device=dev)
 if world > 1:
     torch.distributed.all_reduce(flags, op=torch.distributed.ReduceOp.MIN)
