@@ -273,7 +273,7 @@ def kernel_table(lib, dmma_peak_tflops):
     return out
 
 
-def c2_extra(lib, steps=5):
+def c2_extra(lib, steps=5, fma_peak_tflops=None):
     """Round 1's headline configuration (c2: 2-D shells, Matern-3/2, N = 1000), one GPU: predict
     mean+var points/s (device-resident and through GP.predict on host buffers), the sampler
     (1000 walkers x 5000 steps) device-timed and end to end, and one-point call latencies."""
@@ -343,6 +343,11 @@ def c2_extra(lib, steps=5):
             "mcmc_walker_steps_per_s": mc_dev, "mcmc_e2e_walker_steps_per_s": mc_e2e,
             "mcmc_shape": f"{nw} walkers x {ns} steps, chain and log-prob delivered to host ({ns * nw * 3 * 8} B)",
             "sampler_flops_per_walker_step": 1000.0 * (3 * 2 + 35 + 2) + 12,
+            "mcmc_roofline": {"bound": "latency (two grid barriers and two dependent L2 round trips per half-step, DESIGN.md "
+                                       "section 3); against the FP64 FMA roof for reference",
+                              "achieved": mc_dev * (1000.0 * (3 * 2 + 35 + 2) + 12) * 1e-12, "peak": fma_peak_tflops,
+                              "unit": "TFLOP/s",
+                              "frac": (mc_dev * (1000.0 * (3 * 2 + 35 + 2) + 12) * 1e-12 / fma_peak_tflops) if fma_peak_tflops else None},
             "one_point_calls": one}
 
 
@@ -591,7 +596,7 @@ def main():
         gp5 = lp5 = es = None
         torch.cuda.empty_cache()
         kernels = kernel_table(lib, peak.value)
-        extra = {"c2": c2_extra(lib)}
+        extra = {"c2": c2_extra(lib, fma_peak_tflops=fma_peak.value)}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
