@@ -147,3 +147,60 @@ def test_sampler_proposals_per_unit_variants_replay():
     ref, _, _, _ = oem.replay_device_chain(p0, lp_o, 25, 21)
     for c in chains:
         assert np.allclose(c, ref, rtol=1e-9, atol=1e-12)
+
+
+def test_round2_paths_at_their_smallest_sizes():
+    """The round-2 device paths on degenerate shapes: batched CV with ragged folds that straddle a
+    128-row padding boundary and a one-block factor; nested walks in one dimension; a wide streamed
+    sampler whose (unit, chunk) ranges cut units in the middle with thinning."""
+    import alabi_b200 as ab
+    from alabi_b200.ensemble import EnsembleSampler, SurrogateLogProb
+    from alabi_b200.nested import DeviceWalker
+    from oracle import nested as onest
+    rng = np.random.default_rng(9)
+    # (1) CV: n = 161, 5 folds of 33 / 32 rows -> 128 or 129 training rows (one or two 128-blocks)
+    n, d = 161, 2
+    X = rng.uniform(-1, 1, size=(n, d))
+    y = np.cos(2 * X[:, 0]) + X[:, 1]
+    o, g = _pair("ExpSquaredKernel", X, y, np.array([0.1, 0.3]), wn=-8.0)
+    base = g.get_parameter_vector()
+    idx = rng.permutation(n)
+    folds = [(np.sort(np.setdiff1d(idx, f)), np.sort(f)) for f in np.array_split(idx, 5)]
+    preds, lls, st = g.cv_batch(X, y, np.array([base, base + 0.1]), folds * 2)
+    assert np.all(st == 0) and len(preds) == 10
+    for b, (tr, va) in enumerate(folds * 2):
+        oc = ogp.make_gp("ExpSquaredKernel", X[tr], y[tr], np.zeros(d), amp=1.0, compute=False)
+        oc.set_parameter_vector(base + (0.1 if b >= 5 else 0.0))
+        oc.compute(X[tr])
+        assert abs(lls[b] - oc.log_likelihood(y[tr])) <= 1e-9 * abs(oc.log_likelihood(y[tr]))
+        np.testing.assert_allclose(preds[b], oc.predict(y[tr], X[va]), rtol=1e-8, atol=1e-9)
+    # (2) nested walk in one dimension
+    X1 = rng.uniform(-2, 2, size=(60, 1))
+    y1 = -0.5 * (X1[:, 0] / 0.5) ** 2
+    o1, g1 = _pair("Matern52Kernel", X1, y1, np.array([0.0]), wn=-8.0)
+    b1 = np.array([(-2.0, 2.0)])
+    w = DeviceWalker(SurrogateLogProb(g1, y1, b1), b1, seed=5)
+    u0 = rng.uniform(0.3, 0.7, size=(9, 1))
+    th0 = w.transform(u0)
+    l0 = o1.predict(y1, th0)
+    cnt = w.counter
+    u, th, ll, acc = w.walk(u0, th0, l0, float(np.min(l0)) - 1.0, 0.5, np.array([[0.2]]), 7)
+    ur, thr, llr, nacc, margin = onest.replay_walk(u0, th0, l0, float(np.min(l0)) - 1.0, 0.5, np.array([[0.2]]), 7, 5, cnt,
+                                                   w.transform, lambda t: o1.predict(y1, t))
+    np.testing.assert_allclose(u, ur, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(ll, llr, rtol=1e-9, atol=1e-9)
+    # (3) wide streamed sampler, ranges cutting units, thinning: continuing a run reproduces the long run
+    n3, d3, nw = 5000, 16, 4736
+    X3 = rng.uniform(-1, 1, size=(n3, d3))
+    y3 = -0.5 * np.sum((X3 / 0.6) ** 2, axis=1)
+    o3, g3 = _pair("ExpSquaredKernel", X3, y3, np.full(d3, 0.5), wn=-8.0)
+    lp = SurrogateLogProb(g3, y3, [(-1.0, 1.0)] * d3)
+    p0 = rng.uniform(-0.5, 0.5, size=(nw, d3))
+    s = EnsembleSampler(nw, d3, lp, seed=3)
+    s.run_mcmc(p0, 3, thin_by=2)
+    s2 = EnsembleSampler(nw, d3, lp, seed=3)
+    s2.run_mcmc(p0, 1, thin_by=2)
+    s2.run_mcmc(None, 2, thin_by=2)
+    np.testing.assert_array_equal(s.get_chain(), s2.get_chain())
+    lp_last = o3.predict(y3, s.get_chain()[-1][:200])
+    np.testing.assert_allclose(s.get_log_prob()[-1][:200], lp_last, rtol=1e-9, atol=1e-9)
