@@ -108,12 +108,15 @@ __device__ __forceinline__ void grid_wait(unsigned long long* counter, unsigned 
     __syncthreads();
 }
 
-template <int KIND, int D, int EW, int P>
+// CHT > 0: the chunk length is a compile-time constant (the streamed wide unit at 512 points per
+// chunk): the shared-memory row addresses bX[k * CH + j] of the inner loop become immediate offsets
+// instead of one integer multiply-add per dimension and point pair.  CHT = 0: run-time A.ch.
+template <int KIND, int D, int EW, int P, int CHT = 0>
 __global__ void __launch_bounds__(EW * 32, (P == 32 && EW == 8) ? 2 : 1)
 ensemble_kernel(const __grid_constant__ EnsArgs A) {
     constexpr int ETHREADS = EW * 32;
     extern __shared__ __align__(16) double sm[];
-    const int CH = A.ch;
+    const int CH = CHT > 0 ? CHT : A.ch;
     double* sX = sm;                 // [D][CH]
     double* sAl = sm + D * CH;       // [CH]
     // P proposals per unit (2: small ensembles, more units; 4: large ensembles, each
@@ -492,7 +495,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
 template <int KIND, int D, int P, int EW = 8>
 int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
     constexpr int ETHREADS = EW * 32;
-    auto kern = ensemble_kernel<KIND, D, EW, P>;
+    void (*kern)(const EnsArgs) = ensemble_kernel<KIND, D, EW, P>;
     // shared memory: resident when the whole training set fits, else two chunk buffers
     const size_t budget = 160 * 1024;
     long long need = (long long)A.n * (D + 1) * 8;
@@ -511,6 +514,9 @@ int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
         smem = 2 * (size_t)ch * (D + 1) * 8;
     }
     A.ch = ch;
+    if constexpr (P == 32 && EW == 16) {
+        if ((size_t)need > budget && ch == 512) kern = ensemble_kernel<KIND, D, EW, P, 512>;
+    }
     AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     AB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ETHREADS, smem));
