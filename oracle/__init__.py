@@ -20,4 +20,14 @@ Parity status
   **parity unpinned** for these two modules.  They are anchored on the
   reference's call sites (cited per function) and on self-consistency checks
   (finite differences, closed forms, detailed balance); see DESIGN.md.
+  ``tests/test_reference_packages.py`` compares them with george / emcee /
+  dynesty themselves wherever those packages can be imported (it skips here).
+* ``oracle.nested`` replays the device's constrained random walks (dynesty's
+  ``rwalk`` replacement step; dynesty unpinned and not installed): **parity
+  unpinned** against dynesty, draw layout restated from include/alabi_b200.h.
+* The MATHEMATICS of the benchmarked configurations c1-c4 (kernel matrix,
+  Cholesky, alpha, log-likelihood, mean, variance) is additionally pinned by
+  extended-precision references (``tests/golden/make_extended.py`` ->
+  ``tests/golden/extended_c*.npz``), against which both this oracle and the
+  device path are measured.
 """
