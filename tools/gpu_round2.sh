@@ -17,5 +17,7 @@ python tools/prof_headline.py > gpurun_out/prof_plain.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'predict_var|ensemble_kernel|predict_mean_kernel' -o gpurun_out/prof_headline -f python tools/prof_headline.py > gpurun_out/ncu_full.log 2>&1
 echo "full exit $?"
 ncu -i gpurun_out/prof_headline.ncu-rep --page raw --csv > gpurun_out/prof_headline_raw.csv 2> gpurun_out/prof_raw.err
+# gpurun copies back at most 64 MiB: the report itself stays on the box when it is large, its raw page travels
+if [ $(stat -c %s gpurun_out/prof_headline.ncu-rep) -gt 30000000 ]; then rm gpurun_out/prof_headline.ncu-rep; fi
 ls -la gpurun_out | tail -15
 tail -n 3 gpurun_out/ncu_launch.log; tail -n 3 gpurun_out/ncu_full.log

@@ -41,7 +41,9 @@ if os.path.exists(launch_csv):
     print(open(os.path.join(out_dir, f"{tag}_launches.txt")).read())
 
 if rep and os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep, or its raw page already exported as csv (the report itself may be too large to bring back)
+    raw = open(rep).read() if rep.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     keep = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
