@@ -27,7 +27,7 @@ class EnsembleConfig(ctypes.Structure):
                 ("walker_offset", ctypes.c_int64), ("y_scale", ctypes.c_double), ("y_offset", ctypes.c_double),
                 ("lo", ctypes.c_double * MAX_DIM), ("hi", ctypes.c_double * MAX_DIM),
                 ("theta_scale", ctypes.c_double * MAX_DIM), ("theta_offset", ctypes.c_double * MAX_DIM),
-                ("use_normal_prior", ctypes.c_int), ("reserved2", ctypes.c_int),
+                ("use_normal_prior", ctypes.c_int), ("schedule", ctypes.c_int),
                 ("prior_mu", ctypes.c_double * MAX_DIM), ("prior_sd", ctypes.c_double * MAX_DIM)]
 
 

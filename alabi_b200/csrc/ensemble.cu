@@ -24,9 +24,15 @@
 #include "handle.h"
 #include "alabi_b200.h"
 
+#define AB_ENS_RING 32             // versions of a walker's position the dataflow schedule keeps
+#define AB_ENS_THROTTLE 15         // steps between its (non-blocking) progress barriers: 2 * 15 + 1 <= 32
 #define AB_ENS_MAXSEG 64           // segments a streamed wide unit may be cut into (ranged schedule)
 #ifndef AB_ENS_WIDE_UNROLL
 #define AB_ENS_WIDE_UNROLL 2      // point pairs per iteration of the wide unit's inner loop (1 and 4 measured: tools/ens_variants.sh)
+#endif
+
+#ifndef AB_ENS_WARP_RING
+#define AB_ENS_WARP_RING 1        // streamed wide unit: 1 = a private cp.async ring per warp (no CTA barrier per chunk), 0 = one ring per CTA
 #endif
 
 namespace {
@@ -52,6 +58,9 @@ struct EnsArgs {
     // segment sums meet in slice_part (fixed segment order), completions are counted in slice_cnt.
     int ranged, max_units;
     double* slice_part; unsigned* slice_cnt;
+    // dataflow schedule (FLOW kernels): ring of AB_ENS_RING versions of every walker's position,
+    // one 16-byte line {lo, flag, hi, flag} per coordinate, flag = version + 1 (0 = never written)
+    uint4* ring;
     double a;
     unsigned seed_lo, seed_hi;
     long long first_step, walker_offset;
@@ -91,30 +100,55 @@ __device__ __forceinline__ int member_of(const EnsArgs& A, int i, int s, unsigne
 // grid barrier split in two: arrive as soon as this CTA's updates are published,
 // wait only when the next half-step needs the other CTAs' updates.  Release / acquire
 // on the counter itself orders the walker updates (no separate fences).
-__device__ __forceinline__ void grid_arrive(unsigned long long* counter, unsigned long long& target) {
-    __syncthreads();
+template <class Sync>
+__device__ __forceinline__ void grid_arrive(unsigned long long* counter, unsigned long long& target, Sync csync) {
+    csync();
     if (threadIdx.x == 0) {
         target += gridDim.x;
         asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(counter), "l"(1ULL) : "memory");
     }
 }
-__device__ __forceinline__ void grid_wait(unsigned long long* counter, unsigned long long target) {
+template <class Sync>
+__device__ __forceinline__ void grid_wait(unsigned long long* counter, unsigned long long target, Sync csync) {
     if (threadIdx.x == 0) {
         unsigned long long v;
         do {
             asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
         } while (v < target);
     }
-    __syncthreads();
+    csync();
 }
 
 // CHT > 0: the chunk length is a compile-time constant (the streamed wide unit at 512 points per
 // chunk): the shared-memory row addresses bX[k * CH + j] of the inner loop become immediate offsets
 // instead of one integer multiply-add per dimension and point pair.  CHT = 0: run-time A.ch.
-template <int KIND, int D, int EW, int P, int CHT = 0>
-__global__ void __launch_bounds__(EW * 32, (P == 32 && EW == 8) ? 2 : 1)
+//
+// FLOW (small ensembles, resident training set): the grid barrier between half-steps is replaced
+// by dataflow on the one remote input of a proposal, its partner's position.  The pair (2i, 2i+1)
+// is always updated by the same lanes of the same CTA, so a walker's own state is ordered by
+// program order; the partner is read from a ring of versioned records that the updating lane
+// publishes with its accept decision: one 16-byte line {lo, flag, hi, flag} per coordinate
+// (8-byte halves are single-copy atomic, so a line whose two flags carry the wanted version holds
+// that version's value: the data IS the signal, one L2 round trip instead of counter + poll +
+// load).  Version v of walker w (its position after v steps) lives in slot v mod AB_ENS_RING; a
+// half-step (t, 0) reads version t of its partner, (t, 1) version t + 1 -- exactly the positions
+// the barrier schedule reads, so the chain has identical bits.  A progress barrier every
+// AB_ENS_THROTTLE steps, arrived at once and waited for one period later, keeps any two CTAs less
+// than 2 * AB_ENS_THROTTLE steps apart, so a slot is never overwritten while a reader needs it.
+//
+// Small units (P = 2 or 4) carry one extra warp, the PREP warp: it draws the random-stream part
+// (walker, partner, stretch factor, accept threshold: three Philox blocks and two logarithms, ~1 us
+// as a serial chain) of the CTA's work items TWO items ahead of the EW compute warps, into a ring of
+// three buffers, so that chain never sits between a half-step's accept and the next gather and has a
+// whole item period to finish, however short the kernel evaluations are.  The compute warps
+// synchronise among themselves on named barrier 1; barrier 2 (all warps) opens every work item: the
+// prep warp arrives there with the item's buffer filled.
+template <int KIND, int D, int EW, int P, int CHT = 0, bool FLOW = false>
+__global__ void __launch_bounds__(EW * 32 + (P == 32 ? 0 : 32), ((P == 32 && EW == 8) || EW == 4) ? 2 : 1)
 ensemble_kernel(const __grid_constant__ EnsArgs A) {
-    constexpr int ETHREADS = EW * 32;
+    constexpr int ETHREADS = EW * 32;               // compute threads
+    constexpr bool PW = (P != 32);                  // prep warp present (warp EW)
+    constexpr int ATHREADS = ETHREADS + (PW ? 32 : 0);
     extern __shared__ __align__(16) double sm[];
     const int CH = CHT > 0 ? CHT : A.ch;
     double* sX = sm;                 // [D][CH]
@@ -128,14 +162,24 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
     constexpr int NU = WIDE ? 1 : EW;            // units per CTA the per-unit arrays must hold
     __shared__ double sQ[NU][P][D], sQs[NU][P][D];
     __shared__ double sS[NU][P][D];              // current position of the walker being updated
-    __shared__ double sPart[EW][P], sLogZ[NU][P], sLogU[NU][P], sLps[NU][P], sZZ[NU][P];
-    __shared__ int sW[NU][P], sInside[NU][P], sPartner[NU][P];
+    constexpr int NPB = PW ? 3 : 1;               // prep buffers
+    __shared__ double sPart[EW][P], sLogZ[NPB][NU][P], sLogU[NPB][NU][P], sLps[NU][P], sZZ[NPB][NU][P];
+    __shared__ int sW[NPB][NU][P], sInside[NU][P], sPartner[NPB][NU][P];
     __shared__ double sPrior[NU][P];             // ln of the normal part of the prior at the proposal
     __shared__ int sSliceLast;                   // split units: this CTA delivered the last slice of its unit
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int WS = A.ws, G = EW / WS;
-    const int unit = warp / WS, wiu = warp - unit * WS;
+    const bool is_prep = PW && warp == EW;
+    // barrier among the compute warps (the prep warp runs on its own clock)
+    auto csync = [&]() {
+        if constexpr (PW) asm volatile("bar.sync 1, %0;" ::"r"(ETHREADS) : "memory");
+        else __syncthreads();
+    };
+    auto item_sync = [&]() {                     // opens a work item: compute warps + prep warp
+        if constexpr (PW) asm volatile("bar.sync 2, %0;" ::"r"(ATHREADS) : "memory");
+    };
+    const int unit = is_prep ? 0 : warp / WS, wiu = is_prep ? -1 : warp - unit * WS;   // (the prep warp leaves before the item loop)
     const int d = A.d, nw = A.nwalkers;
     const bool resident = A.n <= CH;
     const bool prop_lane = (wiu == 0 && lane < P);
@@ -143,18 +187,18 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
 
     // resident: the whole training set (rows >= n zero-filled) is loaded once
     auto load_resident = [&]() {
-        for (int idx = tid; idx < D * CH; idx += ETHREADS) {
+        for (int idx = tid; idx < D * CH; idx += ATHREADS) {
             int k = idx / CH, jj = idx - k * CH;
             sX[idx] = (k < d && jj < A.n) ? A.XsT[(long long)k * A.npad + jj] : 0.0;
         }
-        for (int jj = tid; jj < CH; jj += ETHREADS) sAl[jj] = (jj < A.n) ? A.alpha[jj] : 0.0;
+        for (int jj = tid; jj < CH; jj += ATHREADS) sAl[jj] = (jj < A.n) ? A.alpha[jj] : 0.0;
     };
     // streamed: chunks of CH points (CH divides npad; padding rows of XsT and alpha
     // are zero) through a double-buffered cp.async ring: buffer = [D][CH] + [CH]
     const int BUF = (D + 1) * CH;
     auto issue_chunk = [&](long long c0, int buf) {
         double* bX = sm + buf * BUF;
-        for (int idx = tid; idx < (D + 1) * (CH / 2); idx += ETHREADS) {
+        for (int idx = tid; idx < (D + 1) * (CH / 2) && !is_prep; idx += ETHREADS) {
             int k = idx / (CH / 2), j2 = (idx - k * (CH / 2)) * 2;
             const double* src = (k < D) ? ((k < d) ? A.XsT + (long long)k * A.npad + c0 + j2 : nullptr)
                                         : A.alpha + c0 + j2;
@@ -169,13 +213,23 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (resident) { load_resident(); __syncthreads(); }
+    unsigned long long flow_prev_target = 0;
+    bool flow_have_prev = false;
+    if constexpr (FLOW) {
+        // version 0 = the initial positions (the log-prob pass of step -1 does not move them)
+        for (long long idx = (long long)blockIdx.x * ATHREADS + tid; idx < (long long)nw * d; idx += (long long)gridDim.x * ATHREADS) {
+            const double v = A.coords[idx];
+            const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+            asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(A.ring + idx), "r"(lo), "r"(1u), "r"(hi), "r"(1u) : "memory");
+        }
+    }
 
     // Everything of a proposal that depends on the random stream only (which walker,
     // which partner, the stretch factor, the accept threshold): computed by the
     // proposal lanes BEFORE they wait on the grid barrier of the previous half-step.
-    auto prep = [&](int step, int split, int b) {
-        if (!prop_lane) return;
-        const int e = lane, item = (b * G + unit) * P + e;
+    // (u, e): unit and proposal slot the calling lane prepares, pb: prep buffer it writes
+    auto prep_to = [&](int step, int split, int b, int u, int e, int pb) {
+        const int item = (b * G + u) * P + e;
         const int n_items = (step < 0) ? nw : (split == 0 ? (nw + 1) / 2 : nw / 2);
         const int n_other = (split == 0) ? nw / 2 : (nw + 1) / 2;
         int w = -1, partner = -1;
@@ -200,8 +254,28 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 }
             }
         }
-        sW[unit][e] = w; sPartner[unit][e] = partner; sZZ[unit][e] = zz; sLogZ[unit][e] = logz; sLogU[unit][e] = logu;
+        sW[pb][u][e] = w; sPartner[pb][u][e] = partner; sZZ[pb][u][e] = zz; sLogZ[pb][u][e] = logz; sLogU[pb][u][e] = logu;
     };
+    // wide unit: every proposal lane prepares its own slot in place
+    auto prep = [&](int step, int split, int b) {
+        if (prop_lane) prep_to(step, split, b, unit, lane, 0);
+    };
+    // small units: the prep warp's lane l serves slot (l / P, l % P) of the CTA's work item `b` of (step, split)
+    auto prep_warp = [&](int step, int split, int b, int pb) {
+        if (is_prep && lane < G * P) prep_to(step, split, b, lane / P, lane % P, pb);
+    };
+    // the work item of this CTA that follows item `it` of half-step (step, split); false: none left
+    auto next_item = [&](int& step, int& split, int& it) -> bool {
+        it += gridDim.x;
+        for (;;) {
+            if (step >= A.nsteps) return false;
+            const int n_items = (step < 0) ? nw : (split == 0 ? (nw + 1) / 2 : nw / 2);
+            if (it < (n_items + P * G - 1) / (P * G)) return true;
+            if (step < 0 || split == 1) { step++; split = 0; } else split = 1;
+            it = blockIdx.x;
+        }
+    };
+    int pbuf = 0;                                    // prep buffer of the current work item
 
     const int first = A.init_logp ? -1 : 0;
     // contiguous ranges of (unit, chunk) pairs: CTA c owns [c W / G, (c + 1) W / G)
@@ -220,7 +294,31 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
         const int nchunks = (int)(A.npad / CH);
         return (int)(range_begin((long long)nbatch * nchunks, blockIdx.x) / nchunks);
     };
-    if (first < A.nsteps) prep(first, 0, first_unit(first, 0));
+    if constexpr (PW) {
+        if (is_prep) {
+            // the prep warp's whole life: stay two work items ahead of the compute warps
+            int s0 = first, p0 = 0, i0 = (int)blockIdx.x - (int)gridDim.x;
+            bool more = next_item(s0, p0, i0);
+            int prepared = 0, opened = 0;
+            for (int a2 = 0; a2 < 2 && more; a2++) {
+                prep_warp(s0, p0, i0, prepared % 3);
+                prepared++;
+                more = next_item(s0, p0, i0);
+            }
+            while (opened < prepared) {
+                item_sync();                          // item `opened` starts: its buffer is complete
+                opened++;
+                if (more) {                           // buffer (opened + 1) % 3 was last read by item opened - 2
+                    prep_warp(s0, p0, i0, prepared % 3);
+                    prepared++;
+                    more = next_item(s0, p0, i0);
+                }
+            }
+            return;
+        }
+    } else {
+        if (first < A.nsteps) prep(first, 0, first_unit(first, 0));
+    }
     for (int step = first; step < A.nsteps; step++) {
         const int nsplit = (step < 0) ? 1 : 2;
         // row of the stored chain this step writes (-1: not stored)
@@ -256,23 +354,46 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 }
                 long long t0 = 0, t1 = 0, t2 = 0;
                 if (A.dbg) t0 = clock64();
-                if (!first_seg) prep(step, split, b);                // further units of this CTA: inline
+                if (!PW && !first_seg) prep(step, split, b);         // wide: further units of this CTA inline
                 first_seg = false;
+                item_sync();                                         // small units: this item's prep buffer is complete
                 // ---- gather (proposal lanes): own state and partner position, proposal ----
                 if (prop_lane) {
-                    const int e = lane, w = sW[unit][e], partner = sPartner[unit][e];
+                    const int e = lane, w = sW[pbuf][unit][e], partner = sPartner[pbuf][unit][e];
                     int inside = 1;
                     if (w >= 0) {
                         // all global loads first (one L2 round trip), then the arithmetic
                         double cs[D], ss[D];
                         const long long ow = (long long)w * d, op = (long long)(partner >= 0 ? partner : w) * d;
+                        const bool from_ring = FLOW && step >= 0 && partner >= 0;
 #pragma unroll
                         for (int k = 0; k < D; k++) {
                             ss[k] = (k < d) ? __ldcg(&A.coords[ow + k]) : 0.0;
-                            cs[k] = (k < d) ? __ldcg(&A.coords[op + k]) : 0.0;
+                            cs[k] = (k < d && !from_ring) ? __ldcg(&A.coords[op + k]) : 0.0;
                         }
                         if (step >= 0) sLps[unit][e] = __ldcg(&A.logp[w]);
-                        const double zz = sZZ[unit][e];
+                        if constexpr (FLOW) {
+                            if (from_ring) {
+                                // partner's position after `step` (split 0) or `step + 1` (split 1) updates
+                                const unsigned need = (unsigned)step + (split == 0 ? 1u : 2u);
+                                const uint4* line = A.ring + ((long long)((need - 1u) % AB_ENS_RING) * nw + partner) * d;
+                                bool ok;
+                                do {
+                                    ok = true;
+#pragma unroll
+                                    for (int k = 0; k < D; k++) {
+                                        if (k < d) {
+                                            unsigned x0, x1, x2, x3;
+                                            asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                                         : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "l"(line + k) : "memory");
+                                            ok = ok && (x1 == need) && (x3 == need);
+                                            cs[k] = __hiloint2double((int)x2, (int)x0);
+                                        }
+                                    }
+                                } while (!ok);
+                            }
+                        }
+                        const double zz = sZZ[pbuf][unit][e];
                         if (step >= 0 && partner < 0) inside = -1;      // no complementary walker: keep the state
 #pragma unroll
                         for (int k = 0; k < D; k++) {
@@ -302,7 +423,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                     for (int k = (w < 0 ? 0 : d); k < D; k++) { sQ[unit][e][k] = 0.0; sQs[unit][e][k] = 0.0; }
                     sInside[unit][e] = inside;
                 }
-                __syncthreads();
+                csync();
                 if (A.dbg) t1 = clock64();
                 // ---- surrogate mean of the two proposals of this unit ------------
                 if constexpr (WIDE) {
@@ -339,16 +460,50 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                     if (resident) {
                         eval_wide(sX, sAl, CH);
                     } else {
+                        // every warp streams ITS slice of a chunk (the CH / EW points it evaluates) through
+                        // its own two-deep cp.async ring: no CTA barrier in the chunk loop, a warp that
+                        // falls behind delays nobody
+                        const int per = CH / EW, j0 = warp * per;
+                        auto issue_slice = [&](long long c0, int buf) {
+                            double* bX = sm + buf * BUF + j0;
+                            for (int idx = lane; idx < (D + 1) * (per / 2); idx += 32) {
+                                const int k = idx / (per / 2), j2 = (idx - k * (per / 2)) * 2;
+                                const double* src = (k < D) ? ((k < d) ? A.XsT + (long long)k * A.npad + c0 + j0 + j2 : nullptr)
+                                                            : A.alpha + c0 + j0 + j2;
+                                double* dst = bX + k * CH + j2;
+                                if (src) {
+                                    unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+                                } else {
+                                    dst[0] = 0.0; dst[1] = 0.0;
+                                }
+                            }
+                            asm volatile("cp.async.commit_group;" ::: "memory");
+                        };
+#if AB_ENS_WARP_RING
+                        if (c_lo < c_hi) issue_slice((long long)c_lo * CH, 0);
+                        for (int c = c_lo; c < c_hi; c++) {
+                            if (c + 1 < c_hi) issue_slice((long long)(c + 1) * CH, (c + 1 - c_lo) & 1);
+                            else asm volatile("cp.async.commit_group;" ::: "memory");
+                            asm volatile("cp.async.wait_group 1;" ::: "memory");
+                            __syncwarp();
+                            const double* bX = sm + ((c - c_lo) & 1) * BUF;
+                            eval_wide(bX, bX + D * CH, CH);
+                            __syncwarp();
+                        }
+#else
+                        (void)issue_slice;
                         if (c_lo < c_hi) issue_chunk((long long)c_lo * CH, 0);
                         for (int c = c_lo; c < c_hi; c++) {
                             if (c + 1 < c_hi) issue_chunk((long long)(c + 1) * CH, (c + 1 - c_lo) & 1);
                             else asm volatile("cp.async.commit_group;" ::: "memory");
                             asm volatile("cp.async.wait_group 1;" ::: "memory");
-                            __syncthreads();
+                            csync();
                             const double* bX = sm + ((c - c_lo) & 1) * BUF;
                             eval_wide(bX, bX + D * CH, CH);
-                            __syncthreads();
+                            csync();
                         }
+#endif
                     }
                     sPart[warp][lane] = accw;
                 } else {
@@ -388,10 +543,10 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                         if (c + 1 < nch) issue_chunk((long long)(c + 1) * CH, (c + 1) & 1);
                         else asm volatile("cp.async.commit_group;" ::: "memory");
                         asm volatile("cp.async.wait_group 1;" ::: "memory");
-                        __syncthreads();
+                        csync();
                         const double* bX = sm + (c & 1) * BUF;
                         eval_points(bX, bX + D * CH, CH);
-                        __syncthreads();             // buffer c & 1 is refilled by chunk c + 2
+                        csync();             // buffer c & 1 is refilled by chunk c + 2
                     }
                 }
 #pragma unroll
@@ -400,7 +555,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                     if (lane == 0) sPart[warp][e] = acc[e];
                 }
                 }
-                __syncthreads();
+                csync();
                 if (A.dbg) t2 = clock64();
                 // ---- split units: publish this slice's sums; the CTA that completes the unit goes on ----
                 bool finisher = true;
@@ -413,18 +568,18 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                         __stcg(&part[seg * 32 + lane], sp);
                     }
                     __threadfence();
-                    __syncthreads();
+                    csync();
                     if (tid == 0) {
                         const unsigned old = atomicAdd(&A.slice_cnt[(long long)slot * A.max_units + b], 1u);
                         sSliceLast = ((old + 1u) % (unsigned)nseg == 0u) ? 1 : 0;   // nseg is the same in every half-step of this kind
                         __threadfence();
                     }
-                    __syncthreads();
+                    csync();
                     finisher = sSliceLast != 0;
                 }
                 // ---- accept / reject ------------------------------------------------
                 if (prop_lane && finisher) {
-                    const int e = lane, w = sW[unit][e];
+                    const int e = lane, w = sW[pbuf][unit][e];
                     if (w >= 0) {
                         double s = 0.0;
                         if (WIDE && nseg > 1) {
@@ -448,7 +603,17 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                             A.logp[w] = lp_q;
                         } else {
                             double lp_s = sLps[unit][e];
-                            bool acc = (inside >= 0) && ((sLogZ[unit][e] + lp_q - lp_s) > sLogU[unit][e]);
+                            bool acc = (inside >= 0) && ((sLogZ[pbuf][unit][e] + lp_q - lp_s) > sLogU[pbuf][unit][e]);
+                            if constexpr (FLOW) {
+                                // the record other CTAs wait for goes out before anything else
+                                const unsigned fl = (unsigned)step + 2u;
+                                uint4* line = A.ring + ((long long)((fl - 1u) % AB_ENS_RING) * nw + w) * d;
+                                for (int k = 0; k < d; k++) {
+                                    const double v = acc ? sQ[unit][e][k] : sS[unit][e][k];
+                                    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line + k),
+                                                 "r"((unsigned)__double2loint(v)), "r"(fl), "r"((unsigned)__double2hiint(v)), "r"(fl) : "memory");
+                                }
+                            }
                             if (acc) {
                                 for (int k = 0; k < d; k++) A.coords[(long long)w * d + k] = sQ[unit][e][k];
                                 A.logp[w] = lp_q;
@@ -473,28 +638,41 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                     long long t3 = clock64();
                     A.dbg[0] += t1 - t0; A.dbg[1] += t2 - t1; A.dbg[2] += t3 - t2;
                 }
-                // the proposal lanes own sW.. of their unit: the next prep / gather by the same
-                // lanes follows in program order; sQs / sPart readers are fenced by the two
-                // __syncthreads above and the one that opens grid_arrive / the next gather
-                __syncthreads();
+                // wide: the proposal lanes own sW.. of their unit, the next prep / gather by the same
+                // lanes follows in program order; small units: the next item's values sit in the other
+                // prep buffer since the barrier after the compute phase.  sQs / sPart readers are fenced
+                // by the two __syncthreads above and the one that opens grid_arrive / the next gather
+                csync();
+                if constexpr (PW) pbuf = (pbuf + 1) % 3;
             }
             long long tb = 0;
-            if (A.dbg) { __syncthreads(); tb = clock64(); }
-            grid_arrive(A.barrier, bar_target);
+            if (A.dbg) { csync(); tb = clock64(); }
+            const bool flow_step = FLOW && step >= 0;
+            if (!flow_step) grid_arrive(A.barrier, bar_target, csync);
             {   // random-stream part of the next half-step, overlapped with the barrier
                 int nstep = step, nsp = split + 1;
                 if (nsp >= nsplit) { nstep = step + 1; nsp = 0; }
-                if (nstep < A.nsteps) prep(nstep, nsp, first_unit(nstep, nsp));
+                if (!PW && nstep < A.nsteps) prep(nstep, nsp, first_unit(nstep, nsp));
             }
-            grid_wait(A.barrier, bar_target);
+            if (!flow_step) {
+                grid_wait(A.barrier, bar_target, csync);
+            } else if (split == 1 && (step + 1) % AB_ENS_THROTTLE == 0) {
+                // progress barrier: wait for the one arrived at a period ago (everybody has finished
+                // step + 1 - AB_ENS_THROTTLE), then arrive at this one
+                if (flow_have_prev) grid_wait(A.barrier, flow_prev_target, csync);
+                grid_arrive(A.barrier, bar_target, csync);
+                flow_prev_target = bar_target;
+                flow_have_prev = true;
+            }
             if (A.dbg && blockIdx.x == 0 && tid == 0) { A.dbg[3] += clock64() - tb; A.dbg[4] += 1; }
         }
     }
 }
 
+// one_pass_only: return 1 without launching unless every unit of a half-step gets its own co-resident CTA
 template <int KIND, int D, int P, int EW = 8>
-int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
-    constexpr int ETHREADS = EW * 32;
+int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half, bool one_pass_only = false) {
+    constexpr int ETHREADS = EW * 32 + (P == 32 ? 0 : 32);     // small units: + the prep warp
     void (*kern)(const EnsArgs) = ensemble_kernel<KIND, D, EW, P>;
     // shared memory: resident when the whole training set fits, else two chunk buffers
     const size_t budget = 160 * 1024;
@@ -517,6 +695,13 @@ int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
     if constexpr (P == 32 && EW == 16) {
         if ((size_t)need > budget && ch == 512) kern = ensemble_kernel<KIND, D, EW, P, 512>;
     }
+    if constexpr (P == 2) {
+        // dataflow schedule: resident training set, a ring was provided by the caller
+        if (A.ring && (size_t)need <= budget) kern = ensemble_kernel<KIND, D, EW, P, 0, true>;
+        else A.ring = nullptr;
+    } else {
+        A.ring = nullptr;
+    }
     AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     AB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ETHREADS, smem));
@@ -524,6 +709,7 @@ int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
     int G = EW / A.ws;
     int nbatch = (n_half + P * G - 1) / (P * G);
     const int grid_max = per_sm * h->nsm;
+    if (one_pass_only && grid_max < nbatch) return 1;
     int grid = grid_max;
     A.ranged = 0;
     if (P == 32 && (size_t)need > budget) {
@@ -544,12 +730,26 @@ int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half) {
 }
 
 // n_half: proposals of the larger half-step (or all walkers for a log-prob-only call)
+// small_cta: 0 = 8-warp CTAs (ws8 warps per unit), 1 = try 4-warp CTAs first, 2 = 4-warp CTAs in any case
 template <int KIND, int D>
-int launch_ens(ab_gp* h, EnsArgs& A, int n_half, int p) {
+int launch_ens(ab_gp* h, EnsArgs& A, int n_half, int p, int small_cta, int ws8) {
     // wide unit: 16 warps split the training points (4 warps per scheduler hide the FP64 dependency
     // latency that 2 leave exposed: ncu, c5 share, FP64 pipe 56 % with 8 warps); one CTA per SM
     if (p == 32) return launch_ens_p<KIND, D, 32, 16>(h, A, n_half);
+#ifdef AB_ENS_WITH_P4              // 4 proposals per unit: measured, never selected; development builds only
     if (D <= 24 && p == 4) return launch_ens_p<KIND, (D <= 24 ? D : 2), 4>(h, A, n_half);
+#endif
+    if (small_cta) {
+        // One 4-warp unit (+ prep warp) per CTA, two or more CTAs per SM: units that would share an
+        // 8-warp CTA in lockstep instead run as independent CTAs, so one unit's publish -> poll latency
+        // is covered by its neighbour's kernel evaluations on the same SM.
+        uint4* ring = A.ring;
+        A.ws = 4;
+        const int rc = launch_ens_p<KIND, D, 2, 4>(h, A, n_half, small_cta == 1);
+        if (rc != 1) return rc;
+        A.ring = ring;
+    }
+    A.ws = ws8;
     return launch_ens_p<KIND, D, 2>(h, A, n_half);
 }
 
@@ -567,9 +767,30 @@ static int ens_enqueue(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords
     const int max_units = (cfg->nwalkers + 31) / 32;
     const size_t cnt_bytes = ((size_t)3 * max_units * sizeof(unsigned) + 255) / 256 * 256;
     const size_t part_bytes = (size_t)3 * max_units * AB_ENS_MAXSEG * 32 * sizeof(double);
-    int rc = ab_ensure_scratch(h, 4096 + cnt_bytes + part_bytes);
+    // proposals per half-step; P = 4 per unit once 2 per unit would need several passes per CTA
+    int n_half = (cfg->nwalkers + 1) / 2;
+    if (cfg->init_logp && cfg->nsteps == 0) n_half = cfg->nwalkers;
+    const int nsm = h->nsm;
+    // proposals per unit: 2 (small ensembles, many units), 32 = one lane per proposal once
+    // there are enough proposals for one 32-wide unit per SM
+    int p = (n_half >= 16 * nsm) ? 32 : 2;
+    if (cfg->reserved >= 2)                                                        // development override
+        p = (cfg->reserved == 32) ? 32 : 2;
+#ifdef AB_ENS_WITH_P4
+    if (cfg->reserved == 4 && h->d <= 24) p = 4;
+#endif
+    // dataflow schedule (ab_ensemble_config.schedule 0 = automatic, 1 = grid barriers): small ensembles
+    // whose half-steps are latency bound; the launcher drops it when the training set is not resident
+    const int dpad = h->d <= 2 ? 2 : h->d <= 4 ? 4 : h->d <= 8 ? 8 : h->d <= 24 ? (h->d + 3) / 4 * 4 : 32;   // the dispatch below
+    const bool flow = p == 2 && cfg->schedule != 1 && cfg->nsteps > 0 && (size_t)h->n * (dpad + 1) * 8 <= 160 * 1024;
+    const size_t ring_bytes = flow ? (size_t)AB_ENS_RING * cfg->nwalkers * h->d * sizeof(uint4) : 0;
+    int rc = ab_ensure_scratch(h, 4096 + cnt_bytes + part_bytes + ring_bytes);
     if (rc) return rc;
     EnsArgs A{};
+    if (flow) {
+        A.ring = reinterpret_cast<uint4*>(reinterpret_cast<char*>(h->scratch) + 4096 + cnt_bytes + part_bytes);
+        AB_CUDA(cudaMemsetAsync(A.ring, 0, ring_bytes, h->stream));
+    }
     A.max_units = max_units;
     A.slice_cnt = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(h->scratch) + 4096);
     A.slice_part = reinterpret_cast<double*>(reinterpret_cast<char*>(h->scratch) + 4096 + cnt_bytes);
@@ -603,25 +824,23 @@ static int ens_enqueue(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords
             }
         }
     }
-    // proposals per half-step; P = 4 per unit once 2 per unit would need several passes per CTA
-    int n_half = (cfg->nwalkers + 1) / 2;
-    if (cfg->init_logp && cfg->nsteps == 0) n_half = cfg->nwalkers;
-    const int nsm = h->nsm;
-    // proposals per unit: 2 (small ensembles, many units), 32 = one lane per proposal once
-    // there are enough proposals for one 32-wide unit per SM
-    int p = (n_half >= 16 * nsm) ? 32 : 2;
-    if (cfg->reserved >= 2)                                                        // development override
-        p = (cfg->reserved == 32) ? 32 : ((cfg->reserved == 4 && h->d <= 24) ? 4 : 2);
     // warps per unit: all 8 warps on one unit while that still fills the GPU
     const int units_half = (n_half + p - 1) / p;
     int ws = 1;
     if (p == 32) ws = 16;                      // wide unit = the whole CTA (16 warps)
-    else if (cfg->warps_per_unit > 0) ws = cfg->warps_per_unit;
-    else while (ws < 8 && units_half * ws <= nsm * 8) ws *= 2;
-    if (ws != 1 && ws != 2 && ws != 4 && ws != 8 && !(p == 32 && ws == 16)) { ab_set_error("warps_per_unit must be 1, 2, 4 or 8"); return -1; }
+    else if (cfg->warps_per_unit > 0 && cfg->warps_per_unit != 104) ws = cfg->warps_per_unit;
+    else while (ws < 8 && units_half * ws * 2 <= nsm * 8) ws *= 2;   // the half-step in ONE pass of one 8-warp CTA per SM
+    if (ws != 1 && ws != 2 && ws != 4 && ws != 8 && !(p == 32 && ws == 16)) { ab_set_error("warps_per_unit must be 1, 2, 4, 8 or 104"); return -1; }
     A.ws = ws;
+    // 4-warp CTAs (one unit each, several per SM) when 8-warp CTAs would run several units in lockstep
+    // and every unit still gets a co-resident CTA; warps_per_unit = 104 forces them (development)
+    const int small_cta = (p != 2) ? 0 : (cfg->warps_per_unit == 104) ? 2 : (cfg->warps_per_unit == 0 && ws < 8) ? 1 : 0;
     const int d = h->d;
-#define AB_ENS(DD) AB_DISPATCH_KIND(h->kp.kind, rc = (launch_ens<KIND, DD>(h, A, n_half, p)))
+#define AB_ENS(DD) AB_DISPATCH_KIND(h->kp.kind, rc = (launch_ens<KIND, DD>(h, A, n_half, p, small_cta, ws)))
+#ifdef AB_ENS_DEV_D2               // development: compile the d <= 2 kernels only (seconds instead of minutes)
+    if (d <= 2) AB_ENS(2);
+    else { ab_set_error("development build: d <= 2 only"); return -1; }
+#else
     if (d <= 2) AB_ENS(2);
     else if (d <= 4) AB_ENS(4);
     else if (d <= 8) AB_ENS(8);
@@ -630,6 +849,7 @@ static int ens_enqueue(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords
     else if (d <= 20) AB_ENS(20);
     else if (d <= 24) AB_ENS(24);
     else AB_ENS(32);
+#endif
 #undef AB_ENS
     if (rc) return rc;
     h->ens_dbg = A.dbg != nullptr; h->ens_ws = A.ws;

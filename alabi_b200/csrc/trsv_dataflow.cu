@@ -9,10 +9,18 @@
 //
 // A CTA pre-issues the 128 x 128 block L_kj into registers (coalesced rows, 64
 // doubles per thread) BEFORE it waits for z_j, so the step on the critical path is:
-// flag + 1 KB of z_j from L2, 64 FMAs per thread, one reduction, the D_k^-1 product
-// from shared memory (D_k^-1 is staged there by cp.async when the task starts), a
-// fence and the flag of z_k.  The summation order is fixed (block order j, lanes,
-// then warps), so results do not depend on timing.
+// z_j from L2, 64 FMAs per thread, one reduction, the D_k^-1 product from shared
+// memory (D_k^-1 is staged there by cp.async when the task starts) and the stores of
+// z_k.  The summation order is fixed (block order j, lanes, then warps), so results
+// do not depend on timing.
+//
+// Signalling (round 2): the solution vectors travel between CTAs as 16-byte lines
+// {lo, tag, hi, tag} per value (8-byte halves are single-copy atomic; a line whose two
+// tags are set holds the value), written with relaxed gpu-scope vector stores and polled
+// with relaxed vector loads: the data is its own ready flag.  That takes the flag poll
+// (one L2 round trip before the dependent load of z_j), the __threadfence of 256 threads
+// and the release store out of every one of the 2 N / 128 dependent block steps; z and
+// alpha are also written in plain form for the kernels that follow.
 //
 // Deadlock freedom: cooperative launch (all CTAs resident); every CTA walks its
 // rows in dependency order, so the first unfinished row can always run.  Wait
@@ -27,24 +35,32 @@ constexpr int NB = AB_NB;
 struct TrsvArgs {
     const double* L; int64_t ld; const double* Dinv; int T;
     const double* r; double* z; double* alpha;
-    int* zflag; int* aflag; int* abort_flag;
+    uint4* zline; uint4* aline; int* abort_flag;      // one line per value, zeroed before the launch
     int backward;                 // 0: forward sweep only (z), 1: both
 };
 
-__device__ __forceinline__ int ld_acquire_i(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_i(int* p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_line(uint4* p, double v) {
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)__double2loint(v)), "r"(1u),
+                 "r"((unsigned)__double2hiint(v)), "r"(1u) : "memory");
 }
 
-__device__ __forceinline__ void wait_flag(const int* flag, int* abort_flag, bool& aborted) {
-    if (aborted) return;
+// NV values x[c] = line[c * STRIDE]: all loads of a round are issued together; rounds repeat until
+// every line carries its tags.  The watchdog raises the abort flag instead of hanging.
+template <int NV, int STRIDE>
+__device__ __forceinline__ void poll_lines(double (&x)[NV], const uint4* line, int* abort_flag, bool& aborted) {
     long long t0 = 0;
     unsigned spins = 0;
-    while (ld_acquire_i(flag) == 0) {
+    for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int c = 0; c < NV; c++) {
+            unsigned x0, x1, x2, x3;
+            asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "l"(line + c * STRIDE) : "memory");
+            ok = ok && (x1 == 1u) && (x3 == 1u);
+            x[c] = __hiloint2double((int)x2, (int)x0);
+        }
+        if (ok || aborted) return;
         if ((++spins & 1023u) == 0) {
             if (t0 == 0) t0 = clock64();
             if (*((volatile int*)abort_flag) != 0 || clock64() - t0 > 4000000000LL) {
@@ -87,10 +103,8 @@ trsv_dataflow_kernel(const __grid_constant__ TrsvArgs a) {
         for (int i = 0; i < 16; i++) part[i] = 0.0;
         if (k > 0) load_block(v, a.L + o * a.ld, a.ld, warp, lane);
         for (int j = 0; j < k; j++) {
-            wait_flag(a.zflag + j, a.abort_flag, aborted);
             double x[4];
-#pragma unroll
-            for (int c = 0; c < 4; c++) x[c] = __ldcg(a.z + (int64_t)j * NB + lane + 32 * c);
+            poll_lines<4, 32>(x, a.zline + (int64_t)j * NB + lane, a.abort_flag, aborted);
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 double s = v[i][0] * x[0];
@@ -119,11 +133,12 @@ trsv_dataflow_kernel(const __grid_constant__ TrsvArgs a) {
             s = fma(Dr[64], x[2], s);
             s = fma(Dr[96], x[3], s);
             s = ab_warp_sum(s);
-            if (lane == 0) a.z[o + warp + 8 * i] = s;
+            if (lane == 0) {
+                st_line(a.zline + o + warp + 8 * i, s);
+                a.z[o + warp + 8 * i] = s;
+            }
         }
-        __threadfence();
-        __syncthreads();                                  // also: sD / sw are free for the next task
-        if (tid == 0) st_release_i(a.zflag + k, 1);
+        __syncthreads();                                  // sD / sw are free for the next task
     }
 
     if (!a.backward) return;
@@ -135,10 +150,8 @@ trsv_dataflow_kernel(const __grid_constant__ TrsvArgs a) {
         double y[4] = {0.0, 0.0, 0.0, 0.0};
         if (k + 1 < T) load_block(v, a.L + (int64_t)(T - 1) * NB * a.ld + o, a.ld, warp, lane);
         for (int j = T - 1; j > k; j--) {
-            wait_flag(a.aflag + j, a.abort_flag, aborted);
             double xr[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) xr[i] = __ldcg(a.alpha + (int64_t)j * NB + warp + 8 * i);
+            poll_lines<16, 8>(xr, a.aline + (int64_t)j * NB + warp, a.abort_flag, aborted);
 #pragma unroll
             for (int i = 0; i < 16; i++)
 #pragma unroll
@@ -147,13 +160,14 @@ trsv_dataflow_kernel(const __grid_constant__ TrsvArgs a) {
         }
 #pragma unroll
         for (int c = 0; c < 4; c++) spart[warp][lane + 32 * c] = y[c];
-        wait_flag(a.zflag + k, a.abort_flag, aborted);    // z_k (own forward row when G divides evenly)
         __syncthreads();
         if (tid < NB) {
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; w++) s += spart[w][tid];
-            sw[tid] = __ldcg(a.z + o + tid) - s;
+            double zk[1];                                 // z_k (own forward row when G divides evenly)
+            poll_lines<1, 1>(zk, a.zline + o + tid, a.abort_flag, aborted);
+            sw[tid] = zk[0] - s;
         }
         abg::cp_async_wait<0>();
         __syncthreads();
@@ -174,11 +188,10 @@ trsv_dataflow_kernel(const __grid_constant__ TrsvArgs a) {
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; w++) s += spart[w][tid];
+            st_line(a.aline + o + tid, s);
             a.alpha[o + tid] = s;
         }
-        __threadfence();
         __syncthreads();
-        if (tid == 0) st_release_i(a.aflag + k, 1);
     }
 }
 
@@ -194,16 +207,19 @@ int ab_launch_trsv_dataflow(ab_gp* h, const double* r, int backward) {
         if (h->device < 64) configured |= 1ULL << h->device;
     }
     const int T = (int)(h->npad / NB);
-    // control ints live behind the sums slot of scratch: [abort][zflag T][aflag T]
-    int rc = ab_ensure_scratch(h, 256 + (size_t)(2 * T + 1) * sizeof(int));
+    // control area behind the sums slot of scratch: [abort flag, padded to 256 B][z lines npad][alpha lines npad]
+    const size_t line_bytes = (size_t)2 * h->npad * sizeof(uint4);
+    int rc = ab_ensure_scratch(h, 512 + line_bytes);
     if (rc) return rc;
     int* ctrl = reinterpret_cast<int*>(h->scratch + 32);
     cudaStream_t s = h->stream;
-    AB_CUDA(cudaMemsetAsync(ctrl, 0, (size_t)(2 * T + 1) * sizeof(int), s));
+    AB_CUDA(cudaMemsetAsync(ctrl, 0, 256 + line_bytes, s));
     TrsvArgs a;
     a.L = h->L; a.ld = h->npad; a.Dinv = h->Dinv; a.T = T;
     a.r = r; a.z = h->z; a.alpha = h->alpha;
-    a.abort_flag = ctrl; a.zflag = ctrl + 1; a.aflag = ctrl + 1 + T;
+    a.abort_flag = ctrl;
+    a.zline = reinterpret_cast<uint4*>(reinterpret_cast<char*>(ctrl) + 256);
+    a.aline = a.zline + h->npad;
     a.backward = backward;
     int grid = T < h->nsm ? T : h->nsm;
     void* args[] = {(void*)&a};

@@ -82,7 +82,7 @@ class SurrogateLogProb:
 class EnsembleSampler:
     def __init__(self, nwalkers, ndim, log_prob_fn, pool=None, moves=None, args=None, kwargs=None,
                  backend=None, vectorize=False, blobs_dtype=None, parameter_names=None, a=2.0, seed=None,
-                 randomize_split=True, live_dangerously=False, warps_per_unit=0):
+                 randomize_split=True, live_dangerously=False, warps_per_unit=0, schedule=0):
         if not isinstance(log_prob_fn, SurrogateLogProb):
             raise TypeError("alabi_b200.EnsembleSampler runs on the GPU and needs a SurrogateLogProb "
                             "(GP surrogate + uniform prior); arbitrary Python log-probabilities are not supported")
@@ -98,6 +98,9 @@ class EnsembleSampler:
         self.seed = int(np.random.SeedSequence().entropy % (2 ** 63)) if seed is None else int(seed)
         self.randomize_split = bool(randomize_split)
         self.warps_per_unit = int(warps_per_unit)
+        # small ensembles: 0 = dataflow on the partner's versioned record (default), 1 = a grid barrier
+        # per half-step (ab_ensemble_config.schedule); the chains are identical
+        self.schedule = int(schedule)
         self.pinned_limit_bytes = 4 << 30      # larger stored chains land in pageable host memory
         self.reset()
 
@@ -128,6 +131,7 @@ class EnsembleSampler:
             cfg.theta_scale[k], cfg.theta_offset[k] = lp.theta_scale[k], lp.theta_offset[k]
             cfg.prior_mu[k], cfg.prior_sd[k] = lp.prior_mu[k], lp.prior_sd[k]
         cfg.use_normal_prior = int(lp.use_normal_prior)
+        cfg.schedule = self.schedule
         return cfg
 
     def run_mcmc(self, initial_state, nsteps, progress=False, thin_by=1, store=True, record_proposals=False,

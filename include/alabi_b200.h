@@ -173,7 +173,9 @@ typedef struct ab_ensemble_config {
     int thin_by;           /* store every thin_by-th step (>= 1) */
     int init_logp;         /* 1: evaluate log-prob of d_coords first */
     int randomize_split;   /* 1: coin per walker pair, 0: parity split */
-    int warps_per_unit;    /* 0 = auto, else 1/2/4/8 */
+    int warps_per_unit;    /* 0 = auto; 1/2/4/8 = that many warps per unit inside 8-warp CTAs; 104 = one 4-warp
+                            * unit per CTA, several CTAs per SM (what auto picks when every unit of a half-step
+                            * then has a co-resident CTA) */
     int y_kind;            /* y = ys*y_scale + y_offset (0), -10^ys (1), 10^ys (2) */
     int reserved;            /* 0 in production.  Development aids: 1 = print per-phase cycle counts of
                               * block 0 to stderr; 2 / 4 / 32 = force that many proposals per unit */
@@ -188,7 +190,9 @@ typedef struct ab_ensemble_config {
      * alabi/utility.py:370-378): use_normal_prior != 0 adds norm.logpdf(theta_k; prior_mu[k],
      * prior_sd[k]) for every k with prior_sd[k] > 0 (prior_sd[k] <= 0: uniform dimension) */
     int use_normal_prior;
-    int reserved2;
+    int schedule;          /* small ensembles (2 proposals per unit, training set resident in shared memory):
+                            * 0 = dataflow (a proposal waits for its partner's versioned record only; default),
+                            * 1 = a grid barrier per half-step.  Identical chains. */
     double prior_mu[AB_MAX_DIM_PUBLIC], prior_sd[AB_MAX_DIM_PUBLIC];
 } ab_ensemble_config;
 

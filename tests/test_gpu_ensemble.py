@@ -164,3 +164,32 @@ def test_wide_streamed_split_units_replay():
     s2.run_mcmc(p0, 2)
     s2.run_mcmc(None, 3)
     np.testing.assert_array_equal(s2.get_chain(), s.get_chain())
+
+
+@pytest.mark.parametrize("kind,n,d,nw,rs,wpu,nsteps,thin", [("Matern32Kernel", 1000, 2, 1000, True, 0, 150, 1),
+                                                            ("ExpSquaredKernel", 300, 3, 41, False, 2, 97, 1),
+                                                            ("Matern52Kernel", 500, 5, 333, True, 4, 64, 3),
+                                                            ("ExpSquaredKernel", 150, 2, 10, True, 8, 200, 1)])
+def test_dataflow_schedule_gives_the_barrier_schedules_chain(kind, n, d, nw, rs, wpu, nsteps, thin):
+    """Small ensembles: the dataflow schedule (a proposal waits for its partner's versioned record,
+    progress barrier every 15 steps, ring of 32 versions) must reproduce the chain of the grid-barrier
+    schedule bit for bit -- stored rows, log-probabilities, acceptance counts and the final state --
+    over more steps than the ring holds versions, for odd ensembles, thinning and cut runs."""
+    from alabi_b200.ensemble import EnsembleSampler
+    g, lp, lp_oracle, rng, b = surrogate(kind, n, d, 23, [(-2.0, 2.0)] * d)
+    p0 = rng.uniform(-1.9, 1.9, size=(nw, d))
+    runs = []
+    for schedule in (1, 0):
+        s = EnsembleSampler(nw, d, lp, seed=4242, randomize_split=rs, warps_per_unit=wpu, schedule=schedule,
+                            live_dangerously=True)
+        s.run_mcmc(p0, nsteps, thin_by=thin)
+        st = s.run_mcmc(None, 40, thin_by=thin)              # continued run: versions restart, step counter goes on
+        runs.append((s.get_chain().copy(), s.get_log_prob().copy(), s._naccepted.copy(), st.coords.copy(), st.log_prob.copy()))
+    for a, b_ in zip(runs[0], runs[1]):
+        np.testing.assert_array_equal(a, b_)
+    # without a stored chain (final state only) the dataflow run ends in the same state
+    s = EnsembleSampler(nw, d, lp, seed=4242, randomize_split=rs, warps_per_unit=wpu, live_dangerously=True)
+    s.run_mcmc(p0, nsteps * thin, store=False)
+    st = s.run_mcmc(None, 40 * thin, store=False)
+    np.testing.assert_array_equal(st.coords, runs[0][3])
+    np.testing.assert_array_equal(st.log_prob, runs[0][4])
