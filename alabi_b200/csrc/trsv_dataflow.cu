@@ -72,6 +72,36 @@ __device__ __forceinline__ void poll_lines(double (&x)[NV], const uint4* line, i
     }
 }
 
+// Sums of 16 per-lane values over the 32 lanes of a warp with 16 exchanges instead of 16 x 5:
+// every round halves the number of values a lane carries (it keeps the half its lane bit selects
+// and adds the partner's copy of that half), so after offsets 16, 8, 4, 2 a lane holds one value
+// and offset 1 completes it.  Returns the total of v[lane >> 1] (both lanes of a pair hold it).
+// Fixed order, so results do not depend on timing.  (The butterfly per value cost 160 SHFL and 80
+// DADD per warp twice per block step: the largest item on the dependent chain of the sweeps.)
+__device__ __forceinline__ double warp_reduce16(const double (&v)[16], int lane) {
+    double a8[8], a4[4], a2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const double keep = b4 ? v[i + 8] : v[i], send = b4 ? v[i] : v[i + 8];
+        a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double keep = b3 ? a8[i + 4] : a8[i], send = b3 ? a8[i] : a8[i + 4];
+        a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const double keep = b2 ? a4[i + 2] : a4[i], send = b2 ? a4[i] : a4[i + 2];
+        a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const double keep = b1 ? a2[1] : a2[0], send = b1 ? a2[0] : a2[1];
+    double r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
 // the 16 rows {warp + 8 i} of a 128 x 128 row-major block, columns {lane + 32 c}
 __device__ __forceinline__ void load_block(double (&v)[16][4], const double* __restrict__ M, int64_t ldm, int warp, int lane) {
 #pragma unroll
@@ -115,16 +145,17 @@ trsv_dataflow_kernel(const __grid_constant__ TrsvArgs a) {
             }
             if (j + 1 < k) load_block(v, a.L + o * a.ld + (int64_t)(j + 1) * NB, a.ld, warp, lane);
         }
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const double s = ab_warp_sum(part[i]);
-            if (lane == 0) sw[warp + 8 * i] = a.r[o + warp + 8 * i] - s;
+        {
+            const double s = warp_reduce16(part, lane);          // row warp + 8 (lane >> 1)
+            const int row = warp + 8 * (lane >> 1);
+            if ((lane & 1) == 0) sw[row] = a.r[o + row] - s;
         }
         abg::cp_async_wait<0>();
         __syncthreads();
         double x[4];
 #pragma unroll
         for (int c = 0; c < 4; c++) x[c] = sw[lane + 32 * c];
+        double dz[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) {
             const double* Dr = sD + (warp + 8 * i) * NB + lane;
@@ -132,10 +163,14 @@ trsv_dataflow_kernel(const __grid_constant__ TrsvArgs a) {
             s = fma(Dr[32], x[1], s);
             s = fma(Dr[64], x[2], s);
             s = fma(Dr[96], x[3], s);
-            s = ab_warp_sum(s);
-            if (lane == 0) {
-                st_line(a.zline + o + warp + 8 * i, s);
-                a.z[o + warp + 8 * i] = s;
+            dz[i] = s;
+        }
+        {
+            const double s = warp_reduce16(dz, lane);
+            const int row = warp + 8 * (lane >> 1);
+            if ((lane & 1) == 0) {
+                st_line(a.zline + o + row, s);
+                a.z[o + row] = s;
             }
         }
         __syncthreads();                                  // sD / sw are free for the next task
