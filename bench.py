@@ -343,8 +343,9 @@ def c2_extra(lib, steps=5, fma_peak_tflops=None):
             "mcmc_walker_steps_per_s": mc_dev, "mcmc_e2e_walker_steps_per_s": mc_e2e,
             "mcmc_shape": f"{nw} walkers x {ns} steps, chain and log-prob delivered to host ({ns * nw * 3 * 8} B)",
             "sampler_flops_per_walker_step": 1000.0 * (3 * 2 + 35 + 2) + 12,
-            "mcmc_roofline": {"bound": "latency (two grid barriers and two dependent L2 round trips per half-step, DESIGN.md "
-                                       "section 3); against the FP64 FMA roof for reference",
+            "mcmc_roofline": {"bound": "latency (dataflow schedule: per half-step one publish -> poll round trip through the L2, "
+                                       "the kernel evaluations of two units per SM and the accept; DESIGN.md section 3); "
+                                       "against the FP64 FMA roof for reference",
                               "achieved": mc_dev * (1000.0 * (3 * 2 + 35 + 2) + 12) * 1e-12, "peak": fma_peak_tflops,
                               "unit": "TFLOP/s",
                               "frac": (mc_dev * (1000.0 * (3 * 2 + 35 + 2) + 12) * 1e-12 / fma_peak_tflops) if fma_peak_tflops else None},
