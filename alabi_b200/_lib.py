@@ -16,6 +16,8 @@ LIB_PATH = os.environ.get("ALABI_B200_LIB") or os.path.join(HERE, "libalabi_b200
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)
 MAX_DIM = 32
+MAX_PEERS = 15
+PEER_HANDLE_BYTES = 64
 
 
 class EnsembleConfig(ctypes.Structure):
@@ -28,7 +30,10 @@ class EnsembleConfig(ctypes.Structure):
                 ("lo", ctypes.c_double * MAX_DIM), ("hi", ctypes.c_double * MAX_DIM),
                 ("theta_scale", ctypes.c_double * MAX_DIM), ("theta_offset", ctypes.c_double * MAX_DIM),
                 ("use_normal_prior", ctypes.c_int), ("schedule", ctypes.c_int),
-                ("prior_mu", ctypes.c_double * MAX_DIM), ("prior_sd", ctypes.c_double * MAX_DIM)]
+                ("prior_mu", ctypes.c_double * MAX_DIM), ("prior_sd", ctypes.c_double * MAX_DIM),
+                ("chain_row_walkers", ctypes.c_int64), ("chain_walker_offset", ctypes.c_int64),
+                ("n_chain_peers", ctypes.c_int), ("reserved3", ctypes.c_int),
+                ("chain_peers", ctypes.c_void_p * MAX_PEERS), ("logp_chain_peers", ctypes.c_void_p * MAX_PEERS)]
 
 
 class NestedConfig(ctypes.Structure):
@@ -102,6 +107,10 @@ SIGNATURES = {
     "ab_nccl_broadcast": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int]),
     "ab_nccl_allgather": (ctypes.c_int, [_P, _P, _P, ctypes.c_int64]),
     "ab_nccl_broadcast_gp": (ctypes.c_int, [_P, _P, ctypes.c_int]),
+    "ab_peer_alloc": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_ubyte)]),
+    "ab_peer_open": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_ubyte), ctypes.POINTER(_P)]),
+    "ab_peer_close": (ctypes.c_int, [ctypes.c_int, _P]),
+    "ab_peer_free": (ctypes.c_int, [ctypes.c_int, _P]),
     "ab_sizeof_nested_config": (ctypes.c_int, []),
     "ab_nested_walk": (ctypes.c_int, [_P, ctypes.POINTER(NestedConfig), _P, _P, _P, _P]),
     "ab_ensemble_run_host": (ctypes.c_int, [_P, ctypes.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P, _P, ctypes.c_int]),

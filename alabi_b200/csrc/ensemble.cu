@@ -58,6 +58,11 @@ struct EnsArgs {
     // segment sums meet in slice_part (fixed segment order), completions are counted in slice_cnt.
     int ranged, max_units;
     double* slice_part; unsigned* slice_cnt;
+    // stored rows: walker w of stored row r sits at r * chain_ld + chain_off + w of chain_dst[0] (= chain)
+    // and of the n_dst - 1 peer buffers behind it (fused all_gather of chain blocks)
+    long long chain_ld, chain_off;
+    int n_dst;
+    double* chain_dst[AB_MAX_PEERS + 1]; double* logp_dst[AB_MAX_PEERS + 1];
     // dataflow schedule (FLOW kernels): ring of AB_ENS_RING versions of every walker's position,
     // one 16-byte line {lo, flag, hi, flag} per coordinate, flag = version + 1 (0 = never written)
     uint4* ring;
@@ -626,10 +631,13 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                                 A.rec_lp[r] = lp_q;
                             }
                             if (store_row >= 0) {
-                                long long r = store_row * nw + w;
-                                for (int k = 0; k < d; k++)
-                                    A.chain[r * d + k] = acc ? sQ[unit][e][k] : sS[unit][e][k];
-                                A.logp_chain[r] = lp_s;
+                                const long long r = store_row * A.chain_ld + A.chain_off + w;
+#pragma unroll 1
+                                for (int pd = 0; pd < A.n_dst; pd++) {       // own buffer, then the peers' (NVLink stores)
+                                    double* cdst = A.chain_dst[pd] + r * d;
+                                    for (int k = 0; k < d; k++) cdst[k] = acc ? sQ[unit][e][k] : sS[unit][e][k];
+                                    A.logp_dst[pd][r] = lp_s;
+                                }
                             }
                         }
                     }
@@ -797,6 +805,20 @@ static int ens_enqueue(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords
     if (first) AB_CUDA(cudaMemsetAsync(A.slice_cnt, 0, cnt_bytes, h->stream));
     A.coords = d_coords; A.logp = d_logp; A.naccept = d_naccept;
     A.chain = d_chain; A.logp_chain = d_logp_chain; A.rec_q = d_rec_q; A.rec_lp = d_rec_lp;
+    if (cfg->n_chain_peers < 0 || cfg->n_chain_peers > AB_MAX_PEERS || cfg->chain_row_walkers < 0 || cfg->chain_walker_offset < 0 ||
+        (cfg->chain_row_walkers > 0 && cfg->chain_walker_offset + cfg->nwalkers > cfg->chain_row_walkers) ||
+        (cfg->chain_row_walkers == 0 && (cfg->chain_walker_offset != 0 || cfg->n_chain_peers != 0))) {
+        ab_set_error("ab_ensemble_run: bad chain layout (chain_row_walkers / chain_walker_offset / n_chain_peers)"); return -1;
+    }
+    A.chain_ld = cfg->chain_row_walkers > 0 ? cfg->chain_row_walkers : cfg->nwalkers;
+    A.chain_off = cfg->chain_walker_offset;
+    A.n_dst = d_chain ? 1 + cfg->n_chain_peers : 0;
+    A.chain_dst[0] = d_chain; A.logp_dst[0] = d_logp_chain;
+    for (int q = 0; q < cfg->n_chain_peers; q++) {
+        if (!cfg->chain_peers[q] || !cfg->logp_chain_peers[q]) { ab_set_error("ab_ensemble_run: null peer buffer"); return -1; }
+        A.chain_dst[1 + q] = static_cast<double*>(cfg->chain_peers[q]);
+        A.logp_dst[1 + q] = static_cast<double*>(cfg->logp_chain_peers[q]);
+    }
     A.barrier = reinterpret_cast<unsigned long long*>(h->scratch);
     A.nan_flag = reinterpret_cast<int*>(h->scratch + 1);
     A.dbg = cfg->reserved == 1 ? reinterpret_cast<long long*>(h->scratch + 16) : nullptr;
@@ -881,6 +903,9 @@ extern "C" int ab_ensemble_run_host(ab_gp* h, const ab_ensemble_config* cfg, dou
     if (h->ens_pending) { ab_set_error("ab_ensemble_run_host: the previous run was not finished (ab_ensemble_finish)"); return -1; }
     if (cfg->thin_by < 1 || cfg->nsteps < 0 || cfg->nsteps % cfg->thin_by != 0) {
         ab_set_error("ab_ensemble_run_host: nsteps must be a multiple of thin_by"); return -1;
+    }
+    if (cfg->chain_row_walkers != 0 || cfg->n_chain_peers != 0) {
+        ab_set_error("ab_ensemble_run_host: gathered chain layouts go through ab_ensemble_launch"); return -1;
     }
     AB_CUDA(cudaSetDevice(h->device));
     const long long rows = cfg->nsteps / cfg->thin_by, nw = cfg->nwalkers, d = h->d;

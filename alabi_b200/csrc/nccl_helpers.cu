@@ -168,3 +168,47 @@ extern "C" int ab_nccl_sync(ab_comm* c) {
     AB_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
+
+// ---- peer memory (CUDA IPC) for the fused chain all_gather of the sampler ----------------------
+extern "C" int ab_peer_alloc(int device, size_t bytes, void** d_ptr, unsigned char* h_handle) {
+    if (!d_ptr || !h_handle || bytes == 0) { ab_set_error("ab_peer_alloc: bad argument"); return -1; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == AB_PEER_HANDLE_BYTES, "handle size");
+    AB_CUDA(cudaSetDevice(device));
+    void* p = nullptr;
+    AB_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t hnd;
+    cudaError_t e = cudaIpcGetMemHandle(&hnd, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        ab_set_error("ab_peer_alloc: cudaIpcGetMemHandle -> %s", cudaGetErrorString(e));
+        return -100 - (int)e;
+    }
+    memcpy(h_handle, &hnd, sizeof(hnd));
+    *d_ptr = p;
+    return 0;
+}
+
+extern "C" int ab_peer_open(int device, const unsigned char* h_handle, void** d_ptr) {
+    if (!d_ptr || !h_handle) { ab_set_error("ab_peer_open: bad argument"); return -1; }
+    AB_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, h_handle, sizeof(hnd));
+    void* p = nullptr;
+    AB_CUDA(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = p;
+    return 0;
+}
+
+extern "C" int ab_peer_close(int device, void* d_ptr) {
+    if (!d_ptr) return 0;
+    AB_CUDA(cudaSetDevice(device));
+    AB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
+extern "C" int ab_peer_free(int device, void* d_ptr) {
+    if (!d_ptr) return 0;
+    AB_CUDA(cudaSetDevice(device));
+    AB_CUDA(cudaFree(d_ptr));
+    return 0;
+}

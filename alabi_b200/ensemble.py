@@ -135,12 +135,15 @@ class EnsembleSampler:
         return cfg
 
     def run_mcmc(self, initial_state, nsteps, progress=False, thin_by=1, store=True, record_proposals=False,
-                 walker_offset=0, **kwargs):
+                 walker_offset=0, gather=None, **kwargs):
         """Run ``nsteps * thin_by`` ensemble steps on the device, storing every
         ``thin_by``-th.  Returns the final :class:`State`.  ``store``: True (chain and
         log-probabilities end up in host arrays, emcee's backend), False (final state only) or
         ``"device"`` (the stored chain stays in HBM as ``device_chain`` / ``device_log_prob``
-        torch tensors: what ``parallel.sharded_ensemble`` all_gathers over NVLink)."""
+        torch tensors: what ``parallel.sharded_ensemble`` all_gathers over NVLink).  ``gather`` (with
+        ``store="device"``): a ``parallel.PeerChainBuffers`` spec — the kernel writes the stored rows
+        straight into the gathered (nsteps, nwalkers_total, ndim) buffers of this rank AND of the
+        other ranks (peer memory over NVLink), the fused form of the chain-block all_gather."""
         import torch
         gp = self.log_prob_fn.gp
         gp.recompute()
@@ -168,11 +171,23 @@ class EnsembleSampler:
         logp = torch.from_numpy(np.ascontiguousarray(initial_state.log_prob)).to(dev) if have_lp \
             else torch.empty(self.nwalkers, dtype=torch.float64, device=dev)
         nacc = torch.zeros(self.nwalkers, dtype=torch.int64, device=dev)
-        chain = torch.empty((int(nsteps), self.nwalkers, self.ndim), dtype=torch.float64, device=dev) if store else None
-        lpc = torch.empty((int(nsteps), self.nwalkers), dtype=torch.float64, device=dev) if store else None
+        if gather is not None:
+            if not on_device or record_proposals:
+                raise ValueError("gather needs store='device' and no proposal record")
+            chain, lpc = gather["chain"], gather["log_prob"]            # gathered buffers of THIS rank
+            if tuple(chain.shape) != (int(nsteps), gather["nwalkers_total"], self.ndim) or chain.dtype != torch.float64:
+                raise ValueError("gather buffers do not match (nsteps, nwalkers_total, ndim)")
+        else:
+            chain = torch.empty((int(nsteps), self.nwalkers, self.ndim), dtype=torch.float64, device=dev) if store else None
+            lpc = torch.empty((int(nsteps), self.nwalkers), dtype=torch.float64, device=dev) if store else None
         rq = torch.full((total, self.nwalkers, self.ndim), float("nan"), dtype=torch.float64, device=dev) if record_proposals else None
         rl = torch.full((total, self.nwalkers), float("nan"), dtype=torch.float64, device=dev) if record_proposals else None
         cfg = self._config(total, thin_by, not have_lp, walker_offset)
+        if gather is not None:
+            cfg.chain_row_walkers, cfg.chain_walker_offset = int(gather["nwalkers_total"]), int(gather["column"])
+            cfg.n_chain_peers = len(gather["peer_chain_ptrs"])
+            for q, (pc, pl) in enumerate(zip(gather["peer_chain_ptrs"], gather["peer_log_prob_ptrs"])):
+                cfg.chain_peers[q], cfg.logp_chain_peers[q] = pc, pl
         lib = hd.lib
         prof_prev = lib.ab_gp_set_profiling(hd.h, 1)
         if store and not record_proposals and not on_device:
@@ -216,6 +231,10 @@ class EnsembleSampler:
         self._naccepted += nacc.cpu().numpy()
         if on_device:
             # the stored rows stay in HBM; get_chain() / get_log_prob() copy them on first use
+            if gather is not None:
+                # own columns of the gathered buffers, copied: the buffers are reused by the next gather
+                c0 = int(gather["column"])
+                chain, lpc = chain[:, c0:c0 + self.nwalkers].clone(), lpc[:, c0:c0 + self.nwalkers].clone()
             self.device_chain, self.device_log_prob = chain, lpc
             self._device_rows_pending = True
             self.iteration += int(nsteps)

@@ -254,11 +254,75 @@ def sharded_utility_argmin(gp, y, candidates, bounds, algorithm="bape", y_best=0
     return argmin_allgather(val, idx + lo if idx >= 0 else -1)
 
 
-def sharded_ensemble(sampler_factory, p0, nsteps, gather=True, to_host=True, **run_kwargs):
+class PeerChainBuffers:
+    """Gathered chain buffers of one shape in peer memory: every rank owns a (nsteps, nwalkers_total,
+    ndim) chain and a (nsteps, nwalkers_total) log-probability buffer (one cudaMalloc, exported with
+    CUDA IPC) and maps the buffers of all other ranks, so that the sampler kernel of rank r can write
+    its columns into all of them (``ab_ensemble_config.chain_peers``).  Built collectively (one
+    ``all_gather_object`` of the 64-byte handles); cached per shape for the life of the process."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, lib, device, nsteps, nwalkers_total, ndim):
+        key = (int(device), int(nsteps), int(nwalkers_total), int(ndim))
+        if key not in cls._cache:
+            cls._cache[key] = cls(lib, *key)
+        return cls._cache[key]
+
+    def __init__(self, lib, device, nsteps, nwalkers_total, ndim):
+        import ctypes
+        import torch
+        from . import _lib
+        dist = _dist()
+        self.shape = (nsteps, nwalkers_total, ndim)
+        nchain = nsteps * nwalkers_total * ndim * 8
+        self._lp_off = (nchain + 255) // 256 * 256
+        nbytes = self._lp_off + nsteps * nwalkers_total * 8
+        own, hnd = ctypes.c_void_p(), (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+        _lib.check(lib.ab_peer_alloc(device, nbytes, ctypes.byref(own), hnd), "ab_peer_alloc")
+        self.own = own.value
+        handles = [None] * dist.get_world_size()
+        dist.all_gather_object(handles, bytes(hnd))
+        self.peers = []                                          # base pointers of the other ranks' buffers, by rank order
+        for r, hb in enumerate(handles):
+            if r == dist.get_rank():
+                continue
+            p = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES).from_buffer_copy(hb)
+            _lib.check(lib.ab_peer_open(device, buf, ctypes.byref(p)), "ab_peer_open")
+            self.peers.append(p.value)
+        self.chain = _tensor_at(self.own, (nsteps, nwalkers_total, ndim), device)
+        self.log_prob = _tensor_at(self.own + self._lp_off, (nsteps, nwalkers_total), device)
+
+    def spec(self, column):
+        """What ``EnsembleSampler.run_mcmc(gather=...)`` takes: this rank's walkers are columns
+        [column, column + nwalkers_local) of every row."""
+        return {"chain": self.chain, "log_prob": self.log_prob, "nwalkers_total": self.shape[1], "column": int(column),
+                "peer_chain_ptrs": list(self.peers), "peer_log_prob_ptrs": [p + self._lp_off for p in self.peers]}
+
+
+def _tensor_at(ptr, shape, device):
+    """float64 torch tensor over device memory this package owns (zero copy)."""
+    import torch
+
+    class _Mem:
+        __cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": "<f8", "data": (int(ptr), False),
+                                    "version": 2, "strides": None}
+    return torch.as_tensor(_Mem(), device=f"cuda:{device}")
+
+
+def sharded_ensemble(sampler_factory, p0, nsteps, gather=True, to_host=True, fused=True, **run_kwargs):
     """Independent sub-ensembles: rank r advances walkers [lo, hi) of ``p0`` with
     RNG counters offset by ``lo`` (statistically independent streams), then the
-    chain blocks are all_gather-ed along the walker axis — on the device over NCCL when the
-    backend is nccl (the stored chain never leaves HBM before the collective).
+    chain blocks are all_gather-ed along the walker axis — on the device when the backend is nccl
+    (the stored chain never leaves HBM before the collective).
+
+    ``fused`` (nccl, equal shards, at most 16 ranks): the collective is fused into the sampler
+    kernel — every rank's kernel stores its rows into the gathered buffer of every rank (peer memory
+    over NVLink / NVSwitch, :class:`PeerChainBuffers`) while it samples, so nothing of the all_gather
+    is left after the run but a barrier.  The gathered tensor then aliases a buffer that the next
+    fused gather of the same shape overwrites (``to_host=True`` copies it).  ``fused=False``: one NCCL
+    ``all_gather_into_tensor`` after the run.
 
     ``sampler_factory(nwalkers_local)`` builds the rank-local EnsembleSampler.  Returns
     (sampler, chain): the gathered (nsteps, nwalkers, ndim) chain as a NumPy array
@@ -271,6 +335,16 @@ def sharded_ensemble(sampler_factory, p0, nsteps, gather=True, to_host=True, **r
     if not gather or world == 1:
         s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, **run_kwargs)
         return s, s.get_chain()
+    from . import _lib
+    if (fused and dist.get_backend() == "nccl" and len(p0) % world == 0 and world - 1 <= _lib.MAX_PEERS
+            and not run_kwargs.get("record_proposals")):
+        hd = s.log_prob_fn.gp._hd
+        bufs = PeerChainBuffers.get(hd.lib, hd.device, int(nsteps), len(p0), s.ndim)
+        dist.barrier()                                           # nobody still reads the buffers of an earlier gather
+        s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, store="device", gather=bufs.spec(lo), **run_kwargs)
+        torch.cuda.synchronize(hd.device)
+        dist.barrier()                                           # every rank's kernel has finished: all columns are in place
+        return s, (_to_host(bufs.chain) if to_host else bufs.chain)
     if dist.get_backend() == "nccl":
         s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, store="device", **run_kwargs)
         local = s.device_chain

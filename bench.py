@@ -514,19 +514,57 @@ def main():
     del _w1, _w2
     es.device_chain = es.device_log_prob = None
     es._device_rows_pending = False
+    # N > 1: the chain-block all_gather is FUSED into the sampler kernel (every rank's kernel stores its
+    # rows into the gathered buffer of every rank over NVLink, parallel.PeerChainBuffers); what is left of
+    # the collective inside the timed region is the barrier that tells a rank all columns are in place
+    fused = world > 1 and WALKERS_TOTAL % world == 0
+    bufs = par.PeerChainBuffers.get(lib, local, MCMC_STEPS, WALKERS_TOTAL, d5) if fused else None
+    if fused:
+        es.run_mcmc(None, MCMC_STEPS, store="device", walker_offset=wlo, gather=bufs.spec(wlo))     # warm-up of this route
+        torch.cuda.synchronize()
+        dist.barrier()
+        es.device_chain = es.device_log_prob = None
+        es._device_rows_pending = False          # (pending device rows would be copied to the host by the next run)
     barrier()
+    # the unfused route (one NCCL all_gather_into_tensor per array after the run), timed for comparison
+    mc_nccl_s = None
+    if world > 1:
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        es.run_mcmc(None, MCMC_STEPS, store="device", walker_offset=wlo)
+        _w1 = par.allgather_walkers(es.device_chain, WALKERS_TOTAL)
+        _w2 = par.allgather_walkers(es.device_log_prob, WALKERS_TOTAL)
+        u1.record()
+        barrier()
+        mc_nccl_s = max_over_ranks(u0.elapsed_time(u1) * 1e-3)
+        del _w1, _w2
+        es.device_chain = es.device_log_prob = None
+        es._device_rows_pending = False
+        barrier()
     mc_launch0 = lib.ab_launch_counter()
     m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     m0.record()
-    es.run_mcmc(None, MCMC_STEPS, store="device", walker_offset=wlo)
-    full_chain = par.allgather_walkers(es.device_chain, WALKERS_TOTAL)
-    full_logp = par.allgather_walkers(es.device_log_prob, WALKERS_TOTAL)
+    if fused:
+        es.run_mcmc(None, MCMC_STEPS, store="device", walker_offset=wlo, gather=bufs.spec(wlo))
+        torch.cuda.synchronize()
+        dist.barrier()
+        full_chain, full_logp = bufs.chain, bufs.log_prob
+    else:
+        es.run_mcmc(None, MCMC_STEPS, store="device", walker_offset=wlo)
+        full_chain = par.allgather_walkers(es.device_chain, WALKERS_TOTAL)
+        full_logp = par.allgather_walkers(es.device_log_prob, WALKERS_TOTAL)
     m1.record()
     barrier()
     mc_dev_s = max_over_ranks(m0.elapsed_time(m1) * 1e-3)
     mc_kernel_s = max_over_ranks(es.last_run_device_seconds)
     mc_launches = sum_over_ranks(lib.ab_launch_counter() - mc_launch0)
     gathered_ok = tuple(full_chain.shape) == (MCMC_STEPS, WALKERS_TOTAL, d5)
+    if fused:
+        # every rank's columns of the last stored row arrived in THIS rank's buffer: they equal what the owner holds
+        last_local = es.device_chain[-1].contiguous()
+        rows = [torch.empty_like(last_local) for _ in range(world)]
+        dist.all_gather(rows, last_local)
+        gathered_ok = gathered_ok and bool(torch.equal(torch.cat(rows, dim=0), full_chain[-1]))
     acc = float(es.acceptance_fraction.mean())
     alpha5_host = np.array(gp5._alpha) if (rank == 0 and world == 1) else None
     del full_chain, full_logp
@@ -585,6 +623,10 @@ def main():
             "kernel_only": WALKERS_TOTAL * MCMC_STEPS / mc_kernel_s, "acceptance": acc,
             "gathered_chain_ok": bool(gathered_ok), "gpu_launches": int(mc_launches),
             "allgather_bytes_per_rank": int(chain_bytes / world + MCMC_STEPS * WALKERS_TOTAL * 8 / world),
+            "allgather": ("fused into the sampler kernel: every rank's kernel stores its chain rows into the gathered buffer of "
+                          "every rank (peer memory over NVLink, CUDA IPC); the timed region ends with the barrier that says all "
+                          "columns are in place") if fused else ("none (one GPU)" if world == 1 else "NCCL all_gather_into_tensor after the run"),
+            "value_with_nccl_allgather_after_the_run": (WALKERS_TOTAL * MCMC_STEPS / mc_nccl_s) if mc_nccl_s else None,
             "d2h_bytes": chain_bytes + (int(MCMC_STEPS * WALKERS_TOTAL * 8) if world == 1 else 0),
             "roofline": {"bound": "fp64_fma", "kernel": "ensemble_kernel (wide unit), c5: N=16384, d=20",
                          "achieved": mc_ach, "peak": fma_peak.value, "unit": "TFLOP/s (per GPU)",

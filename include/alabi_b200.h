@@ -167,6 +167,7 @@ int ab_gp_import_state_full(ab_gp* h, const double* d_L, const double* d_Dinv /*
 
 /* K5: emcee.EnsembleSampler(...).run_mcmc over lnprob = surrogate mean + uniform
  * (optionally times independent normal) prior (alabi/core.py:2073-2100, 2319-2325). */
+#define AB_MAX_PEERS 15
 typedef struct ab_ensemble_config {
     int nwalkers;
     int nsteps;            /* ensemble steps to run in this call */
@@ -194,6 +195,18 @@ typedef struct ab_ensemble_config {
                             * 0 = dataflow (a proposal waits for its partner's versioned record only; default),
                             * 1 = a grid barrier per half-step.  Identical chains. */
     double prior_mu[AB_MAX_DIM_PUBLIC], prior_sd[AB_MAX_DIM_PUBLIC];
+    /* Fused all_gather of chain blocks (sub-ensembles sharded over GPUs): the stored rows
+     * are written as columns [chain_walker_offset, + nwalkers) of rows of chain_row_walkers walkers
+     * (0 = nwalkers: a private block), into d_chain / d_logp_chain AND into the same places of
+     * n_chain_peers other buffers (peer memory of the other GPUs, ab_peer_open) by the sampler kernel
+     * itself, so the collective costs no launch and no pass over the chain after the run.  The caller
+     * synchronises the ranks (all kernels finished) before anybody reads a gathered buffer. */
+    int64_t chain_row_walkers;
+    int64_t chain_walker_offset;
+    int n_chain_peers;     /* 0 .. AB_MAX_PEERS */
+    int reserved3;
+    void* chain_peers[AB_MAX_PEERS];
+    void* logp_chain_peers[AB_MAX_PEERS];
 } ab_ensemble_config;
 
 /* d_coords (nwalkers x d) and d_logp (nwalkers) are in/out state; d_naccept is
@@ -272,6 +285,18 @@ int ab_nccl_allgather(ab_comm* c, const void* d_send, void* d_recv /* world x nb
  * the same inputs and hyper-parameters (ab_gp_set_inputs / ab_gp_set_kernel).  Returns after the
  * transfer has completed. */
 int ab_nccl_broadcast_gp(ab_comm* c, ab_gp* h, int root);
+
+/* Peer memory between the processes of one box (one process per GPU): a device buffer that the
+ * sampler kernels of the other ranks write their chain blocks into (ab_ensemble_config.chain_peers).
+ * ab_peer_alloc allocates it (cudaMalloc) and fills the 64-byte handle that travels to the other
+ * processes by any host channel; ab_peer_open maps another rank's buffer into this process (CUDA IPC,
+ * peer access over NVLink / NVSwitch enabled on first use); ab_peer_close unmaps it, ab_peer_free
+ * releases the owner's allocation (after every rank has closed it). */
+#define AB_PEER_HANDLE_BYTES 64
+int ab_peer_alloc(int device, size_t bytes, void** d_ptr, unsigned char* h_handle);
+int ab_peer_open(int device, const unsigned char* h_handle, void** d_ptr);
+int ab_peer_close(int device, void* d_ptr);
+int ab_peer_free(int device, void* d_ptr);
 
 /* k-fold cross-validation of hyper-parameter candidates as one batched job
  * (gp_utils.optimize_gp_kfold_cv and its per-candidate worker, alabi/gp_utils.py:511-637, 640-1231;

@@ -193,3 +193,33 @@ def test_dataflow_schedule_gives_the_barrier_schedules_chain(kind, n, d, nw, rs,
     st = s.run_mcmc(None, 40 * thin, store=False)
     np.testing.assert_array_equal(st.coords, runs[0][3])
     np.testing.assert_array_equal(st.log_prob, runs[0][4])
+
+
+@pytest.mark.parametrize("nw,n,d", [(64, 300, 3), (4800, 700, 2)])
+def test_gathered_chain_layout_and_second_destination(nw, n, d):
+    """The fused all_gather of chain blocks on one GPU: the kernel writes its stored rows as columns
+    [column, column + nwalkers) of wider rows, into its own buffer AND into a second destination (the
+    role a peer GPU's buffer plays over NVLink).  Both must hold exactly the chain of a plain run, the
+    other columns stay untouched; small units (dataflow schedule) and the wide unit."""
+    import torch
+    from alabi_b200.ensemble import EnsembleSampler
+    g, lp, lp_oracle, rng, b = surrogate("ExpSquaredKernel", n, d, 5, [(-2.0, 2.0)] * d)
+    p0 = rng.uniform(-1.5, 1.5, size=(nw, d))
+    steps, thin, col, total = 9, 2, 5, nw + 11
+    plain = EnsembleSampler(nw, d, lp, seed=31)
+    plain.run_mcmc(p0, steps, thin_by=thin, walker_offset=col)
+    dev = f"cuda:{g._hd.device}"
+    own_c = torch.full((steps, total, d), -7.0, dtype=torch.float64, device=dev)
+    own_l = torch.full((steps, total), -7.0, dtype=torch.float64, device=dev)
+    peer_c, peer_l = own_c.clone(), own_l.clone()
+    spec = {"chain": own_c, "log_prob": own_l, "nwalkers_total": total, "column": col,
+            "peer_chain_ptrs": [peer_c.data_ptr()], "peer_log_prob_ptrs": [peer_l.data_ptr()]}
+    s = EnsembleSampler(nw, d, lp, seed=31)
+    s.run_mcmc(p0, steps, thin_by=thin, walker_offset=col, store="device", gather=spec)
+    torch.cuda.synchronize()
+    for c_, l_ in ((own_c, own_l), (peer_c, peer_l)):
+        np.testing.assert_array_equal(c_[:, col:col + nw].cpu().numpy(), plain.get_chain())
+        np.testing.assert_array_equal(l_[:, col:col + nw].cpu().numpy(), plain.get_log_prob())
+        assert bool((c_[:, :col] == -7.0).all()) and bool((c_[:, col + nw:] == -7.0).all())
+        assert bool((l_[:, :col] == -7.0).all()) and bool((l_[:, col + nw:] == -7.0).all())
+    np.testing.assert_array_equal(s.get_chain(), plain.get_chain())

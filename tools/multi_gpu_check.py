@@ -61,6 +61,19 @@ out["ensemble_gather"] = bool(chain.shape == (steps, nw, d) and np.array_equal(c
 ref = EnsembleSampler(hi - lo, d, lp, seed=5)
 ref.run_mcmc(p0[lo:hi], steps, walker_offset=lo)
 out["ensemble_reproducible"] = bool(np.array_equal(ref.get_chain(), s.get_chain()))
+# the fused gather (the sampler kernels store into every rank's buffer over NVLink, default with nccl)
+# and the NCCL all_gather after the run deliver the same gathered chain on EVERY rank
+if world > 1:
+    s_u, chain_u = par.sharded_ensemble(lambda k: EnsembleSampler(k, d, lp, seed=5), p0, steps, fused=False)
+    out["ensemble_fused_equals_nccl_gather"] = bool(np.array_equal(chain, chain_u))
+    # a larger, wide-unit ensemble with thinning, twice through the same cached peer buffers
+    nw2 = 4736 * 2
+    p2 = rng.uniform(-1, 1, size=(nw2, d))
+    for rep_ in range(2):
+        s_f, ch_f = par.sharded_ensemble(lambda k: EnsembleSampler(k, d, lp, seed=11 + rep_), p2, 6, thin_by=2)
+        s_n, ch_n = par.sharded_ensemble(lambda k: EnsembleSampler(k, d, lp, seed=11 + rep_), p2, 6, thin_by=2, fused=False)
+        out[f"ensemble_fused_wide_{rep_}"] = bool(ch_f.shape == (6, nw2, d) and np.array_equal(ch_f, ch_n)
+                                                  and np.array_equal(s_f.get_log_prob(), s_n.get_log_prob()))
 
 # the library's own NCCL communicator (ab_nccl_*): factor state handle to handle, all_gather of records
 if world > 1:
