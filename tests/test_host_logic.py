@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.ab_version() == 100
-    assert ctypes.sizeof(_lib.EnsembleConfig) == lib.ab_sizeof_ensemble_config() == 8 * 4 + 8 * 6 + 4 * 32 * 8 + 8 + 2 * 32 * 8
+    assert ctypes.sizeof(_lib.EnsembleConfig) == lib.ab_sizeof_ensemble_config() == 8 * 4 + 8 * 6 + 4 * 32 * 8 + 8 + 2 * 32 * 8 + 2 * 8 + 2 * 4 + 2 * 15 * 8
 
 
 def test_header_is_plain_c_and_links(tmp_path):
