@@ -480,3 +480,22 @@ def test_shared_point_cache_host_logic():
     assert g.calls == 2
     mu, var = sp.predict(np.zeros((5, 3)))           # a batch goes to the plain predict
     assert g.calls == 2 and mu.shape == (5,)
+
+
+def test_exp_half_sequence_has_the_bits_of_the_general_exponential(tmp_path):
+    """common.cuh's ab_exp_neg_half(r2) (the squared-exponential kernel's exponential with the factor
+    -1/2 folded into its constants, two FP64 issue slots cheaper) must return the bits of
+    ab_exp_neg(-0.5 r2): both operation sequences restated in C (correctly rounded fma / mul / add on
+    either machine) agree on 2e7 random and special arguments, within 1 ulp of libm."""
+    import subprocess
+    exe = str(tmp_path / "exp_half")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "csrc", "exp_half_identity.c"), "-lm"],
+                   check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert " mismatches 0 " in out.stdout
+    assert float(out.stdout.split()[-1]) < 4.5e-16
+    # and the library really uses it: the constants of the restatement are the header's
+    src = open(os.path.join(ROOT, "alabi_b200", "csrc", "common.cuh")).read()
+    for token in ("-46.16624130844683", "0x1.62e42fee00000p-6", "0x1.a39ef35793c76p-38", "0x40961800"):
+        assert token in src
