@@ -61,7 +61,7 @@ struct EnsArgs {
     // stored rows: walker w of stored row r sits at r * chain_ld + chain_off + w of chain_dst[0] (= chain)
     // and of the n_dst - 1 peer buffers behind it (fused all_gather of chain blocks)
     long long chain_ld, chain_off;
-    int n_dst;
+    int n_dst, chain_vec;         // chain_vec: d is even and every destination is 16-byte aligned (double2 row stores)
     double* chain_dst[AB_MAX_PEERS + 1]; double* logp_dst[AB_MAX_PEERS + 1];
     // dataflow schedule (FLOW kernels): ring of AB_ENS_RING versions of every walker's position,
     // one 16-byte line {lo, flag, hi, flag} per coordinate, flag = version + 1 (0 = never written)
@@ -172,6 +172,8 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
     __shared__ int sW[NPB][NU][P], sInside[NU][P], sPartner[NPB][NU][P];
     __shared__ double sPrior[NU][P];             // ln of the normal part of the prior at the proposal
     __shared__ int sSliceLast;                   // split units: this CTA delivered the last slice of its unit
+    __shared__ int sAccF[WIDE ? P : 1];          // wide unit: accept flags and stored log-probabilities of the unit,
+    __shared__ double sLpOut[WIDE ? P : 1];      // handed from the proposal lanes to the cooperative row stores
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int WS = A.ws, G = EW / WS;
@@ -630,7 +632,10 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                                 for (int k = 0; k < d; k++) A.rec_q[r * d + k] = sQ[unit][e][k];
                                 A.rec_lp[r] = lp_q;
                             }
-                            if (store_row >= 0) {
+                            if constexpr (WIDE) {
+                                sAccF[e] = acc ? 1 : 0;                      // rows are stored by the whole CTA below
+                                sLpOut[e] = lp_s;
+                            } else if (store_row >= 0) {
                                 const long long r = store_row * A.chain_ld + A.chain_off + w;
 #pragma unroll 1
                                 for (int pd = 0; pd < A.n_dst; pd++) {       // own buffer, then the peers' (NVLink stores)
@@ -639,6 +644,38 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                                     A.logp_dst[pd][r] = lp_s;
                                 }
                             }
+                        }
+                    }
+                }
+                if constexpr (WIDE) {
+                    // Stored rows of the unit's 32 walkers, written by ALL warps: 16-byte stores, the d / 2
+                    // chunks of a walker's row on consecutive lanes (whole 32-byte sectors per row instead of
+                    // d scattered 8-byte stores per lane -- what the peer destinations over NVLink need: as
+                    // scalar stores of the proposal lanes the fused all_gather cost 14 % of the kernel at 8 GPUs)
+                    if (store_row >= 0 && finisher) {
+                        csync();                                         // sAccF / sLpOut / sQ / sS of this unit are complete
+                        const long long rbase = store_row * A.chain_ld + A.chain_off;
+                        if (A.chain_vec) {
+                            const int half = d >> 1, per_dst = P * half;
+                            for (int idx = tid; idx < A.n_dst * per_dst; idx += ETHREADS) {
+                                const int pd = idx / per_dst, rem = idx - pd * per_dst, e = rem / half, c2 = (rem - e * half) * 2;
+                                const int w = sW[0][0][e];
+                                if (w < 0) continue;
+                                const double* srow = sAccF[e] ? &sQ[0][e][0] : &sS[0][e][0];
+                                *reinterpret_cast<double2*>(A.chain_dst[pd] + (rbase + w) * d + c2) = make_double2(srow[c2], srow[c2 + 1]);
+                            }
+                        } else {
+                            const int per_dst = P * d;
+                            for (int idx = tid; idx < A.n_dst * per_dst; idx += ETHREADS) {
+                                const int pd = idx / per_dst, rem = idx - pd * per_dst, e = rem / d, k = rem - e * d;
+                                const int w = sW[0][0][e];
+                                if (w < 0) continue;
+                                A.chain_dst[pd][(rbase + w) * d + k] = sAccF[e] ? sQ[0][e][k] : sS[0][e][k];
+                            }
+                        }
+                        for (int idx = tid; idx < A.n_dst * P; idx += ETHREADS) {
+                            const int pd = idx / P, e = idx - pd * P, w = sW[0][0][e];
+                            if (w >= 0) A.logp_dst[pd][rbase + w] = sLpOut[e];
                         }
                     }
                 }
@@ -819,6 +856,9 @@ static int ens_enqueue(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords
         A.chain_dst[1 + q] = static_cast<double*>(cfg->chain_peers[q]);
         A.logp_dst[1 + q] = static_cast<double*>(cfg->logp_chain_peers[q]);
     }
+    A.chain_vec = (h->d % 2 == 0) ? 1 : 0;
+    for (int q = 0; q < A.n_dst; q++)
+        if (reinterpret_cast<uintptr_t>(A.chain_dst[q]) & 15) A.chain_vec = 0;
     A.barrier = reinterpret_cast<unsigned long long*>(h->scratch);
     A.nan_flag = reinterpret_cast<int*>(h->scratch + 1);
     A.dbg = cfg->reserved == 1 ? reinterpret_cast<long long*>(h->scratch + 16) : nullptr;

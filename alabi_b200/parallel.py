@@ -297,8 +297,14 @@ class PeerChainBuffers:
     def spec(self, column):
         """What ``EnsembleSampler.run_mcmc(gather=...)`` takes: this rank's walkers are columns
         [column, column + nwalkers_local) of every row."""
+        import os
+        peers = list(self.peers)
+        rep = int(os.environ.get("ALABI_B200_PEER_REPEAT", "1"))     # development: the store volume of more ranks on few GPUs
+        if rep > 1:
+            from . import _lib
+            peers = (peers * rep)[:_lib.MAX_PEERS]
         return {"chain": self.chain, "log_prob": self.log_prob, "nwalkers_total": self.shape[1], "column": int(column),
-                "peer_chain_ptrs": list(self.peers), "peer_log_prob_ptrs": [p + self._lp_off for p in self.peers]}
+                "peer_chain_ptrs": peers, "peer_log_prob_ptrs": [p + self._lp_off for p in peers]}
 
 
 def _tensor_at(ptr, shape, device):
