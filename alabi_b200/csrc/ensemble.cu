@@ -32,7 +32,8 @@
 #endif
 
 #ifndef AB_ENS_WARP_RING
-#define AB_ENS_WARP_RING 1        // streamed wide unit: 1 = a private cp.async ring per warp (no CTA barrier per chunk), 0 = one ring per CTA
+#define AB_ENS_WARP_RING 2        // streamed wide unit: 2 = a private ring per warp filled by bulk copies (cp.async.bulk + mbarrier: one
+                                  // instruction per 256-byte row slice), 1 = the same ring filled by 16-byte cp.async, 0 = one ring per CTA
 #endif
 
 namespace {
@@ -220,6 +221,24 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (resident) { load_resident(); __syncthreads(); }
+#if AB_ENS_WARP_RING == 2
+    // bulk-copy ring of the streamed wide unit: one mbarrier per (buffer, warp); the rows k >= d of both
+    // buffers (padding dimensions) are zeroed once, no copy ever touches them
+    __shared__ __align__(8) unsigned long long wbar[2][WIDE ? EW : 1];
+    unsigned wphase = 0;                             // bit b: parity of this warp's next wait on buffer b
+    if (WIDE && !resident) {
+        if (tid < 2 * EW) {
+            const unsigned ba = (unsigned)__cvta_generic_to_shared(&wbar[tid / EW][tid % EW]);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ba) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int idx = tid; idx < 2 * (D - d) * CH; idx += ETHREADS) {
+            const int b2 = idx / ((D - d) * CH), rem = idx - b2 * (D - d) * CH;
+            sm[b2 * ((D + 1) * CH) + d * CH + rem] = 0.0;
+        }
+        __syncthreads();
+    }
+#endif
     unsigned long long flow_prev_target = 0;
     bool flow_have_prev = false;
     if constexpr (FLOW) {
@@ -487,7 +506,43 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                             }
                             asm volatile("cp.async.commit_group;" ::: "memory");
                         };
-#if AB_ENS_WARP_RING
+#if AB_ENS_WARP_RING == 2
+                        (void)issue_slice;
+                        // row slices of `per` points (256 B at per = 32) by bulk copies: lane k issues row k (lane d
+                        // the alpha row), completion on the warp's own mbarrier of that buffer
+                        auto issue_bulk = [&](long long c0, int buf) {
+                            const unsigned ba = (unsigned)__cvta_generic_to_shared(&wbar[buf][warp]);
+                            const unsigned row_bytes = (unsigned)per * 8u;
+                            if (lane == 0)
+                                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"((unsigned)(d + 1) * row_bytes) : "memory");
+                            __syncwarp();
+                            for (int k = lane; k <= d; k += 32) {
+                                const double* src = (k < d) ? A.XsT + (long long)k * A.npad + c0 + j0 : A.alpha + c0 + j0;
+                                const unsigned da = (unsigned)__cvta_generic_to_shared(sm + buf * BUF + (k < d ? k : D) * CH + j0);
+                                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                             ::"r"(da), "l"(src), "r"(row_bytes), "r"(ba) : "memory");
+                            }
+                        };
+                        auto wait_bulk = [&](int buf) {
+                            const unsigned ba = (unsigned)__cvta_generic_to_shared(&wbar[buf][warp]);
+                            const unsigned par = (wphase >> buf) & 1u;
+                            unsigned ok;
+                            do {
+                                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                             : "=r"(ok) : "r"(ba), "r"(par) : "memory");
+                            } while (!ok);
+                            wphase ^= 1u << buf;
+                        };
+                        if (c_lo < c_hi) issue_bulk((long long)c_lo * CH, 0);
+                        for (int c = c_lo; c < c_hi; c++) {
+                            const int buf = (c - c_lo) & 1;
+                            if (c + 1 < c_hi) issue_bulk((long long)(c + 1) * CH, buf ^ 1);     // that buffer was read out before the
+                            wait_bulk(buf);                                                    // __syncwarp that closed chunk c - 1
+                            const double* bX = sm + buf * BUF;
+                            eval_wide(bX, bX + D * CH, CH);
+                            __syncwarp();
+                        }
+#elif AB_ENS_WARP_RING
                         if (c_lo < c_hi) issue_slice((long long)c_lo * CH, 0);
                         for (int c = c_lo; c < c_hi; c++) {
                             if (c + 1 < c_hi) issue_slice((long long)(c + 1) * CH, (c + 1 - c_lo) & 1);
