@@ -259,40 +259,75 @@ class PeerChainBuffers:
     ndim) chain and a (nsteps, nwalkers_total) log-probability buffer (one cudaMalloc, exported with
     CUDA IPC) and maps the buffers of all other ranks, so that the sampler kernel of rank r can write
     its columns into all of them (``ab_ensemble_config.chain_peers``).  Built collectively (one
-    ``all_gather_object`` of the 64-byte handles); cached per shape for the life of the process."""
-    _cache = {}
+    ``all_gather_object`` of the 64-byte handles); the two most recent shapes stay cached (an older one
+    is released collectively, every rank evicting in the same order).  ``get`` returns None on EVERY
+    rank when any rank could not allocate or map (no peer access, out of memory): the caller then takes
+    the NCCL route."""
+    _cache = {}                     # insertion ordered: least recently used first
+    MAX_CACHED = 2
 
     @classmethod
     def get(cls, lib, device, nsteps, nwalkers_total, ndim):
         key = (int(device), int(nsteps), int(nwalkers_total), int(ndim))
-        if key not in cls._cache:
-            cls._cache[key] = cls(lib, *key)
-        return cls._cache[key]
+        if key in cls._cache:
+            cls._cache[key] = cls._cache.pop(key)                # most recently used last
+            return cls._cache[key]
+        while len(cls._cache) >= cls.MAX_CACHED:
+            cls._cache.pop(next(iter(cls._cache))).release()
+        bufs = cls(lib, *key)
+        if not bufs.ok:
+            bufs.release()
+            return None
+        cls._cache[key] = bufs
+        return bufs
 
     def __init__(self, lib, device, nsteps, nwalkers_total, ndim):
         import ctypes
         import torch
         from . import _lib
         dist = _dist()
+        self._lib, self._device = lib, device
         self.shape = (nsteps, nwalkers_total, ndim)
         nchain = nsteps * nwalkers_total * ndim * 8
         self._lp_off = (nchain + 255) // 256 * 256
         nbytes = self._lp_off + nsteps * nwalkers_total * 8
         own, hnd = ctypes.c_void_p(), (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES)()
-        _lib.check(lib.ab_peer_alloc(device, nbytes, ctypes.byref(own), hnd), "ab_peer_alloc")
-        self.own = own.value
+        good = lib.ab_peer_alloc(device, nbytes, ctypes.byref(own), hnd) == 0
+        self.own = own.value if good else None
         handles = [None] * dist.get_world_size()
-        dist.all_gather_object(handles, bytes(hnd))
+        dist.all_gather_object(handles, bytes(hnd) if good else None)
         self.peers = []                                          # base pointers of the other ranks' buffers, by rank order
-        for r, hb in enumerate(handles):
-            if r == dist.get_rank():
-                continue
-            p = ctypes.c_void_p()
-            buf = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES).from_buffer_copy(hb)
-            _lib.check(lib.ab_peer_open(device, buf, ctypes.byref(p)), "ab_peer_open")
-            self.peers.append(p.value)
-        self.chain = _tensor_at(self.own, (nsteps, nwalkers_total, ndim), device)
-        self.log_prob = _tensor_at(self.own + self._lp_off, (nsteps, nwalkers_total), device)
+        good = good and all(hb is not None for hb in handles)
+        if good:
+            for r, hb in enumerate(handles):
+                if r == dist.get_rank():
+                    continue
+                p = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES).from_buffer_copy(hb)
+                if lib.ab_peer_open(device, buf, ctypes.byref(p)) != 0:
+                    good = False
+                    break
+                self.peers.append(p.value)
+        flag = torch.tensor([1.0 if good else 0.0], device=f"cuda:{device}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)              # usable only if every rank mapped every buffer
+        self.ok = bool(flag.item() == 1.0)
+        if self.ok:
+            self.chain = _tensor_at(self.own, (nsteps, nwalkers_total, ndim), device)
+            self.log_prob = _tensor_at(self.own + self._lp_off, (nsteps, nwalkers_total), device)
+
+    def release(self):
+        """Collective: unmap the peers' buffers, then (after everybody has) free the own one."""
+        import torch
+        dist = _dist()
+        torch.cuda.synchronize(self._device)
+        self.chain = self.log_prob = None
+        for p in self.peers:
+            self._lib.ab_peer_close(self._device, p)
+        self.peers = []
+        dist.barrier()
+        if self.own is not None:
+            self._lib.ab_peer_free(self._device, self.own)
+            self.own = None
 
     def spec(self, column):
         """What ``EnsembleSampler.run_mcmc(gather=...)`` takes: this rank's walkers are columns
@@ -346,11 +381,12 @@ def sharded_ensemble(sampler_factory, p0, nsteps, gather=True, to_host=True, fus
             and not run_kwargs.get("record_proposals")):
         hd = s.log_prob_fn.gp._hd
         bufs = PeerChainBuffers.get(hd.lib, hd.device, int(nsteps), len(p0), s.ndim)
-        dist.barrier()                                           # nobody still reads the buffers of an earlier gather
-        s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, store="device", gather=bufs.spec(lo), **run_kwargs)
-        torch.cuda.synchronize(hd.device)
-        dist.barrier()                                           # every rank's kernel has finished: all columns are in place
-        return s, (_to_host(bufs.chain) if to_host else bufs.chain)
+        if bufs is not None:
+            dist.barrier()                                       # nobody still reads the buffers of an earlier gather
+            s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, store="device", gather=bufs.spec(lo), **run_kwargs)
+            torch.cuda.synchronize(hd.device)
+            dist.barrier()                                       # every rank's kernel has finished: all columns are in place
+            return s, (_to_host(bufs.chain) if to_host else bufs.chain)
     if dist.get_backend() == "nccl":
         s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, store="device", **run_kwargs)
         local = s.device_chain

@@ -519,6 +519,7 @@ def main():
     # the collective inside the timed region is the barrier that tells a rank all columns are in place
     fused = world > 1 and WALKERS_TOTAL % world == 0
     bufs = par.PeerChainBuffers.get(lib, local, MCMC_STEPS, WALKERS_TOTAL, d5) if fused else None
+    fused = bufs is not None                                   # no peer access: the NCCL route
     if fused:
         es.run_mcmc(None, MCMC_STEPS, store="device", walker_offset=wlo, gather=bufs.spec(wlo))     # warm-up of this route
         torch.cuda.synchronize()

@@ -74,6 +74,10 @@ if world > 1:
         s_n, ch_n = par.sharded_ensemble(lambda k: EnsembleSampler(k, d, lp, seed=11 + rep_), p2, 6, thin_by=2, fused=False)
         out[f"ensemble_fused_wide_{rep_}"] = bool(ch_f.shape == (6, nw2, d) and np.array_equal(ch_f, ch_n)
                                                   and np.array_equal(s_f.get_log_prob(), s_n.get_log_prob()))
+    # a third shape: the least recently used peer buffers are released collectively and new ones mapped
+    s_3, ch_3 = par.sharded_ensemble(lambda k: EnsembleSampler(k, d, lp, seed=5), p0, 7)
+    s_4, ch_4 = par.sharded_ensemble(lambda k: EnsembleSampler(k, d, lp, seed=5), p0, 7, fused=False)
+    out["ensemble_fused_after_eviction"] = bool(np.array_equal(ch_3, ch_4) and len(par.PeerChainBuffers._cache) == 2)
 
 # the library's own NCCL communicator (ab_nccl_*): factor state handle to handle, all_gather of records
 if world > 1:
