@@ -1,6 +1,6 @@
 """Per-kernel SASS evidence for the built library: counts of the instructions that tell which
 hardware path a kernel uses (DMMA = FP64 tensor pipe, DFMA/DADD/DMUL = FP64 ALU, LDGSTS = cp.async,
-UTMALDG = TMA, UTC*MMA / LDTM = tcgen05 / TMEM), registers and spills from cuobjdump -res-usage.
+UBLKCP = bulk copy (cp.async.bulk, the 1-D TMA path), UTMALDG = tensor-map TMA, UTC*MMA / LDTM = tcgen05 / TMEM), registers and spills from cuobjdump -res-usage.
 
     python tools/sass_summary.py > profiles/sass_summary.txt
 """
@@ -19,7 +19,7 @@ for ln in res.splitlines():
     m = re.search(r"REG:(\d+).*?SHARED:(\d+).*?LOCAL:(\d+)", ln)
     if m and cur:
         usage[cur] = (int(m.group(1)), int(m.group(2)), int(m.group(3)))
-keys = ["DMMA", "DFMA", "DADD", "DMUL", "LDGSTS", "UTMALDG", "UTCMMA", "LDTM", "LDS", "LDG", "BAR"]
+keys = ["DMMA", "DFMA", "DADD", "DMUL", "LDGSTS", "UBLKCP", "UTMALDG", "UTCMMA", "LDTM", "LDS", "LDG", "BAR"]
 counts, arch = collections.OrderedDict(), set()
 cur = None
 for ln in sass.splitlines():
