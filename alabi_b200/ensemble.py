@@ -271,13 +271,16 @@ class EnsembleSampler:
         self._naccepted += nacc.cpu().numpy()
         if on_device:
             # the stored rows stay in HBM; get_chain() / get_log_prob() copy them on first use
-            if gather is not None:
-                # own columns of the gathered buffers, copied: the buffers are reused by the next gather
-                c0 = int(gather["column"])
-                chain, lpc = chain[:, c0:c0 + self.nwalkers].clone(), lpc[:, c0:c0 + self.nwalkers].clone()
-            self.device_chain, self.device_log_prob = chain, lpc
-            self._device_rows_pending = True
-            self.iteration += int(nsteps)
+            if gather is not None and not gather.get("keep_local", True):
+                pass                             # the caller (parallel.sharded_ensemble) attaches the rows when all pieces are in
+            else:
+                if gather is not None:
+                    # own columns of the gathered buffers, copied: the buffers are reused by the next gather
+                    c0 = int(gather["column"])
+                    chain, lpc = chain[:, c0:c0 + self.nwalkers].clone(), lpc[:, c0:c0 + self.nwalkers].clone()
+                self.device_chain, self.device_log_prob = chain, lpc
+                self._device_rows_pending = True
+                self.iteration += int(nsteps)
         elif store:
             ch, lh = hbufs
             self._chain = ch if len(self._chain) == 0 else np.concatenate([self._chain, ch])

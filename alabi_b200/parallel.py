@@ -329,17 +329,22 @@ class PeerChainBuffers:
             self._lib.ab_peer_free(self._device, self.own)
             self.own = None
 
-    def spec(self, column):
+    def spec(self, column, row0=0, rows=None, keep_local=True):
         """What ``EnsembleSampler.run_mcmc(gather=...)`` takes: this rank's walkers are columns
-        [column, column + nwalkers_local) of every row."""
+        [column, column + nwalkers_local) of every row.  ``row0`` / ``rows``: the stored rows a piece of a
+        longer run writes; ``keep_local=False``: the sampler keeps no copy of its own columns."""
         import os
+        rows = self.shape[0] - row0 if rows is None else int(rows)
+        c_off = row0 * self.shape[1] * self.shape[2] * 8
+        l_off = self._lp_off + row0 * self.shape[1] * 8
         peers = list(self.peers)
         rep = int(os.environ.get("ALABI_B200_PEER_REPEAT", "1"))     # development: the store volume of more ranks on few GPUs
         if rep > 1:
             from . import _lib
             peers = (peers * rep)[:_lib.MAX_PEERS]
-        return {"chain": self.chain, "log_prob": self.log_prob, "nwalkers_total": self.shape[1], "column": int(column),
-                "peer_chain_ptrs": peers, "peer_log_prob_ptrs": [p + self._lp_off for p in peers]}
+        return {"chain": self.chain[row0:row0 + rows], "log_prob": self.log_prob[row0:row0 + rows],
+                "nwalkers_total": self.shape[1], "column": int(column), "keep_local": bool(keep_local),
+                "peer_chain_ptrs": [p + c_off for p in peers], "peer_log_prob_ptrs": [p + l_off for p in peers]}
 
 
 def _tensor_at(ptr, shape, device):
@@ -352,7 +357,7 @@ def _tensor_at(ptr, shape, device):
     return torch.as_tensor(_Mem(), device=f"cuda:{device}")
 
 
-def sharded_ensemble(sampler_factory, p0, nsteps, gather=True, to_host=True, fused=True, **run_kwargs):
+def sharded_ensemble(sampler_factory, p0, nsteps, gather=True, to_host=True, fused=True, pieces=None, **run_kwargs):
     """Independent sub-ensembles: rank r advances walkers [lo, hi) of ``p0`` with
     RNG counters offset by ``lo`` (statistically independent streams), then the
     chain blocks are all_gather-ed along the walker axis — on the device when the backend is nccl
@@ -362,7 +367,8 @@ def sharded_ensemble(sampler_factory, p0, nsteps, gather=True, to_host=True, fus
     kernel — every rank's kernel stores its rows into the gathered buffer of every rank (peer memory
     over NVLink / NVSwitch, :class:`PeerChainBuffers`) while it samples, so nothing of the all_gather
     is left after the run but a barrier.  The gathered tensor then aliases a buffer that the next
-    fused gather of the same shape overwrites (``to_host=True`` copies it).  ``fused=False``: one NCCL
+    fused gather of the same shape overwrites (``to_host=True`` copies it; large chains are then sampled
+    in ``pieces`` whose rows travel to the host while the next piece runs).  ``fused=False``: one NCCL
     ``all_gather_into_tensor`` after the run.
 
     ``sampler_factory(nwalkers_local)`` builds the rank-local EnsembleSampler.  Returns
@@ -382,11 +388,42 @@ def sharded_ensemble(sampler_factory, p0, nsteps, gather=True, to_host=True, fus
         hd = s.log_prob_fn.gp._hd
         bufs = PeerChainBuffers.get(hd.lib, hd.device, int(nsteps), len(p0), s.ndim)
         if bufs is not None:
-            dist.barrier()                                       # nobody still reads the buffers of an earlier gather
-            s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, store="device", gather=bufs.spec(lo), **run_kwargs)
-            torch.cuda.synchronize(hd.device)
-            dist.barrier()                                       # every rank's kernel has finished: all columns are in place
-            return s, (_to_host(bufs.chain) if to_host else bufs.chain)
+            # Where any rank wants the chain in host memory and it is large, the run is cut into pieces: after
+            # the barrier that closes piece b its rows are complete in every rank's buffer and travel to the
+            # host on a copy stream while piece b + 1 samples (the random streams are counter based: same chain)
+            want = torch.tensor([1.0 if to_host else 0.0], device=f"cuda:{hd.device}")
+            dist.all_reduce(want, op=dist.ReduceOp.MAX)          # also: nobody still reads the buffers of an earlier gather
+            nbytes = int(nsteps) * len(p0) * s.ndim * 8
+            npieces = min(4, int(nsteps)) if (want.item() > 0 and nbytes >= (128 << 20)) else 1
+            if pieces is not None:
+                npieces = max(1, min(int(pieces), int(nsteps)))   # (the same on every rank)
+            host, copy_stream = None, None
+            if to_host:
+                try:
+                    host = torch.empty(tuple(bufs.chain.shape), dtype=torch.float64, pin_memory=True)
+                except RuntimeError:
+                    host = torch.empty(tuple(bufs.chain.shape), dtype=torch.float64)
+                copy_stream = torch.cuda.Stream(device=hd.device)
+            per, row0 = -(-int(nsteps) // npieces), 0
+            while row0 < int(nsteps):
+                rows = min(per, int(nsteps) - row0)
+                s.run_mcmc(np.asarray(p0)[lo:hi] if row0 == 0 else None, rows, walker_offset=lo, store="device",
+                           gather=bufs.spec(lo, row0, rows, keep_local=False), **run_kwargs)
+                torch.cuda.synchronize(hd.device)
+                dist.barrier()                                   # every rank's kernel of this piece has finished
+                if to_host:
+                    with torch.cuda.stream(copy_stream):
+                        host[row0:row0 + rows].copy_(bufs.chain[row0:row0 + rows], non_blocking=True)
+                row0 += rows
+            # the sampler's own record of the run: its columns of the gathered buffers
+            s.device_chain = bufs.chain[:, lo:hi].clone()
+            s.device_log_prob = bufs.log_prob[:, lo:hi].clone()
+            s._device_rows_pending = True
+            s.iteration += int(nsteps)
+            if to_host:
+                copy_stream.synchronize()
+                return s, host.numpy()
+            return s, bufs.chain
     if dist.get_backend() == "nccl":
         s.run_mcmc(np.asarray(p0)[lo:hi], nsteps, walker_offset=lo, store="device", **run_kwargs)
         local = s.device_chain

@@ -74,6 +74,10 @@ if world > 1:
         s_n, ch_n = par.sharded_ensemble(lambda k: EnsembleSampler(k, d, lp, seed=11 + rep_), p2, 6, thin_by=2, fused=False)
         out[f"ensemble_fused_wide_{rep_}"] = bool(ch_f.shape == (6, nw2, d) and np.array_equal(ch_f, ch_n)
                                                   and np.array_equal(s_f.get_log_prob(), s_n.get_log_prob()))
+    # the same run cut into pieces (rows of piece b copied to the host while piece b + 1 samples)
+    s_p, ch_p = par.sharded_ensemble(lambda k: EnsembleSampler(k, d, lp, seed=12), p2, 6, thin_by=2, pieces=4)
+    out["ensemble_fused_pieces"] = bool(np.array_equal(ch_p, ch_n) and np.array_equal(s_p.get_chain(), s_n.get_chain())
+                                        and np.array_equal(s_p.get_log_prob(), s_n.get_log_prob()))
     # a third shape: the least recently used peer buffers are released collectively and new ones mapped
     s_3, ch_3 = par.sharded_ensemble(lambda k: EnsembleSampler(k, d, lp, seed=5), p0, 7)
     s_4, ch_4 = par.sharded_ensemble(lambda k: EnsembleSampler(k, d, lp, seed=5), p0, 7, fused=False)
