@@ -145,16 +145,17 @@ def test_large_nonresident_training_set():
     np.testing.assert_allclose(s.get_chain(), chain, rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize("d", [12, 10])
-def test_wide_streamed_split_units_replay(d):
+@pytest.mark.parametrize("d,n", [(12, 6000), (10, 6000), (32, 700)])
+def test_wide_streamed_split_units_replay(d, n):
     """Large ensemble on a training set that does not fit shared memory: the wide unit streams the
     points (per-warp rings filled by bulk copies; d = 10 runs the d = 12 kernel with two zero-padded
-    dimensions), and the points of one 32-proposal unit are split over several CTAs whose slice sums
+    dimensions; d = 32, N = 700 runs the run-time chunk length with 33 row slices per warp and chunk),
+    and the points of one 32-proposal unit are split over several CTAs whose slice sums
     are combined in slice order by the CTA that completes the unit.  The chain must still replay on
     the CPU, and must not depend on how a run is cut into pieces."""
     from alabi_b200.ensemble import EnsembleSampler
     nw = 4800
-    g, lp, lp_oracle, rng, b = surrogate("ExpSquaredKernel", 6000, d, 31, [(-2.0, 2.0)] * d)
+    g, lp, lp_oracle, rng, b = surrogate("ExpSquaredKernel", n, d, 31, [(-2.0, 2.0)] * d)
     p0 = rng.uniform(-1, 1, size=(nw, d))
     s = EnsembleSampler(nw, d, lp, seed=77)
     s.run_mcmc(p0, 5)
