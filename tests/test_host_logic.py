@@ -499,3 +499,22 @@ def test_exp_half_sequence_has_the_bits_of_the_general_exponential(tmp_path):
     src = open(os.path.join(ROOT, "alabi_b200", "csrc", "common.cuh")).read()
     for token in ("-46.16624130844683", "0x1.62e42fee00000p-6", "0x1.a39ef35793c76p-38", "0x40961800"):
         assert token in src
+
+
+def test_device_state_is_lazy_and_pickles_as_a_host_state():
+    """The sampler's state after a run stays on the device; it must behave like emcee's State (NumPy
+    coords / log_prob, iterable) and pickle / copy as a plain host State (model caches)."""
+    import copy
+    import pickle
+    import torch
+    from alabi_b200.ensemble import State, _DeviceState
+    c, l = torch.arange(12, dtype=torch.float64).reshape(6, 2), torch.arange(6, dtype=torch.float64)
+    st = _DeviceState(c, l)
+    assert st._host is None                                   # nothing downloaded yet
+    coords, lp, rs = st                                       # State.__iter__
+    assert isinstance(coords, np.ndarray) and coords.shape == (6, 2) and lp.shape == (6,) and rs is None
+    assert st._host is not None and st.coords is coords        # cached
+    for clone in (pickle.loads(pickle.dumps(st)), copy.deepcopy(st)):
+        assert type(clone) is State
+        np.testing.assert_array_equal(clone.coords, c.numpy())
+        np.testing.assert_array_equal(clone.log_prob, l.numpy())
