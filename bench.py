@@ -18,7 +18,11 @@ Workload = the two largest configurations of BASELINE.json (inputs from ``alabi_
 * **c5** (configs[4]: 20-D, N = 16384, "emcee 65536 walkers sharded across 8 B200") carries
   ``mcmc``: surrogate-MCMC walker-steps/s (K5), 65 536 walkers in total split into one
   sub-ensemble per rank, ``MCMC_STEPS`` stored steps, and the ``all_gather`` of the chain blocks
-  over NVLink inside the timed region.  At N = 1 the single GPU advances all 65 536 walkers.
+  over NVLink inside the timed region — fused into the sampler kernel: every rank's kernel stores
+  its rows into the gathered buffer of every rank (peer memory, ``parallel.PeerChainBuffers``), and
+  the timed region ends with the barrier after which every rank holds the whole chain
+  (``mcmc.value_with_nccl_allgather_after_the_run`` is the unfused route, timed beside it).  At
+  N = 1 the single GPU advances all 65 536 walkers.
 
 ``value`` is measured with the inputs resident in HBM (CUDA events, max over ranks).  ``e2e`` is the
 same metric through the public API on HOST buffers (``GP.predict`` on pageable NumPy arrays:
