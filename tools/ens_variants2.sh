@@ -1,5 +1,7 @@
 #!/bin/bash
 # Development: variants of the streamed wide sampler unit (round 2, second pass).
+# (Written when the sampler was one translation unit, ensemble.cu; the kernels now live in ensemble_kernel.cuh and are
+# instantiated by ensemble_k0 / k1 / k2.cu: pass the -D flags to those three files to rebuild a variant.)
 #   tools/ens_variants2.sh        build here (no GPU): cta ring (the previous product), warp ring + unroll 4
 #   tools/ens_variants2.sh run    time them on the GPU next to the product library
 set -e
