@@ -37,7 +37,6 @@ static int ens_enqueue(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords
     // segment sums of split wide units (3 kinds of half-step x units x AB_ENS_MAXSEG segments x 32 proposals)
     const int max_units = (cfg->nwalkers + 31) / 32;
     const size_t cnt_bytes = ((size_t)3 * max_units * sizeof(unsigned) + 255) / 256 * 256;
-    const size_t part_bytes = (size_t)3 * max_units * AB_ENS_MAXSEG * 32 * sizeof(double);
     // proposals per half-step; P = 4 per unit once 2 per unit would need several passes per CTA
     int n_half = (cfg->nwalkers + 1) / 2;
     if (cfg->init_logp && cfg->nsteps == 0) n_half = cfg->nwalkers;
@@ -53,7 +52,25 @@ static int ens_enqueue(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords
     // dataflow schedule (ab_ensemble_config.schedule 0 = automatic, 1 = grid barriers): small ensembles
     // whose half-steps are latency bound; the launcher drops it when the training set is not resident
     const int dpad = h->d <= 2 ? 2 : h->d <= 4 ? 4 : h->d <= 8 ? 8 : h->d <= 24 ? (h->d + 3) / 4 * 4 : 32;   // the dispatch below
-    const bool flow = p == 2 && cfg->schedule != 1 && cfg->nsteps > 0 && (size_t)h->n * (dpad + 1) * 8 <= 160 * 1024;
+    const bool resident_small = (size_t)h->n * (dpad + 1) * 8 <= 160 * 1024;
+    // Small ensemble on a training set that does not fit shared memory (emcee's default 10 x ndim walkers on
+    // an N = 8192 surrogate): a 2-proposal unit would stream all N points through ONE CTA per half-step
+    // (86 us per step at N = 8192, d = 10, whatever the walker count).  "Spread" mode runs the wide unit
+    // instead with SHORT chunks, so that the (unit, chunk) pairs of a half-step cover the GPU: every CTA
+    // evaluates 32 proposals against 128-512 points, the segment sums meet in global memory and the CTA
+    // that delivers a unit's last segment accepts (the ranged schedule of the large ensembles).
+    int ch_hint = 0, maxseg = AB_ENS_MAXSEG;
+    if (p == 2 && !resident_small && cfg->reserved < 2 && cfg->schedule != 3) {
+        p = 32;
+        const long long units = (n_half + 31) / 32;
+        ch_hint = 128;
+        for (int c = 512; c >= 128; c /= 2)
+            if (h->npad % c == 0 && units * (h->npad / c) >= 2LL * nsm) { ch_hint = c; break; }
+        maxseg = (int)(h->npad / ch_hint) + 2;
+        if (maxseg < AB_ENS_MAXSEG) maxseg = AB_ENS_MAXSEG;
+    }
+    const size_t part_bytes = (size_t)3 * max_units * maxseg * 32 * sizeof(double);
+    const bool flow = p == 2 && cfg->schedule != 1 && cfg->nsteps > 0 && resident_small;
     const size_t ring_bytes = flow ? (size_t)AB_ENS_RING * cfg->nwalkers * h->d * sizeof(uint4) : 0;
     int rc = ab_ensure_scratch(h, 4096 + cnt_bytes + part_bytes + ring_bytes);
     if (rc) return rc;
@@ -63,6 +80,8 @@ static int ens_enqueue(ab_gp* h, const ab_ensemble_config* cfg, double* d_coords
         AB_CUDA(cudaMemsetAsync(A.ring, 0, ring_bytes, h->stream));
     }
     A.max_units = max_units;
+    A.maxseg = maxseg;
+    A.ch_hint = ch_hint;
     A.slice_cnt = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(h->scratch) + 4096);
     A.slice_part = reinterpret_cast<double*>(reinterpret_cast<char*>(h->scratch) + 4096 + cnt_bytes);
     if (first) AB_CUDA(cudaMemsetAsync(A.slice_cnt, 0, cnt_bytes, h->stream));

@@ -25,6 +25,8 @@ struct EnsArgs {
     // whose chunks fall into several ranges is finished by the CTA that delivers its last segment:
     // segment sums meet in slice_part (fixed segment order), completions are counted in slice_cnt.
     int ranged, max_units;
+    int maxseg;                   // segments per unit the slice_part layout provides for
+    int ch_hint;                  // > 0 ("spread" mode, small ensembles on a large training set): chunk length to use, ranged
     double* slice_part; unsigned* slice_cnt;
     // stored rows: walker w of stored row r sits at r * chain_ld + chain_off + w of chain_dst[0] (= chain)
     // and of the n_dst - 1 peer buffers behind it (fused all_gather of chain blocks)

@@ -587,7 +587,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 // ---- split units: publish this slice's sums; the CTA that completes the unit goes on ----
                 bool finisher = true;
                 if (WIDE && nseg > 1) {
-                    double* part = A.slice_part + (((long long)slot * A.max_units + b) * AB_ENS_MAXSEG) * 32;
+                    double* part = A.slice_part + (((long long)slot * A.max_units + b) * A.maxseg) * 32;
                     if (prop_lane) {
                         double sp = 0.0;
 #pragma unroll
@@ -610,7 +610,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                     if (w >= 0) {
                         double s = 0.0;
                         if (WIDE && nseg > 1) {
-                            const double* part = A.slice_part + (((long long)slot * A.max_units + b) * AB_ENS_MAXSEG) * 32;
+                            const double* part = A.slice_part + (((long long)slot * A.max_units + b) * A.maxseg) * 32;
                             for (int x = 0; x < nseg; x++) s += __ldcg(&part[x * 32 + e]);   // segments in order
                         } else {
                         double pv[EW];                       // independent loads, then the fixed-order sum
@@ -754,6 +754,7 @@ int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half, bool one_pass_only = false) {
         const size_t per_buf = (EW == 16) ? 100 * 1024 : 48 * 1024;
         ch = 128;
         while (ch * 2 <= 1024 && A.npad % (ch * 2) == 0 && (size_t)(ch * 2) * (D + 1) * 8 <= per_buf) ch *= 2;
+        if (P == 32 && A.ch_hint > 0 && A.ch_hint <= ch && A.npad % A.ch_hint == 0) ch = A.ch_hint;
         smem = 2 * (size_t)ch * (D + 1) * 8;
     }
     A.ch = ch;
@@ -782,7 +783,16 @@ int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half, bool one_pass_only = false) {
         // gets at least 4 chunks and no unit is cut into more than AB_ENS_MAXSEG segments
         const long long nch = A.npad / ch;
         const long long share = (long long)nbatch * nch / grid_max;
-        if (share >= 4 && nch / share + 2 <= AB_ENS_MAXSEG) A.ranged = 1;
+        if (share >= 4 && nch / share + 2 <= A.maxseg) A.ranged = 1;
+        if (A.ch_hint > 0 && nch + 2 <= A.maxseg) {
+            // spread mode: few units, so the (unit, chunk) pairs themselves are dealt over the CTAs; every CTA
+            // must own at least one pair in every kind of half-step (an empty range would be counted as a
+            // segment that never arrives), so the grid is capped at the pairs of the smaller half-step
+            A.ranged = 1;
+            const long long small_items = (A.nsteps > 0) ? (A.nwalkers / 2 > 0 ? A.nwalkers / 2 : 1) : A.nwalkers;
+            const long long w_min = ((small_items + P - 1) / P) * nch;
+            if ((long long)grid > w_min) grid = (int)w_min;
+        }
     }
     if (!A.ranged && grid > nbatch) grid = nbatch;
     if (grid < 1) grid = 1;

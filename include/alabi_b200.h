@@ -193,7 +193,9 @@ typedef struct ab_ensemble_config {
     int use_normal_prior;
     int schedule;          /* small ensembles (2 proposals per unit, training set resident in shared memory):
                             * 0 = dataflow (a proposal waits for its partner's versioned record only; default),
-                            * 1 = a grid barrier per half-step.  Identical chains. */
+                            * 1 = a grid barrier per half-step.  Identical chains.  3 = as 0, and keep 2-proposal units
+                            * even when the training set does not fit shared memory (development: the automatic
+                            * choice there is the wide unit with short chunks spread over the GPU) */
     double prior_mu[AB_MAX_DIM_PUBLIC], prior_sd[AB_MAX_DIM_PUBLIC];
     /* Fused all_gather of chain blocks (sub-ensembles sharded over GPUs): the stored rows
      * are written as columns [chain_walker_offset, + nwalkers) of rows of chain_row_walkers walkers
