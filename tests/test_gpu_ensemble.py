@@ -226,3 +226,25 @@ def test_gathered_chain_layout_and_second_destination(nw, n, d):
         assert bool((c_[:, :col] == -7.0).all()) and bool((c_[:, col + nw:] == -7.0).all())
         assert bool((l_[:, :col] == -7.0).all()) and bool((l_[:, col + nw:] == -7.0).all())
     np.testing.assert_array_equal(s.get_chain(), plain.get_chain())
+
+
+@pytest.mark.parametrize("kind,n,d,nw", [("ExpSquaredKernel", 2600, 12, 150), ("Matern32Kernel", 5000, 8, 67)])
+def test_spread_mode_gives_the_streaming_units_chain(kind, n, d, nw):
+    """Small ensemble on a training set that does not fit shared memory: the automatic choice (wide unit,
+    short chunks, (unit, chunk) pairs dealt over the GPU, segment sums combined in segment order) must give
+    the chain of the 2-proposal units that stream the whole training set (schedule=3), up to the summation
+    order of the surrogate mean: same accept decisions, positions within 1e-12, and the CPU replay holds."""
+    from alabi_b200.ensemble import EnsembleSampler
+    g, lp, lp_oracle, rng, b = surrogate(kind, n, d, 41, [(-2.0, 2.0)] * d)
+    p0 = rng.uniform(-1.5, 1.5, size=(nw, d))
+    runs = []
+    for schedule in (3, 0):
+        s = EnsembleSampler(nw, d, lp, seed=777, schedule=schedule)
+        s.run_mcmc(p0, 24, thin_by=2)
+        s.run_mcmc(None, 6, thin_by=2)
+        runs.append((s.get_chain().copy(), s.get_log_prob().copy(), s._naccepted.copy()))
+    np.testing.assert_array_equal(runs[0][2], runs[1][2])
+    np.testing.assert_allclose(runs[0][0], runs[1][0], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(runs[0][1], runs[1][1], rtol=1e-10, atol=1e-10)
+    chain, lps, nacc, _ = oem.replay_device_chain(p0, lp_oracle, 60, 777)
+    np.testing.assert_allclose(runs[1][0], chain[1::2], rtol=1e-9, atol=1e-12)
