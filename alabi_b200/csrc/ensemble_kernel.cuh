@@ -349,6 +349,30 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                 first_seg = false;
                 item_sync();                                         // small units: this item's prep buffer is complete
                 // ---- gather (proposal lanes): own state and partner position, proposal ----
+                bool first_chunk_issued = false;
+#if AB_ENS_WARP_RING == 2
+                if constexpr (WIDE) {
+                    // streamed wide unit: the first chunk of this item is requested before the gather, so it
+                    // arrives while the proposal lanes fetch the walkers (the warp's buffers are free: its
+                    // reads of the previous item ended before the barriers in between)
+                    if (!resident && c_lo < c_hi) {
+                        const int per = CH / EW, j0 = warp * per;
+                        const unsigned ba = (unsigned)__cvta_generic_to_shared(&wbar[0][warp]);
+                        const unsigned row_bytes = (unsigned)per * 8u;
+                        const long long off = (long long)c_lo * CH + j0;
+                        if (lane == 0)
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"((unsigned)(d + 1) * row_bytes) : "memory");
+                        __syncwarp();
+                        for (int k = lane; k <= d; k += 32) {
+                            const double* src = (k < d) ? A.XsT + (long long)k * A.npad + off : A.alpha + off;
+                            const unsigned da = (unsigned)__cvta_generic_to_shared(sm + (k < d ? k : D) * CH + j0);
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                         ::"r"(da), "l"(src), "r"(row_bytes), "r"(ba) : "memory");
+                        }
+                        first_chunk_issued = true;
+                    }
+                }
+#endif
                 if (prop_lane) {
                     const int e = lane, w = sW[pbuf][unit][e], partner = sPartner[pbuf][unit][e];
                     int inside = 1;
@@ -498,7 +522,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                             } while (!ok);
                             wphase ^= 1u << buf;
                         };
-                        if (c_lo < c_hi) issue_bulk((long long)c_lo * CH, 0);
+                        if (c_lo < c_hi && !first_chunk_issued) issue_bulk((long long)c_lo * CH, 0);
                         for (int c = c_lo; c < c_hi; c++) {
                             const int buf = (c - c_lo) & 1;
                             if (c + 1 < c_hi) issue_bulk((long long)(c + 1) * CH, buf ^ 1);     // that buffer was read out before the
@@ -594,12 +618,15 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                         for (int x = 0; x < EW; x++) sp += sPart[x][lane];          // warps in order
                         __stcg(&part[seg * 32 + lane], sp);
                     }
-                    __threadfence();
                     csync();
                     if (tid == 0) {
-                        const unsigned old = atomicAdd(&A.slice_cnt[(long long)slot * A.max_units + b], 1u);
+                        // one acq_rel counter update instead of a fence by every thread on either side: release is
+                        // cumulative over the segment sums stored before the barrier, acquire orders the finisher's
+                        // reads (behind the next barrier) after the other segments' stores
+                        unsigned old;
+                        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;"
+                                     : "=r"(old) : "l"(&A.slice_cnt[(long long)slot * A.max_units + b]) : "memory");
                         sSliceLast = ((old + 1u) % (unsigned)nseg == 0u) ? 1 : 0;   // nseg is the same in every half-step of this kind
-                        __threadfence();
                     }
                     csync();
                     finisher = sSliceLast != 0;
