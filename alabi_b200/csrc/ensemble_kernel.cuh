@@ -138,6 +138,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
     __shared__ int sW[NPB][NU][P], sInside[NU][P], sPartner[NPB][NU][P];
     __shared__ double sPrior[NU][P];             // ln of the normal part of the prior at the proposal
     __shared__ int sSliceLast;                   // split units: this CTA delivered the last slice of its unit
+    __shared__ int sOut[WIDE ? P : 1];           // wide unit: proposal left the prior box (cooperative gather)
     __shared__ int sAccF[WIDE ? P : 1];          // wide unit: accept flags and stored log-probabilities of the unit,
     __shared__ double sLpOut[WIDE ? P : 1];      // handed from the proposal lanes to the cooperative row stores
 
@@ -373,7 +374,60 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                     }
                 }
 #endif
-                if (prop_lane) {
+                // (the compile-time-chunk kernel of the large ensembles keeps the per-lane gather: with the
+                // cooperative one its inner loop was scheduled 5 % slower, for a gather that is 1 % of its time)
+                if constexpr (WIDE && CHT == 0) {
+                    // Wide unit: the WHOLE CTA gathers.  Element (e, k) = coordinate k of proposal e goes to one
+                    // thread, so a walker's row is one coalesced request and the 32 x d proposals are formed in
+                    // parallel (as scattered 8-byte loads of the 32 proposal lanes the gather took ~7000 cycles
+                    // per segment: a third of a half-step in spread mode).  The arithmetic of a coordinate is the
+                    // same separately rounded sequence as below; "outside the box" is collected as a flag per
+                    // proposal (threads that find a violation store the same value).
+                    if (tid < P) sOut[tid] = 0;
+                    csync();
+                    for (int idx = tid; idx < P * D; idx += ETHREADS) {
+                        const int e = idx / D, k = idx - e * D;
+                        const int w = sW[0][0][e], partner = sPartner[0][0][e];
+                        double q = 0.0, qs = 0.0, sv = 0.0;
+                        if (w >= 0 && k < d) {
+                            sv = __ldcg(&A.coords[(long long)w * d + k]);
+                            if (step >= 0 && partner >= 0) {
+                                const double cv = __ldcg(&A.coords[(long long)partner * d + k]);
+                                q = __dsub_rn(cv, __dmul_rn(__dsub_rn(cv, sv), sZZ[0][0][e]));
+                            } else {
+                                q = sv;                                  // step < 0 or no partner: the current position
+                            }
+                            if (!((q > A.lo[k]) && (q < A.hi[k]))) sOut[e] = 1;
+                            qs = fma(q, A.t_scale[k], A.t_off[k]) * A.kp.inv_len[k];
+                        }
+                        sS[0][e][k] = sv;
+                        sQ[0][e][k] = q;
+                        sQs[0][e][k] = qs;
+                    }
+                    csync();
+                    if (prop_lane) {
+                        const int e = lane, w = sW[0][0][e], partner = sPartner[0][0][e];
+                        int inside = 1;
+                        if (w >= 0) {
+                            if (step >= 0) sLps[0][e] = __ldcg(&A.logp[w]);
+                            if (step >= 0 && partner < 0) inside = -1;  // no complementary walker: keep the state
+                            else if (sOut[e]) inside = 0;
+                            if (A.use_normal) {
+                                // scipy's norm.logpdf term by term, in dimension order (oracle/utility.py)
+                                double pr = 0.0;
+                                for (int k = 0; k < d; k++) {
+                                    if (A.pr_sd[k] > 0.0) {
+                                        const double z = __ddiv_rn(__dsub_rn(sQ[0][e][k], A.pr_mu[k]), A.pr_sd[k]);
+                                        pr = __dadd_rn(pr, __dsub_rn(__dsub_rn(-__dmul_rn(z, z) * 0.5, 0.9189385332046727),
+                                                                     A.pr_lsd[k]));
+                                    }
+                                }
+                                sPrior[0][e] = pr;
+                            }
+                        }
+                        sInside[0][e] = inside;
+                    }
+                } else if (prop_lane) {
                     const int e = lane, w = sW[pbuf][unit][e], partner = sPartner[pbuf][unit][e];
                     int inside = 1;
                     if (w >= 0) {
@@ -786,7 +840,7 @@ int launch_ens_p(ab_gp* h, EnsArgs& A, int n_half, bool one_pass_only = false) {
     }
     A.ch = ch;
     if constexpr (P == 32 && EW == 16) {
-        if ((size_t)need > budget && ch == 512) kern = ensemble_kernel<KIND, D, EW, P, 512>;
+        if ((size_t)need > budget && ch == 512 && A.ch_hint == 0) kern = ensemble_kernel<KIND, D, EW, P, 512>;
     }
     if constexpr (P == 2) {
         // dataflow schedule: resident training set, a ring was provided by the caller
