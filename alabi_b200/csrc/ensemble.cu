@@ -229,6 +229,11 @@ extern "C" int ab_ensemble_run_host(ab_gp* h, const ab_ensemble_config* cfg, dou
     for (cudaEvent_t e : evs) cudaEventDestroy(e);
     if (rc) return rc;
     if (es != cudaSuccess) { ab_set_error("ab_ensemble_run_host: %s", cudaGetErrorString(es)); return -100 - (int)es; }
+    if (reinterpret_cast<int*>(h->h_pinned + 1)[0] == 2) {
+        ab_set_error("ensemble sampler: a partner record did not arrive within the watchdog time (dataflow schedule); "
+                     "the chain of this run is invalid");
+        return -7;
+    }
     if (reinterpret_cast<int*>(h->h_pinned + 1)[0] != 0) {
         ab_set_error("Probability function returned NaN");
         return 1;
@@ -246,6 +251,11 @@ extern "C" int ab_ensemble_finish(ab_gp* h) {
         const long long* dd = reinterpret_cast<const long long*>(h->h_pinned + 16);
         fprintf(stderr, "[ensemble dbg] cycles/half-step: proposal %.0f compute %.0f accept %.0f barrier %.0f (n=%lld, ws=%d)\n",
                 (double)dd[0] / dd[4], (double)dd[1] / dd[4], (double)dd[2] / dd[4], (double)dd[3] / dd[4], dd[4], h->ens_ws);
+    }
+    if (reinterpret_cast<int*>(h->h_pinned + 1)[0] == 2) {
+        ab_set_error("ensemble sampler: a partner record did not arrive within the watchdog time (dataflow schedule); "
+                     "the chain of this run is invalid");
+        return -7;
     }
     if (reinterpret_cast<int*>(h->h_pinned + 1)[0] != 0) {
         ab_set_error("Probability function returned NaN");

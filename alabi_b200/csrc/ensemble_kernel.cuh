@@ -447,6 +447,8 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                                 const unsigned need = (unsigned)step + (split == 0 ? 1u : 2u);
                                 const uint4* line = A.ring + ((long long)((need - 1u) % AB_ENS_RING) * nw + partner) * d;
                                 bool ok;
+                                unsigned spins = 0;
+                                long long wd0 = 0;
                                 do {
                                     ok = true;
 #pragma unroll
@@ -457,6 +459,16 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                                                          : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "l"(line + k) : "memory");
                                             ok = ok && (x1 == need) && (x3 == need);
                                             cs[k] = __hiloint2double((int)x2, (int)x0);
+                                        }
+                                    }
+                                    // watchdog: a record that never arrives (it cannot, by the dependency order; this
+                                    // guards the GPU against a fault elsewhere) raises flag 2 after ~2 s, and every
+                                    // poll loop leaves as soon as it sees the flag: the run ends with an error
+                                    if (!ok && (++spins & 0x3fffu) == 0) {
+                                        if (wd0 == 0) wd0 = clock64();
+                                        if (*((volatile int*)A.nan_flag) == 2 || clock64() - wd0 > 4000000000LL) {
+                                            atomicExch(A.nan_flag, 2);
+                                            break;
                                         }
                                     }
                                 } while (!ok);
@@ -706,7 +718,7 @@ ensemble_kernel(const __grid_constant__ EnsArgs A) {
                         const int inside = sInside[unit][e];
                         if (A.use_normal) y = __dadd_rn(y, sPrior[unit][e]);
                         double lp_q = (inside == 1) ? y : -INFINITY;
-                        if (inside == 1 && isnan(y)) atomicExch(A.nan_flag, 1);
+                        if (inside == 1 && isnan(y)) atomicCAS(A.nan_flag, 0, 1);      // (keeps a watchdog flag 2)
                         if (step < 0) {
                             A.logp[w] = lp_q;
                         } else {
