@@ -281,7 +281,11 @@ class SurrogateModel(object):
             # gp.get_parameter_vector()) is used as it is.  The reference re-expands it through the
             # positions of the OPTIMISED names (alabi/core.py:1780 -> 695-704), which swaps amplitude
             # and white noise on every refit; that accident is not reproduced.
-            if not (self.ndim > 1 and len(np.atleast_1d(optimized_params)) == len(self.param_names_full)):
+            # ``reference_double_expansion = True`` (attribute, default off) reproduces it: the objective of
+            # the reference's ML search then sees amplitude and white noise swapped, exactly as its code does
+            # (pinned by tests/golden/hostlogic_golden.npz, generated from the reference's own init_gp).
+            if getattr(self, "reference_double_expansion", False) or \
+                    not (self.ndim > 1 and len(np.atleast_1d(optimized_params)) == len(self.param_names_full)):
                 full = self.expand_hyperparameter_vector(optimized_params)
         tmp_gp.set_parameter_vector(full)
         return tmp_gp

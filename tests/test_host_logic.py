@@ -518,3 +518,111 @@ def test_device_state_is_lazy_and_pickles_as_a_host_state():
         assert type(clone) is State
         np.testing.assert_array_equal(clone.coords, c.numpy())
         np.testing.assert_array_equal(clone.log_prob, l.numpy())
+
+
+def _oracle_backed_gp():
+    """Stand-in for alabi_b200.gp.GP on the CPU: the same constructor, backed by the NumPy oracle."""
+    from alabi_b200 import kernels as K
+    from oracle import gp as ogp
+
+    class OracleBackedGP(ogp.OracleGP):
+        def __init__(self, kernel=None, fit_mean=False, mean=0.0, white_noise=-12.0, fit_white_noise=False, device=None, **kw):
+            base, log_const = (kernel.k2, float(kernel.k1.log_constant)) if isinstance(kernel, K.Product) else (kernel, None)
+            super().__init__(type(base).__name__, base.ndim, np.array(base.log_M, dtype=float), log_const=log_const, mean=mean,
+                             fit_mean=fit_mean, white_noise=white_noise, fit_white_noise=fit_white_noise)
+            self.kernel = kernel
+    return OracleBackedGP
+
+
+@pytest.mark.parametrize("case", ["full_reg", "uniform_reg", "uniform_noreg", "full_noamp"])
+def test_init_gp_host_logic_matches_the_reference_code(case, tmp_path, monkeypatch):
+    """alabi's OWN logic around the GP fit, pinned against the reference's code: tests/golden/
+    make_hostlogic_golden.py ran the reference's SurrogateModel.init_gp (scalers, hyper-parameter names and
+    order, set_hyperparam_prior_bounds, the _opt_gp objective / gradient closures with uniform_scales and
+    the regulariser, L-BFGS-B from the recorded start) with george replaced by a shim on oracle.gp; here
+    alabi_b200.core.SurrogateModel runs on the same oracle GP and must reproduce names, prior box, start,
+    objective and gradient values at the recorded probe points, and the optimum."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_hostlogic_golden as mh
+    from sklearn import preprocessing
+    from alabi_b200 import core, gp_utils
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hostlogic_golden.npz"))
+    cfg = next(c for c in mh.CASES if c["name"] == case)
+    bounds, theta, y, theta_test, y_test = mh.training_set()
+    stand_in = _oracle_backed_gp()
+    monkeypatch.setattr(core, "GP", stand_in)
+    monkeypatch.setattr(gp_utils, "GP", stand_in)
+    seen = {}
+    real = core.op.minimize
+
+    def spy(fun=None, x0=None, jac=None, method=None, bounds=None, options=None, **kw):
+        seen.update(fun=fun, jac=jac, x0=np.array(x0, dtype=float), bounds=np.array(bounds, dtype=float))
+        return real(fun=fun, x0=x0, jac=jac, method=method, bounds=bounds, options=options, **kw)
+    monkeypatch.setattr(core.op, "minimize", spy)
+    sm = core.SurrogateModel(lnlike_fn=lambda t: 0.0, bounds=bounds, savedir=str(tmp_path), cache=False, verbose=False)
+    sm.theta_train, sm.y_train, sm.theta_test, sm.y_test = theta, y, theta_test, y_test
+    sm.ntrain, sm.ntest = len(theta), len(theta_test)          # (what init_samples leaves behind)
+    # uniform_scales: the reference expands an already expanded vector a second time through the positions of
+    # the OPTIMISED names, so its ML objective sees amplitude and white noise swapped (alabi/core.py:1242-1253
+    # -> 695-704).  The product does not do that by default (DESIGN.md, deliberate differences); with the
+    # switch on it must reproduce the reference's numbers exactly, which pins that the swap is the ONLY difference
+    sm.reference_double_expansion = True
+    np.random.seed(1234)
+    sm.init_gp(kernel=cfg["kernel"], fit_amp=cfg["fit_amp"], fit_mean=cfg["fit_mean"], fit_white_noise=cfg["fit_white_noise"],
+               white_noise=-8, gp_scale_rng=[-2, 2], gp_amp_rng=[-1, 1], uniform_scales=cfg["uniform_scales"],
+               theta_scaler=preprocessing.MinMaxScaler(), y_scaler=preprocessing.StandardScaler(), gp_opt_method="l-bfgs-b",
+               gp_nopt=1, hyperopt_method="ml",
+               regularize=cfg["regularize"], optimizer_kwargs={"maxiter": 60})
+    assert list(sm.param_names_full) == list(g[f"{case}__names_full"])
+    assert list(sm.param_names_optimized) == list(g[f"{case}__names_opt"])
+    np.testing.assert_allclose(sm._theta, g[f"{case}__theta_scaled"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(sm._y, g[f"{case}__y_scaled"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(np.array(sm.hp_bounds, dtype=float), g[f"{case}__hp_bounds"], rtol=1e-14)
+    np.testing.assert_allclose(sm.initial_gp_hyperparameters, g[f"{case}__initial_hp"], rtol=1e-14)
+    np.testing.assert_allclose(seen["x0"], g[f"{case}__x0"], rtol=1e-14)
+    probes = g[f"{case}__probes"]
+    np.testing.assert_allclose([seen["fun"](p) for p in probes], g[f"{case}__nll"], rtol=1e-10)
+    np.testing.assert_allclose([seen["jac"](p) for p in probes], g[f"{case}__grad"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(sm.get_hyperparameter_vector(sm.gp), g[f"{case}__hp_final"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(sm.gp.get_parameter_vector(), g[f"{case}__hp_final_full"], rtol=1e-8, atol=1e-9)
+
+
+def test_uniform_scales_default_objective_is_the_unswapped_one(tmp_path, monkeypatch):
+    """The product's default with ``uniform_scales`` (no second expansion): the ML objective at p_opt is
+    -log L of the GP whose parameters are p_opt mapped BY NAME (amplitude -> amplitude, white noise -> white
+    noise, the tied scale to every dimension) plus the regulariser of the expanded vector -- the reference's
+    formula with its amplitude / white-noise swap taken out (see the test above for the swap itself)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_hostlogic_golden as mh
+    from sklearn import preprocessing
+    from alabi_b200 import core, gp_utils
+    from oracle import gp as ogp
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hostlogic_golden.npz"))
+    bounds, theta, y, theta_test, y_test = mh.training_set()
+    stand_in = _oracle_backed_gp()
+    monkeypatch.setattr(core, "GP", stand_in)
+    monkeypatch.setattr(gp_utils, "GP", stand_in)
+    seen = {}
+    real = core.op.minimize
+    monkeypatch.setattr(core.op, "minimize", lambda fun=None, x0=None, jac=None, **kw: (seen.update(fun=fun, jac=jac), real(fun=fun, x0=x0, jac=jac, **kw))[1])
+    sm = core.SurrogateModel(lnlike_fn=lambda t: 0.0, bounds=bounds, savedir=str(tmp_path), cache=False, verbose=False)
+    sm.theta_train, sm.y_train, sm.theta_test, sm.y_test = theta, y, theta_test, y_test
+    sm.ntrain, sm.ntest = len(theta), len(theta_test)
+    np.random.seed(1234)
+    sm.init_gp(kernel="Matern52Kernel", uniform_scales=True, white_noise=-8, theta_scaler=preprocessing.MinMaxScaler(),
+               y_scaler=preprocessing.StandardScaler(), gp_opt_method="l-bfgs-b", gp_nopt=1, hyperopt_method="ml", regularize=True,
+               optimizer_kwargs={"maxiter": 60})
+    assert list(sm.param_names_optimized) == list(g["uniform_reg__names_opt"])
+    d = bounds.shape[0]
+    differs = 0
+    for p, ref_val in zip(g["uniform_reg__probes"], g["uniform_reg__nll"]):
+        m, a, w, s = p                                        # optimised order: mean, log_constant, white_noise, tied log_M
+        o = ogp.OracleGP("Matern52Kernel", d, np.full(d, s), log_const=a, mean=m, fit_mean=True, white_noise=w, fit_white_noise=True)
+        o.compute(sm._theta)
+        want = -o.log_likelihood(sm._y) + gp_utils.regularization_term(sm.expand_hyperparameter_vector(p), sm.hp_length_indices,
+                                                                       amp_0=1.0, mu_0=1.0, sigma_0=2.0)
+        assert abs(seen["fun"](p) - want) <= 1e-9 * max(1.0, abs(want))
+        differs += abs(seen["fun"](p) - ref_val) > 1e-3 * abs(ref_val)
+    assert differs >= 4                                       # and that is NOT what the reference's swapped objective gives
