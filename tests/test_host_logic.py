@@ -586,6 +586,22 @@ def test_init_gp_host_logic_matches_the_reference_code(case, tmp_path, monkeypat
     np.testing.assert_allclose([seen["jac"](p) for p in probes], g[f"{case}__grad"], rtol=1e-9, atol=1e-10)
     np.testing.assert_allclose(sm.get_hyperparameter_vector(sm.gp), g[f"{case}__hp_final"], rtol=1e-8, atol=1e-9)
     np.testing.assert_allclose(sm.gp.get_parameter_vector(), g[f"{case}__hp_final_full"], rtol=1e-8, atol=1e-9)
+    # a7 / a12 on the fitted model: surrogate_log_likelihood (scalers around predict; the variance goes through
+    # y_scaler.inverse_transform as in the reference, alabi/core.py:1502) and lnprob with the strict uniform prior
+    from functools import partial
+    from alabi_b200 import utility as ut
+    pts = g[f"{case}__query"]
+    np.testing.assert_allclose(sm.surrogate_log_likelihood(pts), g[f"{case}__sll"], rtol=1e-7, atol=1e-9)
+    mu, var = sm.surrogate_log_likelihood(pts, return_var=True)
+    np.testing.assert_allclose(mu, g[f"{case}__sll_mu"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(var, g[f"{case}__sll_var"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(sm.surrogate_log_likelihood(pts[3]), g[f"{case}__sll_one"][0], rtol=1e-7, atol=1e-9)
+    sm.like_fn_name, sm.like_fn = "surrogate", sm.surrogate_log_likelihood
+    sm.prior_fn = partial(ut.lnprior_uniform, bounds=sm.bounds)
+    got = np.array([np.ravel(sm.lnprob(p))[0] for p in pts])
+    want = g[f"{case}__lnprob"]
+    assert np.array_equal(np.isfinite(got), np.isfinite(want))
+    np.testing.assert_allclose(got[np.isfinite(want)], want[np.isfinite(want)], rtol=1e-7, atol=1e-9)
 
 
 def test_uniform_scales_default_objective_is_the_unswapped_one(tmp_path, monkeypatch):
