@@ -596,6 +596,13 @@ def test_init_gp_host_logic_matches_the_reference_code(case, tmp_path, monkeypat
     np.testing.assert_allclose(mu, g[f"{case}__sll_mu"], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(var, g[f"{case}__sll_var"], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(sm.surrogate_log_likelihood(pts[3]), g[f"{case}__sll_one"][0], rtol=1e-7, atol=1e-9)
+    # the refit after appended points (active_train -> _fit_gp with the current full hyper-vector); _y of the
+    # model is untouched, so the prior box is recomputed from the same data as in the reference
+    th2, y2 = mh.GROWN_SET(sm)
+    gp2, _ = sm._fit_gp(_theta=th2, _y=y2, hyperparameters=sm.gp.get_parameter_vector())
+    np.testing.assert_allclose(gp2.get_parameter_vector(), g[f"{case}__refit_vector"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(gp2.log_likelihood(y2), g[f"{case}__refit_loglike"][0], rtol=1e-7)
+    np.testing.assert_allclose(np.array(sm.hp_bounds, dtype=float), g[f"{case}__refit_bounds"], rtol=1e-14)
     sm.like_fn_name, sm.like_fn = "surrogate", sm.surrogate_log_likelihood
     sm.prior_fn = partial(ut.lnprior_uniform, bounds=sm.bounds)
     got = np.array([np.ravel(sm.lnprob(p))[0] for p in pts])
