@@ -649,3 +649,25 @@ def test_uniform_scales_default_objective_is_the_unswapped_one(tmp_path, monkeyp
         assert abs(seen["fun"](p) - want) <= 1e-9 * max(1.0, abs(want))
         differs += abs(seen["fun"](p) - ref_val) > 1e-3 * abs(ref_val)
     assert differs >= 4                                       # and that is NOT what the reference's swapped objective gives
+
+
+def test_minimize_objective_matches_the_reference_code():
+    """ut.minimize_objective against the reference's function run on the same objective, gradient, box and
+    starting points (tests/golden/make_hostlogic_golden.py): L-BFGS-B with and without a gradient (option
+    names translated), Nelder-Mead, and the case in which every restart ends on the boundary and the strict
+    prior rejects it (nan, nan)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_hostlogic_golden as mh
+    from alabi_b200 import utility as ut
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hostlogic_golden.npz"))
+    for nm, kw in mh.MINOBJ_CASES.items():
+        fn, grad, b, starts = mh.MINOBJ_PROBLEM(kw["problem"])
+        th, ob = ut.minimize_objective(fn, bounds=b, nopt=kw["nopt"], method=kw["method"], ps=lambda nsample: starts[:nsample],
+                                       options=kw.get("options"), grad_obj_fn=grad if kw.get("grad") else None)
+        want_t, want_o = g[f"minobj__{nm}__theta"], g[f"minobj__{nm}__obj"]
+        if not np.all(np.isfinite(want_o)):
+            assert not np.all(np.isfinite(np.atleast_1d(ob))) and not np.all(np.isfinite(np.atleast_1d(th))), nm
+            continue
+        np.testing.assert_allclose(np.atleast_1d(th), want_t, rtol=1e-9, atol=1e-10, err_msg=nm)
+        np.testing.assert_allclose(np.atleast_1d(ob), want_o, rtol=1e-10, atol=1e-12, err_msg=nm)
