@@ -671,3 +671,50 @@ def test_minimize_objective_matches_the_reference_code():
             continue
         np.testing.assert_allclose(np.atleast_1d(th), want_t, rtol=1e-9, atol=1e-10, err_msg=nm)
         np.testing.assert_allclose(np.atleast_1d(ob), want_o, rtol=1e-10, atol=1e-12, err_msg=nm)
+
+
+def test_cv_worker_matches_the_reference_code():
+    """The k-fold CV scores of hyper-parameter candidates (f1) against the reference's own worker
+    (alabi/gp_utils.py:511-637, run by tests/golden/make_hostlogic_golden.py on the oracle-backed george shim):
+    same shuffled KFold splits from NumPy's global stream, same per-fold MSE / MAE / -R^2 / weighted MSE on
+    unscaled targets, inf for the candidate with a NaN; and weighted_mse_by_probability for every weighting."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_hostlogic_golden as mh
+    from sklearn import preprocessing
+    from alabi_b200 import gp_utils, kernels as K
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hostlogic_golden.npz"))
+    bounds, theta, y, _tt, _yt = mh.training_set()
+    ts, ys = preprocessing.MinMaxScaler().fit(bounds.T), preprocessing.StandardScaler()
+    _theta, _y = ts.transform(theta), ys.fit_transform(y.reshape(-1, 1)).flatten()
+    gp0 = _oracle_backed_gp()(kernel=K.Matern32Kernel(metric=np.ones(3), ndim=3) * np.var(_y), fit_mean=True, mean=np.median(_y),
+                              white_noise=-8.0, fit_white_noise=True)
+    gp0.compute(_theta)
+    cands = g["cv__cands"]
+    for scoring in ("mse", "mae", "r2", "weighted_mse"):
+        np.random.seed(77)
+        got = gp_utils._evaluate_candidates(gp0, _theta, _y, ys, cands, 4, scoring, "exponential", 1.5, batched=False)
+        want = g[f"cv__{scoring}"]
+        assert np.array_equal(np.isfinite(got), np.isfinite(want)), scoring
+        np.testing.assert_allclose(got[np.isfinite(want)], want[np.isfinite(want)], rtol=1e-8, err_msg=scoring)
+    yv, yp = g["wmse__inputs"]
+    vals = [gp_utils.weighted_mse_by_probability(yv, yp, weight_method=m, temperature=t)
+            for m in ("exponential", "linear", "softmax", "rank") for t in (1.0, 2.5)]
+    np.testing.assert_allclose(vals, g["wmse__values"], rtol=1e-13)
+
+
+def test_cv_stage_candidate_clouds_match_the_reference_code():
+    """Stage-2 / stage-3 candidate clouds of the CV search (alabi/gp_utils.py:1234-1370) under the same NumPy
+    seed: distinct scales (independent perturbations), the reference's kernel-local index quirk with tied
+    entries, and the no-GP fallback (entries 2.. treated as scales)."""
+    from alabi_b200 import gp_utils, kernels as K
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hostlogic_golden.npz"))
+    gp0 = _oracle_backed_gp()(kernel=K.Matern32Kernel(metric=np.ones(3), ndim=3) * 2.0, fit_mean=True, mean=0.0, white_noise=-8.0,
+                              fit_white_noise=True)
+    for nm, with_gp in (("distinct", True), ("tied_kernel_local", True), ("tied_no_gp", False)):
+        best = g[f"stage__{nm}__best"]
+        np.random.seed(5)
+        s2 = gp_utils._generate_stage2_candidates(best, 7, 0.5, gp=gp0 if with_gp else None)
+        s3 = gp_utils._generate_stage3_candidates(best, 5, 0.2, gp=gp0 if with_gp else None)
+        np.testing.assert_allclose(s2, g[f"stage2__{nm}"], rtol=1e-14, atol=1e-15, err_msg=nm)
+        np.testing.assert_allclose(s3, g[f"stage3__{nm}"], rtol=1e-14, atol=1e-15, err_msg=nm)
