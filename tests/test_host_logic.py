@@ -596,6 +596,24 @@ def test_init_gp_host_logic_matches_the_reference_code(case, tmp_path, monkeypat
     np.testing.assert_allclose(mu, g[f"{case}__sll_mu"], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(var, g[f"{case}__sll_var"], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(sm.surrogate_log_likelihood(pts[3]), g[f"{case}__sll_one"][0], rtol=1e-7, atol=1e-9)
+    # the cached likelihood (variance scaled by y_scaler.scale_^2) and eval_gp_at_iteration with a history
+    if not cfg["uniform_scales"]:
+        c0 = sm.create_cached_surrogate_likelihood(iter=-1, return_var=False)
+        c1 = sm.create_cached_surrogate_likelihood(iter=-1, return_var=True)
+        np.testing.assert_allclose(c0(pts), g[f"{case}__cached"], rtol=1e-7, atol=1e-9)
+        cm, cv = c1(pts)
+        np.testing.assert_allclose(cm, g[f"{case}__cached_mu"], rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(cv, g[f"{case}__cached_var"], rtol=1e-6, atol=1e-12)
+        hp_now = np.array(sm.gp.get_parameter_vector(), dtype=float)
+        sm.ninit_train = len(sm._theta) - 3
+        sm.training_results["iteration"] = [1, 2, 3]
+        sm.training_results["gp_hyperparameters"] = list(g[f"{case}__hist"])
+        for it in (0, 1, 2, -1):
+            np.testing.assert_allclose(sm.surrogate_log_likelihood(pts, iter=it), g[f"{case}__sll_iter{it}"], rtol=1e-7, atol=1e-9,
+                                       err_msg=f"iter {it}")
+        sm.training_results["iteration"], sm.training_results["gp_hyperparameters"] = [], []
+        sm.set_hyperparameter_vector(sm.gp, hp_now)
+        sm.gp.compute(sm._theta)
     # the refit after appended points (active_train -> _fit_gp with the current full hyper-vector); _y of the
     # model is untouched, so the prior box is recomputed from the same data as in the reference
     th2, y2 = mh.GROWN_SET(sm)
