@@ -25,6 +25,13 @@ Parity status
 * ``oracle.nested`` replays the device's constrained random walks (dynesty's
   ``rwalk`` replacement step; dynesty unpinned and not installed): **parity
   unpinned** against dynesty, draw layout restated from include/alabi_b200.h.
+* The reference's OWN code around the GP is pinned through this oracle: ``tests/golden/
+  make_hostlogic_golden.py`` runs the reference's ``SurrogateModel.init_gp`` / ``_opt_gp`` / ``_fit_gp`` /
+  ``surrogate_log_likelihood`` / ``lnprob`` / cached likelihood / ``eval_gp_at_iteration``, its k-fold CV
+  worker and candidate clouds and ``ut.minimize_objective`` with ``george`` replaced by a shim on
+  ``oracle.gp``; ``tests/test_host_logic.py`` makes ``alabi_b200.core`` reproduce those numbers on the same
+  oracle GP.  That pins alabi's logic GIVEN the george semantics restated here; the semantics themselves
+  stay unpinned as said above.
 * The MATHEMATICS of the benchmarked configurations c1-c4 (kernel matrix,
   Cholesky, alpha, log-likelihood, mean, variance) is additionally pinned by
   extended-precision references (``tests/golden/make_extended.py`` ->
