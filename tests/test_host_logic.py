@@ -531,6 +531,11 @@ def _oracle_backed_gp():
             super().__init__(type(base).__name__, base.ndim, np.array(base.log_M, dtype=float), log_const=log_const, mean=mean,
                              fit_mean=fit_mean, white_noise=white_noise, fit_white_noise=fit_white_noise)
             self.kernel = kernel
+
+        def predict_grad(self, y, t):                        # the product's GP returns (mu, var, d mu, d var)
+            mu, var = self.predict(y, t, return_var=True)
+            dmu, dvar = super().predict_grad(y, t)
+            return mu, var, dmu, dvar
     return OracleBackedGP
 
 
@@ -596,6 +601,21 @@ def test_init_gp_host_logic_matches_the_reference_code(case, tmp_path, monkeypat
     np.testing.assert_allclose(mu, g[f"{case}__sll_mu"], rtol=1e-7, atol=1e-9)
     np.testing.assert_allclose(var, g[f"{case}__sll_var"], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(sm.surrogate_log_likelihood(pts[3]), g[f"{case}__sll_one"][0], rtol=1e-7, atol=1e-9)
+    # a8-a11 through the GP: utilities and the acquisition gradients handed to scipy.  The reference differences
+    # the kernel (h = 1e-6) and forms a dense K^-1 per call; the product takes analytic derivatives from
+    # predict_grad -- equal up to the finite-difference error
+    if not cfg["uniform_scales"]:
+        gpts = g[f"{case}__grad_pts"]
+        sm.gp.predict(sm._y, gpts[:1], return_var=True)
+        np.testing.assert_allclose([ut.grad_gp_mean_prediction(p, sm.gp) for p in gpts], g[f"{case}__grad_mean"], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose([ut.grad_gp_var_prediction(p, sm.gp) for p in gpts], g[f"{case}__grad_var"], rtol=2e-4, atol=1e-6)
+        np.testing.assert_allclose([ut.grad_bape_utility(p, sm.gp, sm._bounds) for p in gpts], g[f"{case}__grad_bape"], rtol=2e-4, atol=1e-5)
+        np.testing.assert_allclose([ut.grad_agp_utility(p, sm.gp, sm._bounds) for p in gpts], g[f"{case}__grad_agp"], rtol=2e-4, atol=1e-5)
+        pg = lambda t: sm.gp.predict(sm._y, np.atleast_2d(t), return_var=True)
+        np.testing.assert_allclose([np.ravel(ut.bape_utility(p, pg, sm._bounds))[0] for p in gpts], g[f"{case}__bape"], rtol=1e-9)
+        np.testing.assert_allclose([np.ravel(ut.agp_utility(p, pg, sm._bounds))[0] for p in gpts], g[f"{case}__agp"], rtol=1e-9)
+        np.testing.assert_allclose([np.ravel(ut.jones_utility(p, pg, sm._bounds, float(np.max(sm._y))))[0] for p in gpts],
+                                   g[f"{case}__jones"], rtol=1e-8, atol=1e-300)
     # the cached likelihood (variance scaled by y_scaler.scale_^2) and eval_gp_at_iteration with a history
     if not cfg["uniform_scales"]:
         c0 = sm.create_cached_surrogate_likelihood(iter=-1, return_var=False)
