@@ -756,3 +756,42 @@ def test_cv_stage_candidate_clouds_match_the_reference_code():
         s3 = gp_utils._generate_stage3_candidates(best, 5, 0.2, gp=gp0 if with_gp else None)
         np.testing.assert_allclose(s2, g[f"stage2__{nm}"], rtol=1e-14, atol=1e-15, err_msg=nm)
         np.testing.assert_allclose(s3, g[f"stage3__{nm}"], rtol=1e-14, atol=1e-15, err_msg=nm)
+
+
+def test_active_train_loop_matches_the_reference_code(tmp_path, monkeypatch):
+    """The active-learning loop of the API shell against the reference's active_train (alabi/core.py:1670-1865)
+    with find_next_point replaced by the same fixed proposals on both sides: per-point refit, re-optimisation
+    every gp_opt_freq iterations, the y scaler refitted on the grown set, and the training_results bookkeeping
+    (iterations, hyper-vectors, training / test MSE and their scaled forms)."""
+    import sys
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_hostlogic_golden as mh
+    from sklearn import preprocessing
+    from alabi_b200 import core, gp_utils
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hostlogic_golden.npz"))
+    cfg = next(c for c in mh.CASES if c["name"] == "full_reg")
+    bounds, theta, y, theta_test, y_test = mh.training_set()
+    stand_in = _oracle_backed_gp()
+    monkeypatch.setattr(core, "GP", stand_in)
+    monkeypatch.setattr(gp_utils, "GP", stand_in)
+    sm = core.SurrogateModel(lnlike_fn=lambda t: 0.0, bounds=bounds, savedir=str(tmp_path), cache=False, verbose=False)
+    sm.theta_train, sm.y_train, sm.theta_test, sm.y_test = theta, y, theta_test, y_test
+    sm.ntrain, sm.ntest = len(theta), len(theta_test)
+    np.random.seed(1234)
+    sm.init_gp(kernel=cfg["kernel"], fit_amp=True, fit_mean=True, fit_white_noise=True, white_noise=-8, gp_scale_rng=[-2, 2],
+               gp_amp_rng=[-1, 1], uniform_scales=False, theta_scaler=preprocessing.MinMaxScaler(), y_scaler=preprocessing.StandardScaler(),
+               gp_opt_method="l-bfgs-b", gp_nopt=1, hyperopt_method="ml", regularize=True, optimizer_kwargs={"maxiter": 60})
+    sm.ninit_train = len(sm._theta)
+    sm.incremental_fit = False                               # the reference refits from scratch after every point
+    sm.find_next_point = types.MethodType(mh.FAKE_FIND_NEXT_POINT, sm)
+    sm.active_train(niter=4, algorithm="bape", gp_opt_freq=2, save_progress=False, show_progress=False)
+    tr = sm.training_results
+    assert list(tr["iteration"]) == list(g["active__iteration"])
+    assert list(tr["gp_hyperparameter_opt_iteration"]) == list(g["active__opt_iteration"])
+    np.testing.assert_allclose(np.array(tr["gp_hyperparameters"], dtype=float), g["active__hyper"], rtol=1e-7, atol=1e-8)
+    for key in ("training_mse", "test_mse", "training_scaled_mse", "test_scaled_mse"):
+        np.testing.assert_allclose(np.array(tr[key], dtype=float), g[f"active__{key}"], rtol=1e-5, err_msg=key)
+    np.testing.assert_allclose(sm._theta, g["active__theta_scaled"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(sm._y, g["active__y_scaled"], rtol=1e-13, atol=1e-15)
+    assert [sm.ntrain, sm.nactive] == list(g["active__counts"])
