@@ -795,3 +795,13 @@ def test_active_train_loop_matches_the_reference_code(tmp_path, monkeypatch):
     np.testing.assert_allclose(sm._theta, g["active__theta_scaled"], rtol=0, atol=1e-15)
     np.testing.assert_allclose(sm._y, g["active__y_scaled"], rtol=1e-13, atol=1e-15)
     assert [sm.ntrain, sm.nactive] == list(g["active__counts"])
+
+
+def test_prior_sampler_normal_matches_the_reference_code():
+    """ut.prior_sampler_normal (alabi/utility.py:202-215) on NumPy's global stream: the same draws as the
+    reference's function under the same seed (truncated normals where a mean is given, uniform elsewhere)."""
+    from alabi_b200 import utility as ut
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hostlogic_golden.npz"))
+    np.random.seed(31)
+    got = ut.prior_sampler_normal([(0.5, 0.2), (None, None), (-0.3, 1.5)], np.array([(0.0, 1.0), (-2.0, 2.0), (-1.0, 1.0)]), nsample=7)
+    np.testing.assert_allclose(got, g["prior_sampler_normal"], rtol=1e-14, atol=1e-15)
