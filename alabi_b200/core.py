@@ -775,6 +775,16 @@ class SurrogateModel(object):
             self.save()
 
     # -- samplers ------------------------------------------------------------------------------------
+    def _lnlike_fn(self, _theta):
+        """``lnlike_fn`` at a SCALED theta, returned in scaled y (alabi/core.py:407-422)."""
+        theta = self.theta_scaler.inverse_transform(_theta).flatten()
+        y = np.asarray(self.true_log_likelihood(theta)).reshape(-1, 1)
+        return self.y_scaler.transform(y).flatten()
+
+    def find_map(self, theta0=None, prior_fn=None, method="nelder-mead", nRestarts=15, options=None):
+        """Not implemented in the reference either (alabi/core.py:2103-2105)."""
+        raise NotImplementedError("Not implemented.")
+
     def lnprob(self, theta):
         """ln P = like_fn(theta) + prior_fn(theta) (alabi/core.py:2073-2100)."""
         if getattr(self, "like_fn_name", "surrogate") == "surrogate" and not hasattr(self, "gp"):
