@@ -259,6 +259,23 @@ def _evaluate_candidates(gp, theta, y, y_scaler, cands, k_folds, scoring, wmetho
     return scores
 
 
+def _evaluate_candidate_worker(args):
+    """One candidate in the reference's worker format (alabi/gp_utils.py:511-637):
+    ``(cand_idx, hyperparams, gp, _theta, _y, y_scaler, k_folds, scoring, weighted_mse_method, weighted_mse_factor)``
+    -> ``(cand_idx, fold_scores, "success" | message)``; the batched path above is what the search itself uses."""
+    cand_idx, hp, gp, _theta, _y, y_scaler, k_folds, scoring, wmethod, wfactor = args
+    try:
+        hp = np.asarray(hp, dtype=np.float64)
+        if not np.all(np.isfinite(hp)):
+            return (cand_idx, None, "Invalid hyperparameters (NaN/Inf)")
+        scores = list(_evaluate_candidates(gp, _theta, _y, y_scaler, [hp], k_folds, scoring, wmethod, wfactor, batched=False)[0])
+        if all(np.isinf(scores)):
+            return (cand_idx, scores, "All folds failed.")
+        return (cand_idx, scores, "success")
+    except Exception as e:  # noqa: BLE001 - the reference returns the message
+        return (cand_idx, None, str(e))
+
+
 def _mean_scores(scores):
     out = np.full(len(scores), np.inf)
     for i, row in enumerate(scores):

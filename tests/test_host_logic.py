@@ -735,6 +735,17 @@ def test_cv_worker_matches_the_reference_code():
         want = g[f"cv__{scoring}"]
         assert np.array_equal(np.isfinite(got), np.isfinite(want)), scoring
         np.testing.assert_allclose(got[np.isfinite(want)], want[np.isfinite(want)], rtol=1e-8, err_msg=scoring)
+    # the reference's one-candidate worker format
+    np.random.seed(77)
+    for ci, hp in enumerate(cands):
+        idx, fs, msg = gp_utils._evaluate_candidate_worker((ci, hp, gp0, _theta, _y, ys, 4, "weighted_mse", "exponential", 1.5))
+        want = g["cv__weighted_mse"][ci]
+        assert idx == ci
+        if not np.all(np.isfinite(hp)):
+            assert fs is None and "Invalid" in msg
+        else:
+            assert msg == "success"
+            np.testing.assert_allclose(fs, want, rtol=1e-8)
     yv, yp = g["wmse__inputs"]
     vals = [gp_utils.weighted_mse_by_probability(yv, yp, weight_method=m, temperature=t)
             for m in ("exponential", "linear", "softmax", "rank") for t in (1.0, 2.5)]
