@@ -816,3 +816,20 @@ def test_prior_sampler_normal_matches_the_reference_code():
     np.random.seed(31)
     got = ut.prior_sampler_normal([(0.5, 0.2), (None, None), (-0.3, 1.5)], np.array([(0.0, 1.0), (-2.0, 2.0), (-1.0, 1.0)]), nsample=7)
     np.testing.assert_allclose(got, g["prior_sampler_normal"], rtol=1e-14, atol=1e-15)
+
+
+def test_text_reports_match_the_reference_code(tmp_path):
+    """cache_utils.write_report_gp / _emcee / _dynesty (alabi/cache_utils.py:71-193): the report of a stand-in
+    model must equal, byte for byte, what the reference's writers produced for the same object."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_hostlogic_golden as mh
+    from alabi_b200 import cache_utils as cu
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hostlogic_golden.npz"))
+    rep = mh.REPORT_MODEL()
+    f = str(tmp_path / "model")
+    cu.write_report_gp(rep, f)
+    cu.write_report_emcee(rep, f)
+    cu.write_report_dynesty(rep, f)
+    got, want = open(f + ".txt").read(), str(g["report_text"])
+    assert got == want, "\n".join(f"{a!r}\n{b!r}" for a, b in zip(got.splitlines(), want.splitlines()) if a != b)
