@@ -806,6 +806,13 @@ def test_active_train_loop_matches_the_reference_code(tmp_path, monkeypatch):
     np.testing.assert_allclose(sm._theta, g["active__theta_scaled"], rtol=0, atol=1e-15)
     np.testing.assert_allclose(sm._y, g["active__y_scaled"], rtol=1e-13, atol=1e-15)
     assert [sm.ntrain, sm.nactive] == list(g["active__counts"])
+    # the attribute surface: everything the reference's object carries after __init__ and after init_gp + active_train
+    # exists on the product's object too (MPI state aside), and training_results has the same keys
+    have = set(vars(sm).keys())
+    assert set(g["attrs__trained"]) - have <= {"mpi_is_active"}, sorted(set(g["attrs__trained"]) - have)
+    fresh = core.SurrogateModel(lnlike_fn=lambda t: 0.0, bounds=bounds, savedir=str(tmp_path), cache=False, verbose=False)
+    assert set(g["attrs__init"]) - set(vars(fresh).keys()) <= {"mpi_is_active"}
+    assert sorted(tr.keys()) == list(g["attrs__training_results"])
 
 
 def test_prior_sampler_normal_matches_the_reference_code():
